@@ -1,0 +1,509 @@
+// engine.cu -- C ABI of libbmcts.so: engine handle, device buffers, launches.
+//
+// One engine = one CUDA stream on one GPU with its own grow-only device
+// buffers.  Batch calls with BMCTS_MEM_HOST pointers stage through the engine's
+// device buffers (cudaMemcpyAsync on the engine stream, one copy per array) and
+// return when the results are in the caller's memory; calls with
+// BMCTS_MEM_DEVICE pointers only enqueue the kernel.  There is no CPU
+// fallback: without a CUDA device bmcts_create fails with BMCTS_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bmcts_c.h"
+#include "rollout_kernel.cuh"
+
+namespace {
+
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct bmcts_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  bool timed = false;
+  bmcts_config cfg;
+  bmcts_scenario scn;
+  bool has_scenario = false;
+  bmcts_config* d_cfg = nullptr;
+  bmcts_scenario* d_scn = nullptr;
+  float* d_dt_table = nullptr;
+  bool use_dt_table = false;
+  uint64_t launches = 0;
+  std::string err;
+  int max_smem_optin = 0;
+  // staging buffers for host-pointer calls
+  DevBuf b_pose, b_alive, b_hyp, b_depth, b_action, b_draw;
+  DevBuf b_next_pose, b_next_alive, b_reward, b_cost, b_flags, b_last_action;
+  DevBuf b_result, b_ret_agents, b_final_pose, b_prob, b_lik_action;
+};
+
+namespace {
+
+int fail(bmcts_engine* e, int st, const std::string& msg) {
+  if (e) e->err = msg;
+  return st;
+}
+
+int cuda_fail(bmcts_engine* e, cudaError_t ce, const char* what) {
+  return fail(e, BMCTS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+}
+
+#define CU(call)                                       \
+  do {                                                 \
+    cudaError_t ce_ = (call);                          \
+    if (ce_ != cudaSuccess) return cuda_fail(e, ce_, #call); \
+  } while (0)
+
+int ensure(bmcts_engine* e, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return BMCTS_OK;
+  if (b.ptr) CU(cudaFree(b.ptr));
+  b.ptr = nullptr;
+  b.cap = 0;
+  size_t cap = bytes + bytes / 4 + 256;
+  CU(cudaMalloc(&b.ptr, cap));
+  b.cap = cap;
+  return BMCTS_OK;
+}
+
+void free_buf(DevBuf& b) {
+  if (b.ptr) cudaFree(b.ptr);
+  b.ptr = nullptr;
+  b.cap = 0;
+}
+
+int upload_dt_table(bmcts_engine* e) {
+  // MctsStateBase::calculate_prediction_time_span (mcts_state_base.hpp:238-241)
+  e->use_dt_table = e->cfg.prediction_alpha != 0.0f;
+  if (!e->use_dt_table) return BMCTS_OK;
+  std::vector<float> t(BMCTS_MAX_DEPTH);
+  for (int d = 0; d < BMCTS_MAX_DEPTH; ++d)
+    t[d] = (float)((double)e->cfg.prediction_k * std::pow((double)d, (double)e->cfg.prediction_alpha));
+  CU(cudaMemcpyAsync(e->d_dt_table, t.data(), sizeof(float) * BMCTS_MAX_DEPTH,
+                     cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return BMCTS_OK;
+}
+
+template <bool COOP>
+int launch_rollout(bmcts_engine* e, const bmcts::KernelArgs& a) {
+  const size_t smem = bmcts::rollout_smem_bytes(a.A, a.C);
+  if ((int)smem > e->max_smem_optin)
+    return fail(e, BMCTS_ERR_UNSUPPORTED, "scenario needs more shared memory than the SM offers");
+  CU(cudaFuncSetAttribute(bmcts::rollout_kernel<COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)smem));
+  const int blocks = (a.n + bmcts::kLanes - 1) / bmcts::kLanes;
+  const int threads = a.A * bmcts::kLanes;
+  bmcts::rollout_kernel<COOP><<<blocks, threads, smem, e->stream>>>(a);
+  CU(cudaGetLastError());
+  e->launches++;
+  return BMCTS_OK;
+}
+
+int launch(bmcts_engine* e, const bmcts::KernelArgs& a) {
+  if (a.n <= 0) return BMCTS_OK;
+  CU(cudaEventRecord(e->ev_start, e->stream));
+  int st = (e->cfg.state_kind == BMCTS_STATE_COOPERATIVE) ? launch_rollout<true>(e, a)
+                                                          : launch_rollout<false>(e, a);
+  if (st) return st;
+  CU(cudaEventRecord(e->ev_stop, e->stream));
+  e->timed = true;
+  return BMCTS_OK;
+}
+
+void base_args(bmcts_engine* e, bmcts::KernelArgs& a, int n, uint64_t seed, uint32_t stream) {
+  std::memset(&a, 0, sizeof(a));
+  a.scn = e->d_scn;
+  a.cfg = e->d_cfg;
+  a.dt_table = e->use_dt_table ? e->d_dt_table : nullptr;
+  a.n = n;
+  a.A = e->scn.n_agents;
+  a.C = e->scn.n_corridors;
+  a.key0 = (uint32_t)seed;
+  a.key1 = (uint32_t)(seed >> 32) ^ stream;
+}
+
+// stage one host array into a device buffer
+int h2d(bmcts_engine* e, DevBuf& b, const void* src, size_t bytes, const void** dev) {
+  *dev = nullptr;
+  if (!src) return BMCTS_OK;
+  int st = ensure(e, b, bytes);
+  if (st) return st;
+  CU(cudaMemcpyAsync(b.ptr, src, bytes, cudaMemcpyHostToDevice, e->stream));
+  *dev = b.ptr;
+  return BMCTS_OK;
+}
+
+int out_buf(bmcts_engine* e, DevBuf& b, const void* host, size_t bytes, void** dev) {
+  *dev = nullptr;
+  if (!host) return BMCTS_OK;
+  int st = ensure(e, b, bytes);
+  if (st) return st;
+  *dev = b.ptr;
+  return BMCTS_OK;
+}
+
+int d2h(bmcts_engine* e, void* dst, const void* dev, size_t bytes) {
+  if (!dst || !dev) return BMCTS_OK;
+  CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+  return BMCTS_OK;
+}
+
+int check_ready(bmcts_engine* e) {
+  if (!e) return BMCTS_ERR_INVALID_ARG;
+  if (!e->has_scenario) return fail(e, BMCTS_ERR_NO_SCENARIO, "bmcts_set_scenario was not called");
+  CU(cudaSetDevice(e->device));
+  return BMCTS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bmcts_config_validate(const bmcts_config* c);
+
+int bmcts_create(int device, const bmcts_config* cfg, bmcts_engine** out) {
+  if (!out) return BMCTS_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) return BMCTS_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return BMCTS_ERR_INVALID_ARG;
+  bmcts_config c;
+  if (cfg)
+    c = *cfg;
+  else
+    bmcts_config_default(&c);
+  if (bmcts_config_validate(&c) != BMCTS_OK) return BMCTS_ERR_INVALID_ARG;
+  bmcts_engine* e = new bmcts_engine();
+  e->device = device;
+  e->cfg = c;
+  auto bail = [&](cudaError_t err) {
+    (void)err;
+    bmcts_destroy(e);
+    return BMCTS_ERR_CUDA;
+  };
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail(ce);
+  if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail(ce);
+  if ((ce = cudaEventCreate(&e->ev_start)) != cudaSuccess) return bail(ce);
+  if ((ce = cudaEventCreate(&e->ev_stop)) != cudaSuccess) return bail(ce);
+  if ((ce = cudaMalloc(&e->d_cfg, sizeof(bmcts_config))) != cudaSuccess) return bail(ce);
+  if ((ce = cudaMalloc(&e->d_scn, sizeof(bmcts_scenario))) != cudaSuccess) return bail(ce);
+  if ((ce = cudaMalloc(&e->d_dt_table, sizeof(float) * BMCTS_MAX_DEPTH)) != cudaSuccess)
+    return bail(ce);
+  cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if ((ce = cudaMemcpy(e->d_cfg, &e->cfg, sizeof(bmcts_config), cudaMemcpyHostToDevice)) !=
+      cudaSuccess)
+    return bail(ce);
+  if (upload_dt_table(e) != BMCTS_OK) {
+    bmcts_destroy(e);
+    return BMCTS_ERR_CUDA;
+  }
+  *out = e;
+  return BMCTS_OK;
+}
+
+void bmcts_destroy(bmcts_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  DevBuf* bufs[] = {&e->b_pose,      &e->b_alive,      &e->b_hyp,        &e->b_depth,
+                    &e->b_action,    &e->b_draw,       &e->b_next_pose,  &e->b_next_alive,
+                    &e->b_reward,    &e->b_cost,       &e->b_flags,      &e->b_last_action,
+                    &e->b_result,    &e->b_ret_agents, &e->b_final_pose, &e->b_prob,
+                    &e->b_lik_action};
+  for (DevBuf* b : bufs) free_buf(*b);
+  if (e->d_cfg) cudaFree(e->d_cfg);
+  if (e->d_scn) cudaFree(e->d_scn);
+  if (e->d_dt_table) cudaFree(e->d_dt_table);
+  if (e->ev_start) cudaEventDestroy(e->ev_start);
+  if (e->ev_stop) cudaEventDestroy(e->ev_stop);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int bmcts_set_config(bmcts_engine* e, const bmcts_config* cfg) {
+  if (!e || !cfg) return BMCTS_ERR_INVALID_ARG;
+  if (bmcts_config_validate(cfg) != BMCTS_OK) return fail(e, BMCTS_ERR_INVALID_ARG, "bad config");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  e->cfg = *cfg;
+  CU(cudaMemcpyAsync(e->d_cfg, &e->cfg, sizeof(bmcts_config), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return upload_dt_table(e);
+}
+
+int bmcts_set_scenario(bmcts_engine* e, const bmcts_scenario* scn) {
+  if (!e || !scn) return BMCTS_ERR_INVALID_ARG;
+  if (!scn->finalized)
+    return fail(e, BMCTS_ERR_INVALID_ARG, "scenario not finalized (bmcts_scenario_finalize)");
+  if (e->cfg.state_kind != BMCTS_STATE_COOPERATIVE && scn->n_agents > 1 && scn->n_hypotheses < 1)
+    return fail(e, BMCTS_ERR_INVALID_ARG, "hypothesis states need at least one hypothesis");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  e->scn = *scn;
+  CU(cudaMemcpyAsync(e->d_scn, &e->scn, sizeof(bmcts_scenario), cudaMemcpyHostToDevice,
+                     e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->has_scenario = true;
+  return BMCTS_OK;
+}
+
+int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts_rollout_out* out) {
+  int st = check_ready(e);
+  if (st) return st;
+  if (!in || !out || !in->pose || !in->alive || !out->result || in->n_leaves < 0)
+    return fail(e, BMCTS_ERR_INVALID_ARG, "rollout_batch: null argument");
+  const int n = in->n_leaves, A = e->scn.n_agents;
+  if (n == 0) return BMCTS_OK;
+  if (e->cfg.state_kind != BMCTS_STATE_COOPERATIVE && A > 1 && !in->hyp_id)
+    return fail(e, BMCTS_ERR_INVALID_ARG, "rollout_batch: hyp_id required");
+  bmcts::KernelArgs a;
+  base_args(e, a, n, in->seed, in->stream);
+  a.do_rollout = 1;
+  a.first_rollout_id = in->first_rollout_id;
+  if (e->cfg.max_rollout_steps <= 0)
+    return fail(e, BMCTS_ERR_INVALID_ARG, "rollout_batch: max_rollout_steps must be > 0");
+  if (in->memory == BMCTS_MEM_DEVICE) {
+    a.pose = (const float4*)in->pose;
+    a.alive = in->alive;
+    a.hyp = in->hyp_id;
+    a.depth = in->depth;
+    a.result = out->result;
+    a.ret_agents = out->ret_agents;
+    a.final_pose = (float4*)out->final_pose;
+    return launch(e, a);
+  }
+  const void* d;
+  void* o;
+  if ((st = h2d(e, e->b_pose, in->pose, sizeof(float) * 4 * (size_t)n * A, &d))) return st;
+  a.pose = (const float4*)d;
+  if ((st = h2d(e, e->b_alive, in->alive, sizeof(uint32_t) * (size_t)n, &d))) return st;
+  a.alive = (const uint32_t*)d;
+  if ((st = h2d(e, e->b_hyp, in->hyp_id, (size_t)n * A, &d))) return st;
+  a.hyp = (const uint8_t*)d;
+  if ((st = h2d(e, e->b_depth, in->depth, sizeof(uint16_t) * (size_t)n, &d))) return st;
+  a.depth = (const uint16_t*)d;
+  if ((st = out_buf(e, e->b_result, out->result, sizeof(bmcts_rollout_result) * (size_t)n, &o)))
+    return st;
+  a.result = (bmcts_rollout_result*)o;
+  if ((st = out_buf(e, e->b_ret_agents, out->ret_agents, sizeof(float) * (size_t)n * A, &o)))
+    return st;
+  a.ret_agents = (float*)o;
+  if ((st = out_buf(e, e->b_final_pose, out->final_pose, sizeof(float) * 4 * (size_t)n * A, &o)))
+    return st;
+  a.final_pose = (float4*)o;
+  if ((st = launch(e, a))) return st;
+  if ((st = d2h(e, out->result, a.result, sizeof(bmcts_rollout_result) * (size_t)n))) return st;
+  if ((st = d2h(e, out->ret_agents, a.ret_agents, sizeof(float) * (size_t)n * A))) return st;
+  if ((st = d2h(e, out->final_pose, a.final_pose, sizeof(float) * 4 * (size_t)n * A))) return st;
+  CU(cudaStreamSynchronize(e->stream));
+  return BMCTS_OK;
+}
+
+static int step_common(bmcts_engine* e, const bmcts_step_in* in, const bmcts_step_out* so,
+                       const bmcts_rollout_out* ro, uint64_t first_rollout_id) {
+  int st = check_ready(e);
+  if (st) return st;
+  if (!in || !in->pose || !in->alive || !in->action || in->n < 0)
+    return fail(e, BMCTS_ERR_INVALID_ARG, "step_batch: null argument");
+  if (ro && !ro->result) return fail(e, BMCTS_ERR_INVALID_ARG, "expand_rollout: result required");
+  if (!ro && !so) return fail(e, BMCTS_ERR_INVALID_ARG, "step_batch: no outputs");
+  const int n = in->n, A = e->scn.n_agents;
+  if (n == 0) return BMCTS_OK;
+  const bool coop = e->cfg.state_kind == BMCTS_STATE_COOPERATIVE;
+  if (!coop && A > 1 && (!in->hyp_id || !in->draw_id))
+    return fail(e, BMCTS_ERR_INVALID_ARG, "step_batch: hyp_id and draw_id required");
+  bmcts::KernelArgs a;
+  base_args(e, a, n, in->seed, in->stream);
+  a.do_expand = 1;
+  a.do_rollout = ro ? 1 : 0;
+  a.first_rollout_id = first_rollout_id;
+  bmcts_step_out none;
+  std::memset(&none, 0, sizeof(none));
+  if (!so) so = &none;
+  if (in->memory == BMCTS_MEM_DEVICE) {
+    a.pose = (const float4*)in->pose;
+    a.alive = in->alive;
+    a.hyp = in->hyp_id;
+    a.depth = in->depth;
+    a.action = in->action;
+    a.draw_id = in->draw_id;
+    a.next_pose = (float4*)so->next_pose;
+    a.next_alive = so->next_alive;
+    a.reward = so->reward;
+    a.cost = so->cost;
+    a.flags = so->flags;
+    a.last_action = so->last_action;
+    if (ro) {
+      a.result = ro->result;
+      a.ret_agents = ro->ret_agents;
+      a.final_pose = (float4*)ro->final_pose;
+    }
+    return launch(e, a);
+  }
+  const void* d;
+  void* o;
+  const size_t nA = (size_t)n * A;
+  if ((st = h2d(e, e->b_pose, in->pose, sizeof(float) * 4 * nA, &d))) return st;
+  a.pose = (const float4*)d;
+  if ((st = h2d(e, e->b_alive, in->alive, sizeof(uint32_t) * (size_t)n, &d))) return st;
+  a.alive = (const uint32_t*)d;
+  if ((st = h2d(e, e->b_hyp, in->hyp_id, nA, &d))) return st;
+  a.hyp = (const uint8_t*)d;
+  if ((st = h2d(e, e->b_depth, in->depth, sizeof(uint16_t) * (size_t)n, &d))) return st;
+  a.depth = (const uint16_t*)d;
+  if ((st = h2d(e, e->b_action, in->action, nA, &d))) return st;
+  a.action = (const uint8_t*)d;
+  if ((st = h2d(e, e->b_draw, in->draw_id, sizeof(uint64_t) * nA, &d))) return st;
+  a.draw_id = (const uint64_t*)d;
+  if ((st = out_buf(e, e->b_next_pose, so->next_pose, sizeof(float) * 4 * nA, &o))) return st;
+  a.next_pose = (float4*)o;
+  if ((st = out_buf(e, e->b_next_alive, so->next_alive, sizeof(uint32_t) * (size_t)n, &o)))
+    return st;
+  a.next_alive = (uint32_t*)o;
+  if ((st = out_buf(e, e->b_reward, so->reward, sizeof(float) * nA, &o))) return st;
+  a.reward = (float*)o;
+  if ((st = out_buf(e, e->b_cost, so->cost, sizeof(float) * 2 * (size_t)n, &o))) return st;
+  a.cost = (float*)o;
+  if ((st = out_buf(e, e->b_flags, so->flags, sizeof(uint32_t) * (size_t)n, &o))) return st;
+  a.flags = (uint32_t*)o;
+  if ((st = out_buf(e, e->b_last_action, so->last_action, sizeof(float) * nA, &o))) return st;
+  a.last_action = (float*)o;
+  if (ro) {
+    if ((st = out_buf(e, e->b_result, ro->result, sizeof(bmcts_rollout_result) * (size_t)n, &o)))
+      return st;
+    a.result = (bmcts_rollout_result*)o;
+    if ((st = out_buf(e, e->b_ret_agents, ro->ret_agents, sizeof(float) * nA, &o))) return st;
+    a.ret_agents = (float*)o;
+    if ((st = out_buf(e, e->b_final_pose, ro->final_pose, sizeof(float) * 4 * nA, &o))) return st;
+    a.final_pose = (float4*)o;
+  }
+  if ((st = launch(e, a))) return st;
+  if ((st = d2h(e, so->next_pose, a.next_pose, sizeof(float) * 4 * nA))) return st;
+  if ((st = d2h(e, so->next_alive, a.next_alive, sizeof(uint32_t) * (size_t)n))) return st;
+  if ((st = d2h(e, so->reward, a.reward, sizeof(float) * nA))) return st;
+  if ((st = d2h(e, so->cost, a.cost, sizeof(float) * 2 * (size_t)n))) return st;
+  if ((st = d2h(e, so->flags, a.flags, sizeof(uint32_t) * (size_t)n))) return st;
+  if ((st = d2h(e, so->last_action, a.last_action, sizeof(float) * nA))) return st;
+  if (ro) {
+    if ((st = d2h(e, ro->result, a.result, sizeof(bmcts_rollout_result) * (size_t)n))) return st;
+    if ((st = d2h(e, ro->ret_agents, a.ret_agents, sizeof(float) * nA))) return st;
+    if ((st = d2h(e, ro->final_pose, a.final_pose, sizeof(float) * 4 * nA))) return st;
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  return BMCTS_OK;
+}
+
+int bmcts_step_batch(bmcts_engine* e, const bmcts_step_in* in, const bmcts_step_out* out) {
+  if (!out) return e ? fail(e, BMCTS_ERR_INVALID_ARG, "step_batch: out is null") : BMCTS_ERR_INVALID_ARG;
+  return step_common(e, in, out, nullptr, 0);
+}
+
+int bmcts_expand_rollout_batch(bmcts_engine* e, const bmcts_step_in* in,
+                               const bmcts_step_out* step_out, uint64_t first_rollout_id,
+                               const bmcts_rollout_out* rollout_out) {
+  if (!rollout_out)
+    return e ? fail(e, BMCTS_ERR_INVALID_ARG, "expand_rollout: rollout_out is null")
+             : BMCTS_ERR_INVALID_ARG;
+  return step_common(e, in, step_out, rollout_out, first_rollout_id);
+}
+
+int bmcts_likelihood_batch(bmcts_engine* e, const bmcts_likelihood_in* in, float* prob) {
+  int st = check_ready(e);
+  if (st) return st;
+  if (!in || !prob || !in->pose || !in->alive || !in->action || in->n_worlds < 0 ||
+      in->n_samples < 1 || in->n_buckets < 1 || !(in->buckets_upper > in->buckets_lower))
+    return fail(e, BMCTS_ERR_INVALID_ARG, "likelihood_batch: bad argument");
+  const int W = in->n_worlds, A = e->scn.n_agents, H = e->scn.n_hypotheses;
+  if (W == 0 || H == 0) return BMCTS_OK;
+  if (W > 65535 * 32 || H > 65535 || A > 65535)
+    return fail(e, BMCTS_ERR_INVALID_ARG, "likelihood_batch: too many worlds");
+  bmcts::LikelihoodArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.scn = e->d_scn;
+  a.n_worlds = W;
+  a.A = A;
+  a.C = e->scn.n_corridors;
+  a.H = H;
+  a.n_samples = in->n_samples;
+  a.n_buckets = in->n_buckets;
+  a.lower = in->buckets_lower;
+  a.upper = in->buckets_upper;
+  a.key0 = (uint32_t)in->seed;
+  a.key1 = (uint32_t)(in->seed >> 32) ^ in->stream;
+  const size_t nprob = (size_t)W * A * H;
+  if (in->memory == BMCTS_MEM_DEVICE) {
+    a.pose = (const float4*)in->pose;
+    a.alive = in->alive;
+    a.action = in->action;
+    a.prob = prob;
+  } else {
+    const void* d;
+    if ((st = h2d(e, e->b_pose, in->pose, sizeof(float) * 4 * (size_t)W * A, &d))) return st;
+    a.pose = (const float4*)d;
+    if ((st = h2d(e, e->b_alive, in->alive, sizeof(uint32_t) * (size_t)W, &d))) return st;
+    a.alive = (const uint32_t*)d;
+    if ((st = h2d(e, e->b_lik_action, in->action, sizeof(float) * (size_t)W * A, &d))) return st;
+    a.action = (const float*)d;
+    if ((st = ensure(e, e->b_prob, sizeof(float) * nprob))) return st;
+    a.prob = (float*)e->b_prob.ptr;
+  }
+  CU(cudaEventRecord(e->ev_start, e->stream));
+  dim3 grid((unsigned)W, (unsigned)H, (unsigned)A);
+  bmcts::likelihood_kernel<<<grid, 256, 0, e->stream>>>(a);
+  CU(cudaGetLastError());
+  e->launches++;
+  CU(cudaEventRecord(e->ev_stop, e->stream));
+  e->timed = true;
+  if (in->memory != BMCTS_MEM_DEVICE) {
+    if ((st = d2h(e, prob, a.prob, sizeof(float) * nprob))) return st;
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  return BMCTS_OK;
+}
+
+int bmcts_alloc_host(size_t bytes, void** out) {
+  if (!out) return BMCTS_ERR_INVALID_ARG;
+  *out = nullptr;
+  cudaError_t ce = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  return ce == cudaSuccess ? BMCTS_OK : BMCTS_ERR_CUDA;
+}
+
+void bmcts_free_host(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int bmcts_sync(bmcts_engine* e) {
+  if (!e) return BMCTS_ERR_INVALID_ARG;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  return BMCTS_OK;
+}
+
+int bmcts_last_kernel_ms(bmcts_engine* e, float* ms) {
+  if (!e || !ms) return BMCTS_ERR_INVALID_ARG;
+  if (!e->timed) return fail(e, BMCTS_ERR_INVALID_ARG, "no batch call has been timed yet");
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventSynchronize(e->ev_stop));
+  CU(cudaEventElapsedTime(ms, e->ev_start, e->ev_stop));
+  return BMCTS_OK;
+}
+
+uint64_t bmcts_launch_count(const bmcts_engine* e) { return e ? e->launches : 0; }
+
+void* bmcts_stream(bmcts_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+const char* bmcts_last_error(const bmcts_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+}  // extern "C"

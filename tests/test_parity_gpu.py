@@ -1,0 +1,134 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical
+sampled hypotheses, actions and RNG draws.  Bar (BASELINE.json north_star): collision /
+violation flags and terminal indices bit-exact; returns, costs and final poses within
+1e-4 relative (they are in fact bit-exact, which is asserted too)."""
+import numpy as np
+import pytest
+
+import kat_worlds
+import oracle
+import parity
+from planner_mcts_b200 import RolloutEngine, _abi, scenarios
+
+pytestmark = pytest.mark.gpu
+
+WORKLOADS = ["c1_highway_mdp", "c2_merge_sbg", "c3_merge_risk", "c4_coop", "c5_rsbg"]
+
+
+@pytest.mark.parametrize("name", WORKLOADS)
+def test_rollout_parity(name):
+    cfg, scn, meta = scenarios.workload(name, horizon=20)
+    n = 96 if name != "c5_rsbg" else 64
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, n, seed=7)
+    eng = RolloutEngine(cfg, scn)
+    g = eng.rollout(pose, alive, hyp, seed=1000, stream=3, first_rollout_id=12345,
+                    want_agents=True, want_final=True)
+    c = oracle.rollout(cfg, scn, pose, alive, hyp, seed=1000, stream=3, first_rollout_id=12345)
+    parity.assert_results_match(g, c)
+    # the batch must exercise both outcomes
+    assert (g["result"]["n_steps"] > 0).all()
+    assert eng.launch_count() == 1
+
+
+@pytest.mark.parametrize("name", ["c2_merge_sbg", "c3_merge_risk", "c4_coop"])
+def test_step_and_expand_parity(name):
+    cfg, scn, meta = scenarios.workload(name, horizon=12)
+    n = 70   # ragged: not a multiple of the 32-rollout block
+    rng = np.random.default_rng(5)
+    pose, alive, hyp = scenarios.sample_leaves(scn, n, meta["lane_of"], meta["s_of"], rng,
+                                               dead_prob=0.1)
+    A = scn.n_agents
+    action = rng.integers(0, scn.n_ego_actions, size=(A, n)).astype(np.uint8)
+    draw = rng.integers(0, 2**63, size=(A, n)).astype(np.uint64)
+    depth = rng.integers(1, 6, size=n).astype(np.uint16)
+    eng = RolloutEngine(cfg, scn)
+    g = eng.step(pose, alive, hyp, action, draw, depth=depth, seed=99, stream=1)
+    c = oracle.step(cfg, scn, pose, alive, hyp, action, draw, depth=depth, seed=99, stream=1)
+    parity.assert_steps_match(g, c)
+    g = eng.expand_rollout(pose, alive, hyp, action, draw, depth=depth, seed=99, stream=1,
+                           first_rollout_id=777, want_agents=True, want_final=True)
+    c = oracle.expand_rollout(cfg, scn, pose, alive, hyp, action, draw, depth=depth, seed=99,
+                              stream=1, first_rollout_id=777)
+    parity.assert_steps_match(g, c)
+    parity.assert_results_match(g, c)
+
+
+def test_prediction_alpha_and_long_horizon():
+    cfg, scn, meta = scenarios.workload("c1_highway_mdp", horizon=200)
+    cfg.prediction_k, cfg.prediction_alpha = 0.2, 0.3
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, 40, seed=3)
+    depth = np.arange(1, 41).astype(np.uint16)
+    eng = RolloutEngine(cfg, scn)
+    g = eng.rollout(pose, alive, hyp, depth=depth, want_agents=True, want_final=True)
+    c = oracle.rollout(cfg, scn, pose, alive, hyp, depth=depth)
+    parity.assert_results_match(g, c)
+
+
+def test_edge_cases_empty_single_dead_ego():
+    cfg, scn, meta = scenarios.workload("c2_merge_sbg", horizon=10)
+    eng = RolloutEngine(cfg, scn)
+    A = scn.n_agents
+    # empty batch
+    g = eng.rollout(np.zeros((A, 0, 4), np.float32), np.zeros(0, np.uint32),
+                    np.zeros((A, 0), np.uint8))
+    assert g["result"].shape == (0,)
+    # single leaf, ego missing -> out_of_map terminal at the first step
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, 1, seed=2)
+    alive[:] &= np.uint32(0xFFFFFFFE)
+    g = eng.rollout(pose, alive, hyp, want_agents=True, want_final=True)
+    c = oracle.rollout(cfg, scn, pose, alive, hyp)
+    parity.assert_results_match(g, c)
+    assert g["result"]["n_steps"][0] == 1
+    assert g["result"]["flags"][0] & _abi.F_OUT_OF_MAP
+    # only the ego alive
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, 33, seed=4)
+    alive[:] = 1
+    g = eng.rollout(pose, alive, hyp, want_agents=True, want_final=True)
+    c = oracle.rollout(cfg, scn, pose, alive, hyp)
+    parity.assert_results_match(g, c)
+
+
+def test_reference_kat_worlds_on_gpu():
+    """the reference's own execute KAT (behavior_uct_hypothesis_test.cc:174-211) through the GPU"""
+    hyps = [kat_worlds.make_params_hypothesis(1.0, 1.5), kat_worlds.make_params_hypothesis(1.5, 3.0)]
+    cfg, scn, pose, alive = kat_worlds.test_world(1, 10.0, 5.0, -4.0, hyps)
+    cfg.goal_reward, cfg.collision_reward, cfg.out_of_drivable_reward = 200.0, -2000.0, -2000.0
+    cfg.goal_cost, cfg.collision_cost, cfg.out_of_drivable_cost = 10.0, 300.0, 300.0
+    eng = RolloutEngine(cfg, scn)
+    hyp = np.zeros((2, 1), np.uint8)
+    for ego_action, want_r, want_c in ((2, -2000.0, 300.0), (0, 200.0, 10.0)):
+        p, a = pose, alive
+        for i in range(1000):
+            act = np.array([[ego_action], [0]], np.uint8)
+            o = eng.step(p, a, hyp, act, np.full((2, 1), 1000 + i, np.uint64),
+                         depth=np.array([1 + i], np.uint16))
+            p, a = o["next_pose"], o["next_alive"]
+            if o["flags"][0] & _abi.F_TERMINAL:
+                break
+        assert o["flags"][0] & _abi.F_TERMINAL
+        assert o["reward"][0, 0] == pytest.approx(want_r, abs=1e-5)
+        assert o["cost"][0, 0] == pytest.approx(want_c, abs=1e-5)
+
+
+def test_likelihood_parity():
+    cfg, scn, meta = scenarios.workload("c2_merge_sbg")
+    W = 5
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, W, seed=11)
+    rng = np.random.default_rng(0)
+    action = rng.uniform(-3, 2, size=(scn.n_agents, W)).astype(np.float32)
+    eng = RolloutEngine(cfg, scn)
+    g = eng.likelihood(pose, alive, action, n_samples=2000, n_buckets=100)
+    c = oracle.likelihood(cfg, scn, pose, alive, action, n_samples=2000, n_buckets=100)
+    assert np.array_equal(g, c)   # counts / n_samples: exact
+    assert g.max() > 0
+
+
+def test_rollouts_are_reproducible_and_schedule_independent():
+    cfg, scn, meta = scenarios.workload("c2_merge_sbg", horizon=15)
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, 64, seed=9)
+    eng = RolloutEngine(cfg, scn)
+    a = eng.rollout(pose, alive, hyp, first_rollout_id=100)["result"]
+    # the same leaves in two half batches, second half first
+    b1 = eng.rollout(pose[:, 32:], alive[32:], hyp[:, 32:], first_rollout_id=132)["result"]
+    b0 = eng.rollout(pose[:, :32], alive[:32], hyp[:, :32], first_rollout_id=100)["result"]
+    assert np.array_equal(a, np.concatenate([b0, b1]))
