@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- rollout agent-steps/s of the MCTS leaf-evaluation path on B200.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
+A step = one rollout batch (bmcts_rollout_batch) over `--rollouts` synthetic leaf states of
+the configured BASELINE.json workload (default: configs[1], "BehaviorUCTHypothesis SBG, 8
+behavior hypotheses, merge scenario, 10 agents"), horizon 20 steps with terminal early
+exit.  `value` is measured with the leaves resident in HBM (CUDA events on the engine's
+stream); `e2e` is the same metric through the C-ABI call with pinned HOST buffers
+(host->device copy of the leaves and device->host read of the results inside the timed
+region).  `--impl reference` times the CPU oracle (the reference itself cannot be built
+here) on all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "rollout agent-steps/sec"
+UNIT = "agent-steps/s"
+
+
+def flop_per_agent_step(A, cooperative=False):
+    """algorithmic FLOPs per agent-step (FMA = 2)."""
+    if cooperative:
+        return 400.0 + (A - 1) * 168.0 + 680.0
+    return ((A - 1) * (480.0 + 60.0 * (A - 1)) + 400.0 + (A - 1) * 168.0 + 680.0) / A
+
+
+def hbm_bytes_per_rollout(A):
+    """algorithmic HBM bytes of one rollout: leaf state in, 32-byte result record out"""
+    return A * (16 + 1) + 4 + 32
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks and throttle reasons during the timed region"""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.15)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def run_reference(args):
+    """CPU arm: the oracle (kind 'port') on all host cores, bounded sample per step."""
+    import oracle
+    from planner_mcts_b200 import scenarios
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, scn, meta = scenarios.workload(args.workload, horizon=args.horizon)
+    cores = os.cpu_count() or 1
+    n = args.cpu_rollouts
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, n, seed=1)
+    oracle.load()
+    for w in range(args.warmup):
+        oracle.rollout(cfg, scn, pose[:, :max(64, n // 16)], alive[:max(64, n // 16)],
+                       hyp[:, :max(64, n // 16)], n_threads=cores)
+    total, t0 = 0, time.perf_counter()
+    for s in range(args.steps):
+        r = oracle.rollout(cfg, scn, pose, alive, hyp, first_rollout_id=s * n, n_threads=cores)
+        total += int(r["result"]["agent_steps"].sum())
+    dt = time.perf_counter() - t0
+    val = total / dt
+    sample = f"{n} rollouts/step x {args.steps} steps of {args.workload} (horizon {args.horizon})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "agents": meta["A"], "hypotheses": meta["H"],
+                   "horizon": args.horizon, "rollouts_per_step": n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference cannot be compiled here (Bazel + BARK + mamcts absent); this is the "
+                "in-repo CPU oracle, which has none of BARK's heap cloning and is therefore "
+                "faster than the real reference would be",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from planner_mcts_b200 import RESULT_DTYPE, RolloutEngine, _abi, scenarios
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the rollout engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, scn, meta = scenarios.workload(args.workload, horizon=args.horizon)
+    A, n = meta["A"], args.rollouts
+    coop = cfg.state_kind == _abi.STATE_COOPERATIVE
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, n, seed=1 + rank)
+    eng = RolloutEngine(cfg, scn, device=local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+
+    # ---- device-resident arm
+    d_pose = torch.from_numpy(pose).to(dev)
+    d_alive = torch.from_numpy(alive.view(np.int32)).to(dev)
+    d_hyp = torch.from_numpy(hyp).to(dev)
+    d_res = torch.zeros(n, 8, dtype=torch.float32, device=dev)
+    d_stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        eng.rollout_raw(n, _abi.MEM_DEVICE, d_pose, d_alive, d_hyp, None, d_res, seed=1000,
+                        stream=rank, first_rollout_id=i * n)
+
+    def merge_root_stats():
+        # root-parallel merge: sum of the per-rank root statistics over NVLink
+        with torch.cuda.stream(stream):
+            d_stats[:4] = d_res[:, :4].sum(0, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(d_stats)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_device(i)
+        merge_root_stats()
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, total_steps = [], 0
+    ev0.record(stream)
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+        merge_root_stats()
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.summary()
+    # agent-steps are deterministic per (leaf, rollout id): recount them outside the timed region
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+        eng.sync()
+        kernel_ms.append(eng.last_kernel_ms())
+        res = d_res.cpu().numpy().view(RESULT_DTYPE).reshape(-1)
+        total_steps += int(res["agent_steps"].sum())
+    mean_rollout_len = float(res["n_steps"].mean())
+
+    # ---- end-to-end arm: pinned host buffers through the C ABI, copies inside the timed region
+    h_pose = torch.from_numpy(pose).pin_memory()
+    h_alive = torch.from_numpy(alive.view(np.int32)).pin_memory()
+    h_hyp = torch.from_numpy(hyp).pin_memory()
+    h_res = torch.zeros(n, 8, dtype=torch.float32).pin_memory()
+
+    def step_host(i):
+        eng.rollout_raw(n, _abi.MEM_HOST, h_pose, h_alive, h_hyp, None, h_res, seed=1000,
+                        stream=rank, first_rollout_id=i * n)
+
+    for i in range(max(1, args.warmup)):
+        step_host(i)
+    barrier()
+    e2e_steps = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(args.warmup + i)
+        e2e_steps += int(h_res.numpy().view(RESULT_DTYPE)["agent_steps"].sum())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks: time = max, work = sum
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    w = torch.tensor([float(total_steps), float(e2e_steps), float(launches)], dtype=torch.float64,
+                     device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+    total_all, e2e_all, launches_all = float(w[0]), float(w[1]), int(w[2])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = total_all / (elapsed_ms * 1e-3)
+    e2e_value = e2e_all / (e2e_ms * 1e-3)
+    peaks, peak_kind = measured_peaks()
+    k_ms = float(np.mean(kernel_ms))
+    steps_per_launch = total_steps / args.steps
+    flop = flop_per_agent_step(A, coop)
+    achieved_tflops = steps_per_launch * flop / (k_ms * 1e-3) / 1e12
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    peak_tflops = 2 * 128 * 148 * sm_mhz * 1e6 / 1e12
+    peak_tflops_max = 2 * 128 * 148 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    hbm_gbs = n * hbm_bytes_per_rollout(A) / (k_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "agents": A, "hypotheses": meta["H"],
+                   "horizon": args.horizon, "rollouts_per_step_per_gpu": n,
+                   "mean_rollout_steps": mean_rollout_len,
+                   "l2": "inputs larger than L2 (leaf batch %.0f MB per step)" %
+                         (n * (A * 17 + 4) / 1e6),
+                   "rollouts_per_s": n * world / (elapsed_ms / args.steps * 1e-3)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(n * (A * 17 + 4)), "d2h_bytes_per_step": int(n * 32)},
+        "gpu_launches": launches_all,
+        "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops,
+                     "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
+                     "peak_at_max_clock": peak_tflops_max,
+                     "peak_def": "2 x 128 FP32 lanes x 148 SMs x SM clock under load (%s MHz); "
+                                 "algorithmic FLOPs per agent-step = %.0f (SURVEY.md 8d)" %
+                                 (sm_mhz, flop),
+                     "kernel": "bmcts::rollout_kernel", "kernel_ms": k_ms, "traffic": None},
+        "roofline_hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"),
+                         "unit": "GB/s", "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0),
+                         "peak_kind": peak_kind, "traffic": None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, cfg, scn, meta)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, cfg, scn, meta):
+    """oracle ('port') on the host cores, bounded to roughly 10-20 s of CPU work"""
+    import oracle
+    from planner_mcts_b200 import scenarios
+    cores = os.cpu_count() or 1
+    n = 16384
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, n, seed=1)
+    oracle.load()
+    oracle.rollout(cfg, scn, pose[:, :256], alive[:256], hyp[:, :256], n_threads=cores)  # warm-up
+
+    def timed(n_threads, budget_s):
+        steps, calls, t0 = 0, 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s:
+            r = oracle.rollout(cfg, scn, pose, alive, hyp, first_rollout_id=calls * n,
+                               n_threads=n_threads)
+            steps += int(r["result"]["agent_steps"].sum())
+            calls += 1
+        dt = time.perf_counter() - t0
+        return steps / dt, calls, dt
+
+    one_thread, c1, t1 = timed(1, 4.0)
+    val, c2, t2 = timed(cores, 10.0)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "one_thread_value": one_thread,
+            "sample": f"{c2 * n} rollouts of {args.workload} (horizon {args.horizon}) on {cores} "
+                      f"threads in {t2:.1f} s; {c1 * n} rollouts on 1 thread in {t1:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_merge_sbg")
+    ap.add_argument("--horizon", type=int, default=20)
+    ap.add_argument("--rollouts", type=int, default=1 << 20, help="leaf states per step per GPU")
+    ap.add_argument("--cpu-rollouts", type=int, default=65536, help="reference arm: leaves per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

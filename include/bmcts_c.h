@@ -230,6 +230,7 @@ typedef struct bmcts_scenario {
   float agent_rear[BMCTS_MAX_AGENTS];   /* rear edge -> reference point, 1.25 */
   bmcts_hypothesis hypotheses[BMCTS_MAX_HYPOTHESES];
   bmcts_ego_action ego_actions[BMCTS_MAX_EGO_ACTIONS];
+  int32_t pad2_[2]; /* sizeof % 16 == 0: the kernels stage this struct with 16-byte copies */
 } bmcts_scenario;
 
 /* per-rollout scalar results, one 32-byte record */

@@ -164,8 +164,17 @@ BM_HD float bm_atan2(float y, float x) {
 
 /* x^n for a small non-negative integer n (IDM "Exponent", default 4) */
 BM_HD float bm_powi(float x, int n) {
-  float p = 1.0f;
-  for (int i = 0; i < n; ++i) p = p * x;
+  /* left-to-right products ((x*x)*x)*x ...: the unrolled cases round exactly like the loop */
+  switch (n) {
+    case 0: return 1.0f;
+    case 1: return x;
+    case 2: return x * x;
+    case 3: return (x * x) * x;
+    case 4: return ((x * x) * x) * x;
+    default: break;
+  }
+  float p = ((x * x) * x) * x;
+  for (int i = 4; i < n; ++i) p = p * x;
   return p;
 }
 

@@ -1,7 +1,7 @@
 """ctypes mirror of include/bmcts_c.h (the C ABI of libbmcts.so).
 
-The same structure definitions are used by the tests to call the CPU oracle
-(oracle/_build/liboracle.so), which takes the identical PODs.
+The tests reuse these structure definitions for their CPU checker, which takes
+the identical PODs.
 """
 import ctypes as C
 import os
@@ -96,7 +96,7 @@ class Scenario(C.Structure):
         ("agent_length", f32 * MAX_AGENTS), ("agent_width", f32 * MAX_AGENTS),
         ("agent_rear", f32 * MAX_AGENTS),
         ("hypotheses", Hypothesis * MAX_HYPOTHESES),
-        ("ego_actions", EgoAction * MAX_EGO_ACTIONS),
+        ("ego_actions", EgoAction * MAX_EGO_ACTIONS), ("pad2_", i32 * 2),
     ]
 
 

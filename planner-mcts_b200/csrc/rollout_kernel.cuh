@@ -40,6 +40,9 @@ constexpr uint32_t kGoalFailBit = 1u << 16;  // scratch bit: a goal-polygon corn
 // published per-agent fields in shared memory
 enum { F_X = 0, F_Y, F_C, F_S, F_V, F_TH, F_PROJ };  // F_PROJ + 2*c = s, +1 = d_eff
 
+static_assert(sizeof(bmcts_scenario) % 16 == 0, "scenario is staged with 16-byte copies");
+static_assert(sizeof(bmcts_config) % 4 == 0, "config is staged with 4-byte copies");
+
 struct KernelArgs {
   // inputs (agent-major SoA, see bmcts_c.h)
   const float4* pose;
@@ -295,9 +298,24 @@ __device__ __forceinline__ IdmParams sample_idm_params(const bmcts_hypothesis& h
   return p;  // coolness (r1.y) is validated to be 0: no blend
 }
 
-__device__ __forceinline__ float idm_acc(const bmcts_hypothesis& h, const IdmParams& p,
-                                         float inv_v0, float inv_2sab, bool has_leader, float v,
-                                         float v_l, float gap) {
+struct IdmLimits {  // per-hypothesis constants hoisted out of the sub-step loop
+  float acc_lo, acc_hi, v_min, v_max;
+  int exponent;
+};
+
+__device__ __forceinline__ IdmLimits idm_limits(const bmcts_hypothesis& h) {
+  IdmLimits l;
+  l.acc_lo = h.acc_lower_bound;
+  l.acc_hi = h.acc_upper_bound;
+  l.v_min = h.min_velocity;
+  l.v_max = h.max_velocity;
+  l.exponent = h.exponent;
+  return l;
+}
+
+__device__ __forceinline__ float idm_acc(const IdmLimits& h, const IdmParams& p, float inv_v0,
+                                         float inv_2sab, bool has_leader, float v, float v_l,
+                                         float gap) {
   float free_term = 1.0f - bm_powi(v * inv_v0, h.exponent);
   float acc;
   if (has_leader) {
@@ -308,7 +326,7 @@ __device__ __forceinline__ float idm_acc(const bmcts_hypothesis& h, const IdmPar
   } else {
     acc = p.a_max * free_term;
   }
-  return bm_clamp(acc, h.acc_lower_bound, h.acc_upper_bound);
+  return bm_clamp(acc, h.acc_lo, h.acc_hi);
 }
 
 // ---------------------------------------------------------------------------
@@ -413,6 +431,7 @@ __global__ void __launch_bounds__(1024) rollout_kernel(const KernelArgs p) {
   // nearest alive agents ahead of / behind the own agent inside its corridor
   int jf = -1, jr = -1;
   float ds_f = kBig, ds_r = kBig;
+  const bool need_rear = cfg.add_safe_dist && cfg.dyn_to_rear;
   auto neighbours = [&](uint32_t am) {
     jf = -1;
     jr = -1;
@@ -430,7 +449,7 @@ __global__ void __launch_bounds__(1024) rollout_kernel(const KernelArgs p) {
         jf = j;
       }
       float dr = -ds;
-      if (dr > 0.0f && dr < ds_r) {
+      if (need_rear && dr > 0.0f && dr < ds_r) {
         ds_r = dr;
         jr = j;
       }
@@ -514,6 +533,7 @@ __global__ void __launch_bounds__(1024) rollout_kernel(const KernelArgs p) {
                     2u * (uint32_t)n + 1u);
         }
         const IdmParams ip = sample_idm_params(h, r0, r1);
+        const IdmLimits hl = idm_limits(h);
         const bool has_leader = jf >= 0;
         float gap = 0.0f, v_l = 0.0f;
         if (has_leader) {
@@ -525,9 +545,9 @@ __global__ void __launch_bounds__(1024) rollout_kernel(const KernelArgs p) {
         const float half_dt2 = (0.5f * dt) * dt;
         float trav = 0.0f, acc = 0.0f;
         for (int q = 0; q < nsub; ++q) {
-          acc = idm_acc(h, ip, inv_v0, inv_2sab, has_leader, nv, v_l, gap);
+          acc = idm_acc(hl, ip, inv_v0, inv_2sab, has_leader, nv, v_l, gap);
           float ds = bm_max(0.0f, bm_fma(acc, half_dt2, nv * dt));
-          nv = bm_clamp(bm_fma(acc, dt, nv), h.min_velocity, h.max_velocity);
+          nv = bm_clamp(bm_fma(acc, dt, nv), hl.v_min, hl.v_max);
           gap = gap + bm_fma(v_l, dt, -ds);
           trav = trav + ds;
         }
@@ -599,9 +619,10 @@ __global__ void __launch_bounds__(1024) rollout_kernel(const KernelArgs p) {
           // the ego's 4 + 4 corner-in-polygon tests are spread over the other warps
           const float ex = PUB(F_X, 0), ey = PUB(F_Y, 0), ec = PUB(F_C, 0), es = PUB(F_S, 0);
           const int n_items = (scn.goal.kind == BMCTS_GOAL_POLYGON) ? 8 : 4;
-          for (int t = 0; t < n_items; ++t) {
-            int owner = (A > 1) ? 1 + (t % (A - 1)) : 0;
-            if (owner != k) continue;
+          // item t belongs to warp 1 + t % (A-1) (warp 0 when the ego is alone)
+          const int t_first = (A > 1) ? k - 1 : 0;
+          const int t_stride = (A > 1) ? A - 1 : 1;
+          for (int t = t_first; t >= 0 && t < n_items; t += t_stride) {
             if (t < 4) {
               Box bd = agent_box(scn, 0, ex, ey, ec, es, cfg.drivable_lat_safe_dist,
                                  cfg.drivable_lon_safe_dist);
@@ -863,6 +884,7 @@ __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p)
   }
   __syncthreads();
   const bmcts_hypothesis hy = scn.hypotheses[h];
+  const IdmLimits hl = idm_limits(hy);
   const bool has_leader = s_has_leader != 0;
   const float gap = s_gap, v_l = s_vl, v_own = s_vown;
   const float bucket_size = bm_div(p.upper - p.lower, (float)p.n_buckets);
@@ -875,7 +897,7 @@ __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p)
     IdmParams ip = sample_idm_params(hy, r0, r1);
     float inv_v0 = bm_div(1.0f, bm_max(ip.v0, 1.0e-3f));
     float inv_2sab = bm_div(1.0f, 2.0f * bm_sqrt(bm_max(ip.a_max * ip.b, 1.0e-6f)));
-    float acc = idm_acc(hy, ip, inv_v0, inv_2sab, has_leader, v_own, v_l, gap);
+    float acc = idm_acc(hl, ip, inv_v0, inv_2sab, has_leader, v_own, v_l, gap);
     if (acc < p.lower || acc > p.upper) continue;
     int b = (int)floorf(bm_div(acc - p.lower, bucket_size));
     if (b > p.n_buckets - 1) b = p.n_buckets - 1;
