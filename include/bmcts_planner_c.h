@@ -1,0 +1,88 @@
+/*
+ * bmcts_planner_c.h -- C ABI of the BehaviorUCT* planners (host tree search + GPU leaf
+ * evaluation) for bindings that cannot use the C++ classes of
+ * planner-mcts_b200/host/behavior_uct.hpp directly (Python ctypes in this repo's tests and
+ * bench).  It mirrors the reference's pybind surface
+ * (/root/reference/bark_mcts/python_wrapper/python_planner_uct.cpp:131-248): construct a
+ * planner from parameters (+ hypotheses), call Plan(delta_time, observed_world), read the
+ * last_* debug infos.
+ */
+#ifndef BMCTS_PLANNER_C_H_
+#define BMCTS_PLANNER_C_H_
+
+#include "bmcts_c.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  BMCTS_PLANNER_HYPOTHESIS = 0,      /* BehaviorUCTHypothesis */
+  BMCTS_PLANNER_RISK_CONSTRAINT = 1, /* BehaviorUCTRiskConstraint */
+  BMCTS_PLANNER_COOPERATIVE = 2      /* BehaviorUCTCooperative */
+};
+
+#define BMCTS_PLAN_MAX_TRAJ 64
+
+/* one agent of the observed world (BARK Agent: state, shape, last action) */
+typedef struct bmcts_agent_state {
+  uint32_t id;
+  float x, y, theta, v;
+  float length, width, rear;
+  float last_acc; /* GetStateInputHistory().back().second, longitudinal part */
+} bmcts_agent_state;
+
+typedef struct bmcts_plan_result {
+  uint32_t best_action;    /* GetLastMacroAction() */
+  uint32_t num_iterations; /* GetLastNumIterations() */
+  uint32_t num_nodes;      /* GetLastNumNodes() */
+  uint32_t num_actions;    /* GetNumMotionPrimitives(world) */
+  double solution_time_ms; /* GetLastSolutionTime() */
+  double return_values[BMCTS_MAX_EGO_ACTIONS];  /* GetLastReturnValues(); NaN = not visited */
+  double visit_counts[BMCTS_MAX_EGO_ACTIONS];
+  double cost_values[2][BMCTS_MAX_EGO_ACTIONS]; /* GetLastCostValues(): [0] envelope / cost, [1] collision */
+  double policy[BMCTS_MAX_EGO_ACTIONS];         /* GetLastPolicySampled().second */
+  double expected_risk[2];                      /* GetLastExpectedRisk() */
+  double scenario_risk[2];                      /* GetLastScenarioRisk() */
+  float action_acc, action_steering;            /* GetLastAction() = Input[acc, steering] */
+  int32_t max_tree_depth;
+  int32_t root_expanded_actions[BMCTS_MAX_AGENTS];
+  int32_t n_traj;
+  double trajectory[BMCTS_PLAN_MAX_TRAJ * 5];   /* GetLastTrajectory(): rows [t, x, y, theta, v] */
+  uint64_t engine_launches;                     /* kernels launched so far by this planner */
+} bmcts_plan_result;
+
+typedef struct bmcts_planner bmcts_planner;
+
+int bmcts_planner_create(int kind, int device, bmcts_planner** out);
+void bmcts_planner_destroy(bmcts_planner* p);
+/* BARK ParamServer key ("BehaviorUctBase::Mcts::MaxNumIterations", ...), 1..n values;
+ * must be called before the first bmcts_planner_plan */
+int bmcts_planner_set_param(bmcts_planner* p, const char* key, const double* values, int n);
+/* appends one BehaviorHypothesisIDM to the planner's hypothesis set */
+int bmcts_planner_add_hypothesis(bmcts_planner* p, const bmcts_hypothesis* region, int num_samples,
+                                 int num_buckets, float buckets_lower, float buckets_upper);
+/* lane corridors, road polygon and goal of `map` are read; the rest is ignored */
+int bmcts_planner_set_map(bmcts_planner* p, const bmcts_scenario* map);
+/* root-parallel tree index of this planner (rank): distinct Philox streams per rank */
+int bmcts_planner_set_tree_index(bmcts_planner* p, uint32_t tree_index);
+/* BehaviorUCT*::Plan(delta_time, observed_world) */
+int bmcts_planner_plan(bmcts_planner* p, double delta_time, double world_time, uint32_t ego_id,
+                       const bmcts_agent_state* agents, int n_agents, bmcts_plan_result* out);
+/* GetCurrentBeliefs()[agent_id]; returns the number of hypotheses written (<= max_h) */
+int bmcts_planner_get_beliefs(bmcts_planner* p, uint32_t agent_id, double* beliefs, int max_h);
+/* flattened root statistics of the last search (per action: visits, sum of returns, sum of
+ * cost[0], sum of cost[1]; then iterations, nodes): what root-parallel ranks all-reduce.
+ * Returns the number of doubles written. */
+int bmcts_planner_root_stats(bmcts_planner* p, double* stats, int max_n);
+/* re-decide the action from merged statistics (after the NCCL all-reduce) */
+int bmcts_planner_decide_from_root_stats(bmcts_planner* p, const double* stats, int n,
+                                         bmcts_plan_result* out);
+/* BehaviorHypothesis::ParameterSamplingProbability of hypothesis h */
+double bmcts_planner_parameter_sampling_probability(bmcts_planner* p, int h);
+const char* bmcts_planner_last_error(const bmcts_planner* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMCTS_PLANNER_C_H_ */

@@ -1,0 +1,189 @@
+// behavior_uct.hpp -- the drop-in planner surface: BehaviorUCTHypothesis,
+// BehaviorUCTRiskConstraint, BehaviorUCTCooperative with Plan(delta_time, observed_world),
+// Clone() and the reference's parameter keys and debug-info getters
+// (behavior_uct_base.hpp:29-55,71; behavior_uct_hypothesis.hpp:20-35;
+//  behavior_uct_risk_constraint.hpp:34-92; behavior_uct_cooperative.hpp:19-29),
+// over the POD ObservedWorld of world.hpp.  The tree search runs on the host
+// (mcts.hpp); leaf evaluation and expansion steps run on the GPU through the C ABI.
+#pragma once
+
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "evaluator.hpp"
+#include "mcts.hpp"
+#include "params.hpp"
+#include "statistics.hpp"
+#include "world.hpp"
+
+namespace bark_mcts_b200 {
+
+struct UctBaseDebugInfos {  // behavior_uct_base.hpp:29-55
+  Policy GetLastReturnValues() const { return last_return_values_; }
+  std::vector<AgentId> GetLastNearestAgents() const { return last_nearest_agents_; }
+  unsigned GetLastNumIterations() const { return last_num_iterations_; }
+  unsigned GetLastNumNodes() const { return last_num_nodes_; }
+  double GetLastSolutionTime() const { return last_solution_time_; }
+  // tree shape (what the reference's tests derive from GetLastMctsEdgeInfo)
+  int GetLastMaxTreeDepth() const { return last_max_tree_depth_; }
+  std::vector<int> GetLastRootExpandedActions() const { return last_root_expanded_actions_; }
+  Policy last_return_values_;
+  std::vector<AgentId> last_nearest_agents_;
+  unsigned last_num_iterations_ = 0, last_num_nodes_ = 0;
+  double last_solution_time_ = 0.0;
+  int last_max_tree_depth_ = 0;
+  std::vector<int> last_root_expanded_actions_;
+};
+
+struct UctHypothesisDebugInfos {  // behavior_uct_hypothesis_base.hpp:21-25
+  Beliefs GetCurrentBeliefs() const { return current_beliefs_; }
+  Beliefs current_beliefs_;
+};
+
+using PolicySampled = std::pair<unsigned, Policy>;
+
+struct UctRiskConstraintDebugInfos {  // behavior_uct_risk_constraint.hpp:34-51
+  std::vector<double> GetLastScenarioRisk() const { return last_scenario_risk_; }
+  std::vector<double> GetLastExpectedRisk() const { return last_expected_risk_; }
+  PolicySampled GetLastPolicySampled() const { return last_policy_sampled_; }
+  std::map<std::string, Policy> GetLastCostValues() const { return last_cost_values_; }
+  PolicySampled last_policy_sampled_;
+  std::vector<double> last_expected_risk_, last_scenario_risk_;
+  std::map<std::string, Policy> last_cost_values_;
+};
+
+// risk_calculation::ScenarioRiskFunction reduced to what the planner calls
+// (behavior_uct_risk_constraint.cpp:51-72); the risk-function tooling itself is out of scope
+struct ScenarioRiskFunction {
+  virtual ~ScenarioRiskFunction() {}
+  virtual double CalculateIntegralValue(const BehaviorHypothesisIDM& hypothesis) const = 0;
+};
+using ScenarioRiskFunctionPtr = std::shared_ptr<ScenarioRiskFunction>;
+
+class BehaviorUCTBase : public UctBaseDebugInfos {
+ public:
+  BehaviorUCTBase(const ParamsPtr& params, int state_kind, int device);
+  BehaviorUCTBase(const ParamsPtr& params, int state_kind, std::shared_ptr<LeafEvaluator> evaluator);
+  virtual ~BehaviorUCTBase() {}
+
+  virtual Trajectory Plan(double min_planning_time, const ObservedWorld& observed_world) = 0;
+
+  unsigned GetLastMacroAction() const { return last_motion_idx_; }
+  Action GetLastAction() const { return last_action_; }
+  Trajectory GetLastTrajectory() const { return last_trajectory_; }
+  ParamsPtr GetParams() const { return params_; }
+  std::string GetPrimitiveName(unsigned action) const;
+  // behavior_uct_base.cpp:54-64: ego + the MaxNearestAgents nearest agents
+  ObservedWorld FilterAgents(const ObservedWorld& observed_world) const;
+  // statistics of the last search at the root, mergeable over root-parallel ranks
+  RootStats GetLastRootStats() const { return last_root_stats_; }
+  // re-decide from externally merged statistics (NCCL all-reduce over ranks)
+  virtual void DecideFromRootStats(const RootStats& merged);
+  uint64_t EngineLaunchCount() const { return evaluator_ ? evaluator_->LaunchCount() : 0; }
+  const MctsParameters& mcts_parameters() const { return mcts_parameters_; }
+  void set_tree_index(unsigned i) { tree_index_ = i; }
+
+ protected:
+  struct SearchWorld {
+    bmcts_scenario scenario;
+    std::vector<AgentId> slot_ids;  // slot 0 = ego, then ascending AgentId
+    std::vector<float> pose;        // [A][4]
+    uint32_t alive = 0;
+  };
+  // scenario for a world: map + shapes + hypotheses + the ego's valid macro actions
+  SearchWorld BuildSearchWorld(const ObservedWorld& world,
+                               const std::vector<BehaviorHypothesisIDM>& hypotheses) const;
+  // the chosen macro action executed from the current state (ego_behavior_model_->Plan)
+  Trajectory MacroActionTrajectory(const SearchWorld& sw, unsigned action, double delta_time,
+                                   double t0, Action* last_action) const;
+  void FinishPlan(const SearchWorld& sw, const ObservedWorld& observed_world, unsigned best_action,
+                  double min_planning_time);
+
+  ParamsPtr params_;
+  int state_kind_;
+  std::shared_ptr<LeafEvaluator> evaluator_;
+  MctsParameters mcts_parameters_;
+  bmcts_config engine_config_;
+  unsigned max_nearest_agents_;
+  int constant_action_idx_;
+  unsigned last_motion_idx_ = 0;
+  unsigned tree_index_ = 0;
+  Action last_action_;
+  Trajectory last_trajectory_;
+  RootStats last_root_stats_;
+  int last_num_actions_ = 0;
+};
+
+// BehaviorUCTHypothesisBase<T> (behavior_uct_hypothesis_base.hpp:27-114)
+class BehaviorUCTHypothesisBase : public BehaviorUCTBase, public UctHypothesisDebugInfos {
+ public:
+  BehaviorUCTHypothesisBase(const ParamsPtr& params, const std::vector<BehaviorHypothesisIDM>& h,
+                            int state_kind, int device);
+  BehaviorUCTHypothesisBase(const ParamsPtr& params, const std::vector<BehaviorHypothesisIDM>& h,
+                            int state_kind, std::shared_ptr<LeafEvaluator> evaluator);
+  const HypothesisBeliefTracker& GetBeliefTracker() const { return belief_tracker_; }
+  std::vector<BehaviorHypothesisIDM> GetBehaviorHypotheses() const { return behavior_hypotheses_; }
+  // behavior_uct_hypothesis_base.hpp:92-114 (all agents, not only the filtered ones)
+  void UpdateBeliefs(const ObservedWorld& observed_world);
+
+ protected:
+  Mcts::HypothesisSampler MakeSampler(const SearchWorld& sw);
+  std::vector<BehaviorHypothesisIDM> behavior_hypotheses_;
+  bool use_true_behaviors_as_hypothesis_;
+  HypothesisBeliefTracker belief_tracker_;
+  std::shared_ptr<ObservedWorld> last_world_;
+};
+
+class BehaviorUCTHypothesis : public BehaviorUCTHypothesisBase {
+ public:
+  BehaviorUCTHypothesis(const ParamsPtr& params, const std::vector<BehaviorHypothesisIDM>& h,
+                        int device = 0)
+      : BehaviorUCTHypothesisBase(params, h, BMCTS_STATE_HYPOTHESIS, device) {}
+  BehaviorUCTHypothesis(const ParamsPtr& params, const std::vector<BehaviorHypothesisIDM>& h,
+                        std::shared_ptr<LeafEvaluator> evaluator)
+      : BehaviorUCTHypothesisBase(params, h, BMCTS_STATE_HYPOTHESIS, evaluator) {}
+  Trajectory Plan(double min_planning_time, const ObservedWorld& observed_world) override;
+  std::shared_ptr<BehaviorUCTBase> Clone() const {
+    return std::make_shared<BehaviorUCTHypothesis>(*this);
+  }
+};
+
+class BehaviorUCTRiskConstraint : public BehaviorUCTHypothesisBase,
+                                  public UctRiskConstraintDebugInfos {
+ public:
+  BehaviorUCTRiskConstraint(const ParamsPtr& params, const std::vector<BehaviorHypothesisIDM>& h,
+                            const ScenarioRiskFunctionPtr& scenario_risk_function, int device = 0);
+  BehaviorUCTRiskConstraint(const ParamsPtr& params, const std::vector<BehaviorHypothesisIDM>& h,
+                            const ScenarioRiskFunctionPtr& scenario_risk_function,
+                            std::shared_ptr<LeafEvaluator> evaluator);
+  Trajectory Plan(double min_planning_time, const ObservedWorld& observed_world) override;
+  void DecideFromRootStats(const RootStats& merged) override;
+  std::shared_ptr<BehaviorUCTBase> Clone() const {
+    return std::make_shared<BehaviorUCTRiskConstraint>(*this);
+  }
+  ScenarioRiskFunctionPtr GetScenarioRiskFunction() const { return scenario_risk_function_; }
+  double CalculateAvailableScenarioRisk() const;  // behavior_uct_risk_constraint.cpp:51-72
+
+ protected:
+  void InitRisk();
+  std::vector<double> default_available_risk_, current_scenario_risk_;
+  bool estimate_scenario_risk_, initialized_available_risk_, update_scenario_risk_;
+  ScenarioRiskFunctionPtr scenario_risk_function_;
+  std::vector<double> last_lambdas_;
+};
+
+class BehaviorUCTCooperative : public BehaviorUCTBase {
+ public:
+  explicit BehaviorUCTCooperative(const ParamsPtr& params, int device = 0)
+      : BehaviorUCTBase(params, BMCTS_STATE_COOPERATIVE, device) {}
+  BehaviorUCTCooperative(const ParamsPtr& params, std::shared_ptr<LeafEvaluator> evaluator)
+      : BehaviorUCTBase(params, BMCTS_STATE_COOPERATIVE, evaluator) {}
+  Trajectory Plan(double min_planning_time, const ObservedWorld& observed_world) override;
+  std::shared_ptr<BehaviorUCTBase> Clone() const {
+    return std::make_shared<BehaviorUCTCooperative>(*this);
+  }
+};
+
+}  // namespace bark_mcts_b200

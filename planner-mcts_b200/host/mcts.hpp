@@ -1,0 +1,437 @@
+// mcts.hpp -- host tree search, wave-batched over the rollout engine.
+//
+// Restates mamcts mcts::Mcts<S, SE, SO, H>::search / iterate and StageNode::select_or_expand
+// (SURVEY.md section 3.1 and Appendix B).  The difference to the reference is the seam: an
+// iteration does not call S::execute and H::calculate_heuristic_values itself; a WAVE of
+// iterations is selected first (virtual visits keep them apart), their expansions +
+// rollouts go to the engine as ONE batch (LeafEvaluator::ExpandRollout), and the results
+// are backed up in selection order.  WAVE_SIZE = 1 is the strictly sequential search.
+#pragma once
+
+#include <chrono>
+#include <functional>
+#include <map>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <vector>
+
+#include "evaluator.hpp"
+#include "statistics.hpp"
+
+namespace bark_mcts_b200 {
+
+enum class EgoMode { kUct, kCostConstrained };
+enum class OtherMode { kHypothesis, kUct };
+
+struct RootStats {  // what root-parallel trees / ranks merge (mamcts merge_node_statistics)
+  std::vector<double> count, ret_sum, cost0_sum, cost1_sum;
+  double iterations = 0, nodes = 0;
+  void Resize(int n) {
+    count.assign(n, 0.0);
+    ret_sum.assign(n, 0.0);
+    cost0_sum.assign(n, 0.0);
+    cost1_sum.assign(n, 0.0);
+  }
+  void Add(const RootStats& o) {
+    for (size_t i = 0; i < count.size() && i < o.count.size(); ++i) {
+      count[i] += o.count[i];
+      ret_sum[i] += o.ret_sum[i];
+      cost0_sum[i] += o.cost0_sum[i];
+      cost1_sum[i] += o.cost1_sum[i];
+    }
+    iterations += o.iterations;
+    nodes += o.nodes;
+  }
+  std::vector<double> Flatten() const {
+    std::vector<double> f;
+    for (const auto* v : {&count, &ret_sum, &cost0_sum, &cost1_sum}) f.insert(f.end(), v->begin(), v->end());
+    f.push_back(iterations);
+    f.push_back(nodes);
+    return f;
+  }
+  void Unflatten(const std::vector<double>& f) {
+    const size_t n = count.size();
+    for (size_t i = 0; i < n; ++i) {
+      count[i] = f[i];
+      ret_sum[i] = f[n + i];
+      cost0_sum[i] = f[2 * n + i];
+      cost1_sum[i] = f[3 * n + i];
+    }
+    iterations = f[4 * n];
+    nodes = f[4 * n + 1];
+  }
+};
+
+struct Node {
+  Node* parent = nullptr;
+  unsigned state_depth = 1;  // MctsStateBase::depth_
+  int tree_depth = 0;
+  std::vector<float> pose;   // [A][4]
+  uint32_t alive = 0;
+  bool terminal = false;
+  UctStatistic ego_uct;
+  CostConstrainedStatistic ego_cc;
+  std::vector<HypothesisStatistic> other_hyp;  // per agent slot (slot 0 unused)
+  std::vector<UctStatistic> other_uct;
+  std::map<std::vector<ActionKey>, Node*> children;
+  std::vector<double> edge_reward;  // rewards[] of the execute() that created this node
+  double edge_cost[2] = {0.0, 0.0};
+};
+
+class Mcts {
+ public:
+  Mcts(const MctsParameters& params, EgoMode ego_mode, OtherMode other_mode, int num_agents,
+       int num_ego_actions, int num_hypotheses, int num_costs, LeafEvaluator* evaluator,
+       unsigned tree_index = 0)
+      : p_(params), ego_mode_(ego_mode), other_mode_(other_mode), A_(num_agents),
+        n_actions_(num_ego_actions), H_(num_hypotheses), n_costs_(num_costs), eval_(evaluator),
+        tree_index_(tree_index), gen_(params.RANDOM_SEED + tree_index),
+        lambdas_(params.cost_constrained_statistic.LAMBDAS) {
+    lambdas_.resize(std::max(1, n_costs_), lambdas_.empty() ? 1.0 : lambdas_.back());
+  }
+
+  // hypothesis sampler: fills hyp[slot] for slots 1..A-1 (root-belief sampling); may be null
+  using HypothesisSampler = std::function<void(std::vector<uint8_t>*)>;
+
+  void Search(const std::vector<float>& root_pose, uint32_t root_alive, unsigned root_depth,
+              const HypothesisSampler& sample_hypotheses) {
+    using clock = std::chrono::steady_clock;
+    const auto t0 = clock::now();
+    nodes_.clear();
+    root_ = NewNode(nullptr, root_pose, root_alive, root_depth, false);
+    iterations_ = 0;
+    max_tree_depth_ = 0;
+    const long wave = std::max<long>(1, p_.WAVE_SIZE);
+    while (iterations_ < p_.MAX_NUMBER_OF_ITERATIONS) {
+      const double ms = std::chrono::duration<double, std::milli>(clock::now() - t0).count();
+      if (iterations_ > 0 && ms > (double)p_.MAX_SEARCH_TIME) break;
+      const int w = (int)std::min<long>(wave, p_.MAX_NUMBER_OF_ITERATIONS - iterations_);
+      RunWave(w, sample_hypotheses);
+    }
+    search_time_ms_ = std::chrono::duration<double, std::milli>(clock::now() - t0).count();
+  }
+
+  RootStats GetRootStats() const {
+    RootStats s;
+    s.Resize(n_actions_);
+    const UctStatistic& r = ego_mode_ == EgoMode::kUct ? root_->ego_uct : root_->ego_cc.reward_statistic();
+    for (int a = 0; a < n_actions_; ++a) {
+      s.count[a] = r.pairs()[a].count;
+      s.ret_sum[a] = r.pairs()[a].value * r.pairs()[a].count;
+      if (ego_mode_ == EgoMode::kCostConstrained) {
+        s.cost0_sum[a] = root_->ego_cc.cost_statistic(0).pairs()[a].value * r.pairs()[a].count;
+        if (n_costs_ > 1)
+          s.cost1_sum[a] = root_->ego_cc.cost_statistic(1).pairs()[a].value * r.pairs()[a].count;
+      }
+    }
+    s.iterations = (double)iterations_;
+    s.nodes = (double)nodes_.size();
+    return s;
+  }
+
+  long numIterations() const { return iterations_; }
+  size_t numNodes() const { return nodes_.size(); }
+  double searchTime() const { return search_time_ms_; }
+  int maxTreeDepth() const { return max_tree_depth_; }
+  const Node& get_root() const { return *root_; }
+  const std::vector<double>& lambdas() const { return lambdas_; }
+  void set_cost_constraints(const std::vector<double>& c) { constraints_ = c; }
+  // number of distinct actions expanded at the root per agent slot (tree-shape tests)
+  std::vector<int> RootExpandedActions() const {
+    std::vector<int> n(A_, 0);
+    for (int a = 0; a < n_actions_; ++a) {
+      const UctStatistic& r = ego_mode_ == EgoMode::kUct ? root_->ego_uct : root_->ego_cc.reward_statistic();
+      n[0] += r.pairs()[a].count > 0;
+    }
+    for (int s = 1; s < A_; ++s) {
+      if (other_mode_ == OtherMode::kHypothesis) {
+        n[s] = root_->other_hyp[s].NumExpandedActions();
+      } else {
+        for (const auto& pr : root_->other_uct[s].pairs()) n[s] += pr.count > 0;
+      }
+    }
+    return n;
+  }
+
+ private:
+  struct PathStep {
+    Node* node = nullptr;
+    int ego_action = 0;
+    std::vector<int> other_idx;       // HypothesisStatistic entry index / UCT action per slot
+    std::vector<uint8_t> other_new;   // entry was created by this selection
+  };
+  struct Selection {
+    std::vector<PathStep> path;  // path.back() is the expansion step (unless no_expand)
+    std::vector<uint8_t> hyp;    // sampled hypothesis per slot for this iteration
+    bool needs_engine = false;
+    Node* reached = nullptr;     // existing terminal / max-depth node reached instead
+  };
+
+  Node* NewNode(Node* parent, const std::vector<float>& pose, uint32_t alive, unsigned state_depth,
+                bool terminal) {
+    nodes_.emplace_back(new Node());
+    Node* n = nodes_.back().get();
+    n->parent = parent;
+    n->tree_depth = parent ? parent->tree_depth + 1 : 0;
+    max_tree_depth_ = std::max(max_tree_depth_, n->tree_depth);
+    n->state_depth = state_depth;
+    n->pose = pose;
+    n->alive = alive;
+    n->terminal = terminal;
+    n->edge_reward.assign(A_, 0.0);
+    if (ego_mode_ == EgoMode::kUct) {
+      n->ego_uct.Init(n_actions_, p_.uct_statistic.LOWER_BOUND, p_.uct_statistic.UPPER_BOUND,
+                      p_.uct_statistic.EXPLORATION_CONSTANT, p_.DISCOUNT_FACTOR,
+                      p_.USE_BOUND_ESTIMATION);
+    } else {
+      MctsParameters q = p_;
+      q.cost_constrained_statistic.COST_CONSTRAINTS = constraints_;
+      n->ego_cc.Init(n_actions_, n_costs_, q);
+    }
+    if (other_mode_ == OtherMode::kHypothesis) {
+      n->other_hyp.assign(A_, HypothesisStatistic());
+      for (int s = 1; s < A_; ++s) n->other_hyp[s].Init(H_, p_);
+    } else {
+      n->other_uct.assign(A_, UctStatistic());
+      for (int s = 1; s < A_; ++s)
+        n->other_uct[s].Init(n_actions_, p_.uct_statistic.LOWER_BOUND, p_.uct_statistic.UPPER_BOUND,
+                             p_.uct_statistic.EXPLORATION_CONSTANT, p_.DISCOUNT_FACTOR,
+                             p_.USE_BOUND_ESTIMATION);
+    }
+    return n;
+  }
+
+  // StageNode::select_or_expand down the tree for one iteration
+  Selection Select(const HypothesisSampler& sample_hypotheses) {
+    Selection sel;
+    sel.hyp.assign(A_, 0);
+    if (sample_hypotheses) sample_hypotheses(&sel.hyp);
+    Node* node = root_;
+    for (;;) {
+      if (node->terminal || node->tree_depth >= p_.MAX_SEARCH_DEPTH) {
+        sel.reached = node;
+        return sel;
+      }
+      PathStep st;
+      st.node = node;
+      st.other_idx.assign(A_, -1);
+      st.other_new.assign(A_, 0);
+      st.ego_action = ego_mode_ == EgoMode::kUct ? node->ego_uct.ChooseNextAction(gen_)
+                                                 : node->ego_cc.ChooseNextAction(lambdas_, gen_);
+      std::vector<ActionKey> joint(A_, 0);
+      joint[0] = (ActionKey)st.ego_action;
+      bool all_resolved = true;
+      for (int s = 1; s < A_; ++s) {
+        if (!((node->alive >> s) & 1u)) {
+          joint[s] = ~ActionKey(0);
+          continue;
+        }
+        if (other_mode_ == OtherMode::kHypothesis) {
+          bool is_new = false;
+          int idx = node->other_hyp[s].ChooseNextAction(sel.hyp[s], gen_, next_draw_id_++, &is_new);
+          st.other_idx[s] = idx;
+          st.other_new[s] = is_new;
+          if (is_new)
+            all_resolved = false;
+          else
+            joint[s] = node->other_hyp[s].table(sel.hyp[s])[idx].key;
+        } else {
+          st.other_idx[s] = node->other_uct[s].ChooseNextAction(gen_);
+          joint[s] = (ActionKey)st.other_idx[s];
+        }
+      }
+      sel.path.push_back(st);
+      if (all_resolved) {
+        auto it = node->children.find(joint);
+        if (it != node->children.end()) {
+          node = it->second;
+          continue;
+        }
+      }
+      sel.needs_engine = true;
+      return sel;
+    }
+  }
+
+  void RunWave(int w, const HypothesisSampler& sample_hypotheses) {
+    std::vector<Selection> sels;
+    sels.reserve(w);
+    for (int i = 0; i < w; ++i) sels.push_back(Select(sample_hypotheses));
+    std::vector<int> slot(w, -1);
+    int n_engine = 0;
+    for (int i = 0; i < w; ++i)
+      if (sels[i].needs_engine) slot[i] = n_engine++;
+    if (n_engine > 0) {
+      wave_.resize(n_engine, A_);
+      for (int i = 0; i < w; ++i) {
+        if (slot[i] < 0) continue;
+        const int k = slot[i];
+        const PathStep& st = sels[i].path.back();
+        const Node* nd = st.node;
+        wave_.alive[k] = nd->alive;
+        wave_.depth[k] = (uint16_t)std::min<unsigned>(nd->state_depth, BMCTS_MAX_DEPTH - 1);
+        for (int a = 0; a < A_; ++a) {
+          const size_t e = wave_.at(a, k);
+          for (int f = 0; f < 4; ++f) wave_.pose[e * 4 + f] = nd->pose[(size_t)a * 4 + f];
+          wave_.hyp_id[e] = sels[i].hyp[a];
+          if (a == 0) {
+            wave_.action[e] = (uint8_t)st.ego_action;
+          } else if (st.other_idx[a] >= 0) {
+            if (other_mode_ == OtherMode::kHypothesis)
+              wave_.draw_id[e] = nd->other_hyp[a].table(sels[i].hyp[a])[st.other_idx[a]].draw_id;
+            else
+              wave_.action[e] = (uint8_t)st.other_idx[a];
+          }
+        }
+      }
+      const uint64_t first_id = rollout_counter_;
+      rollout_counter_ += (uint64_t)n_engine;
+      int stc = eval_->ExpandRollout(wave_, p_.RANDOM_SEED, tree_index_, first_id);
+      if (stc != BMCTS_OK)
+        throw std::runtime_error("rollout engine failed: " + eval_->LastError());
+    }
+    for (int i = 0; i < w; ++i) {
+      Backup(sels[i], slot[i]);
+      iterations_++;
+      if (ego_mode_ == EgoMode::kCostConstrained) UpdateLambdas();
+    }
+  }
+
+  void SetHeuristic(Node* n, double ret, const double* cost, const float* ret_agents, int k) {
+    if (ego_mode_ == EgoMode::kUct)
+      n->ego_uct.UpdateFromHeuristic(ret);
+    else
+      n->ego_cc.UpdateFromHeuristic(ret, cost);
+    for (int s = 1; s < A_; ++s) {
+      if (other_mode_ == OtherMode::kHypothesis)
+        n->other_hyp[s].UpdateFromHeuristic(cost[0]);
+      else
+        n->other_uct[s].UpdateFromHeuristic(ret_agents ? (double)ret_agents[wave_.at(s, k)] : 0.0);
+    }
+  }
+
+  void Backup(Selection& sel, int k) {
+    Node* leaf = sel.reached;
+    std::vector<int> resolved_idx;
+    if (sel.needs_engine) {
+      PathStep& st = sel.path.back();
+      Node* parent = st.node;
+      // resolve the others' newly planned actions and build the joint action key
+      std::vector<ActionKey> joint(A_, 0);
+      joint[0] = (ActionKey)st.ego_action;
+      for (int s = 1; s < A_; ++s) {
+        if (st.other_idx[s] < 0) {
+          joint[s] = ~ActionKey(0);
+          continue;
+        }
+        if (other_mode_ == OtherMode::kHypothesis) {
+          const int h = sel.hyp[s];
+          if (st.other_new[s]) {
+            ActionKey key = KeyOfAcceleration(wave_.last_action[wave_.at(s, k)]);
+            st.other_idx[s] = parent->other_hyp[s].Resolve(h, st.other_idx[s], key);
+          }
+          joint[s] = parent->other_hyp[s].table(h)[st.other_idx[s]].key;
+        } else {
+          joint[s] = (ActionKey)st.other_idx[s];
+        }
+      }
+      auto it = parent->children.find(joint);
+      if (it != parent->children.end()) {
+        leaf = it->second;  // same joint action expanded earlier (in this wave or by value merge)
+      } else {
+        std::vector<float> pose((size_t)A_ * 4);
+        for (int a = 0; a < A_; ++a)
+          for (int f = 0; f < 4; ++f) pose[(size_t)a * 4 + f] = wave_.next_pose[wave_.at(a, k) * 4 + f];
+        const bool terminal = (wave_.flags[k] & BMCTS_F_TERMINAL) != 0;
+        leaf = NewNode(parent, pose, wave_.next_alive[k], parent->state_depth + 1, terminal);
+        for (int a = 0; a < A_; ++a) leaf->edge_reward[a] = wave_.reward[wave_.at(a, k)];
+        leaf->edge_cost[0] = wave_.cost[k];
+        leaf->edge_cost[1] = wave_.cost[(size_t)wave_.n + k];
+        if ((long)nodes_.size() <= p_.MAX_NUMBER_OF_NODES) {
+          parent->children[joint] = leaf;
+        }  // beyond the node cap the child is evaluated but not linked (bounded memory)
+      }
+      const bmcts_rollout_result& r = wave_.result[k];
+      const double cost[2] = {r.cost0, r.cost1};
+      SetHeuristic(leaf, r.ret_ego, cost, wave_.ret_agents.data(), k);
+    } else {
+      // existing terminal (or depth-capped) node: RandomHeuristic returns a zero estimate
+      const double zero[2] = {0.0, 0.0};
+      SetHeuristicZero(leaf, zero);
+    }
+    // back-propagation child -> parent up to the root
+    Node* child = leaf;
+    for (int i = (int)sel.path.size() - 1; i >= 0; --i) {
+      PathStep& st = sel.path[i];
+      Node* n = st.node;
+      if (ego_mode_ == EgoMode::kUct) {
+        n->ego_uct.ReleasePending(st.ego_action);
+        n->ego_uct.UpdateStatistic(st.ego_action, child->edge_reward[0], child->ego_uct.latest_return());
+      } else {
+        n->ego_cc.ReleasePending(st.ego_action);
+        n->ego_cc.UpdateStatistic(st.ego_action, child->edge_reward[0], child->edge_cost, child->ego_cc);
+      }
+      for (int s = 1; s < A_; ++s) {
+        if (st.other_idx[s] < 0) continue;
+        if (other_mode_ == OtherMode::kHypothesis) {
+          const int h = sel.hyp[s];
+          n->other_hyp[s].ReleasePending(h, st.other_idx[s]);
+          n->other_hyp[s].UpdateStatistic(h, st.other_idx[s], child->edge_cost[0],
+                                          child->other_hyp[s].latest_ego_cost());
+        } else {
+          n->other_uct[s].ReleasePending(st.other_idx[s]);
+          n->other_uct[s].UpdateStatistic(st.other_idx[s], child->edge_reward[s],
+                                          child->other_uct[s].latest_return());
+        }
+      }
+      child = n;
+    }
+  }
+
+  void SetHeuristicZero(Node* n, const double* zero) {
+    if (ego_mode_ == EgoMode::kUct)
+      n->ego_uct.UpdateFromHeuristic(0.0);
+    else
+      n->ego_cc.UpdateFromHeuristic(0.0, zero);
+    for (int s = 1; s < A_; ++s) {
+      if (other_mode_ == OtherMode::kHypothesis)
+        n->other_hyp[s].UpdateFromHeuristic(0.0);
+      else
+        n->other_uct[s].UpdateFromHeuristic(0.0);
+    }
+  }
+
+  // CostConstrainedStatistic::update_statistic_parameters: sub-gradient step on lambda
+  void UpdateLambdas() {
+    const auto& c = p_.cost_constrained_statistic;
+    if (root_->ego_cc.total_visits() == 0) return;
+    auto pol = root_->ego_cc.GreedyPolicy(0.0, c.ACTION_FILTER_FACTOR, lambdas_, gen_);
+    const double range = std::max(1e-9, c.COST_UPPER_BOUND - c.COST_LOWER_BOUND);
+    const double lam_max = 1.0 / (std::max(1e-6, c.TAU_GRADIENT_CLIP) * std::max(1e-6, 1.0 - p_.DISCOUNT_FACTOR));
+    const double step = c.GRADIENT_UPDATE_STEP / (1.0 + 0.01 * (double)iterations_);
+    for (int i = 0; i < n_costs_ && i < (int)lambdas_.size(); ++i) {
+      const double q = root_->ego_cc.cost_statistic(i).pairs()[pol.first].value;
+      const double limit = i < (int)constraints_.size() ? constraints_[i] : 0.0;
+      lambdas_[i] = std::min(lam_max, std::max(0.0, lambdas_[i] + step * (q - limit) / range));
+    }
+  }
+
+  MctsParameters p_;
+  EgoMode ego_mode_;
+  OtherMode other_mode_;
+  int A_, n_actions_, H_, n_costs_;
+  LeafEvaluator* eval_;
+  unsigned tree_index_;
+  std::mt19937 gen_;
+  std::vector<double> lambdas_, constraints_;
+  std::vector<std::unique_ptr<Node>> nodes_;
+  Node* root_ = nullptr;
+  WaveBuffers wave_;
+  long iterations_ = 0;
+  int max_tree_depth_ = 0;
+  double search_time_ms_ = 0.0;
+  uint64_t next_draw_id_ = 1, rollout_counter_ = 0;
+};
+
+}  // namespace bark_mcts_b200

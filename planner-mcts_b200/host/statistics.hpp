@@ -1,0 +1,579 @@
+// statistics.hpp -- node statistics and belief tracker of the host tree search.
+//
+// Restatement of mamcts (github.com/juloberno/mamcts @b3e65e7, not vendored in the
+// reference; behaviour summarised in SURVEY.md Appendix B): UctStatistic,
+// HypothesisStatistic, CostConstrainedStatistic, HypothesisBeliefTracker.  Every
+// statistic additionally carries "pending" visit counts so that a wave of selections
+// can be made before their rollouts return (virtual visits); with a wave size of 1
+// they reduce to the sequential mamcts updates.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <map>
+#include <random>
+#include <vector>
+
+#include "params.hpp"
+#include "world.hpp"
+
+namespace bark_mcts_b200 {
+
+using ActionKey = uint64_t;
+
+inline ActionKey KeyOfAcceleration(float acc) {
+  // the reference addresses a continuous action by boost::hash of its value
+  // (action_store/behavior_action_store.hpp:62-76); the bit pattern serves the same purpose
+  uint32_t b;
+  std::memcpy(&b, &acc, 4);
+  return (ActionKey)b;
+}
+
+// ------------------------------------------------------------------ UctStatistic
+class UctStatistic {
+ public:
+  struct Pair {
+    unsigned count = 0;
+    unsigned pending = 0;
+    double value = 0.0;
+    bool expanded = false;
+  };
+
+  void Init(int num_actions, double lower, double upper, double exploration, double gamma,
+            bool bound_estimation) {
+    pairs_.assign(num_actions, Pair());
+    lower_ = lower;
+    upper_ = upper;
+    c_ = exploration;
+    gamma_ = gamma;
+    bound_estimation_ = bound_estimation;
+    unexpanded_.resize(num_actions);
+    for (int i = 0; i < num_actions; ++i) unexpanded_[i] = i;
+  }
+
+  int num_actions() const { return (int)pairs_.size(); }
+  bool all_expanded() const { return unexpanded_.empty(); }
+  unsigned total_visits() const { return total_visits_; }
+  double value() const { return value_; }
+  double latest_return() const { return latest_return_; }
+  const std::vector<Pair>& pairs() const { return pairs_; }
+
+  // mamcts UctStatistic::choose_next_action: random unexpanded action first, then UCB1
+  int ChooseNextAction(std::mt19937& gen) {
+    int a;
+    if (!unexpanded_.empty()) {
+      std::uniform_int_distribution<size_t> d(0, unexpanded_.size() - 1);
+      size_t i = d(gen);
+      a = unexpanded_[i];
+      unexpanded_.erase(unexpanded_.begin() + i);
+      pairs_[a].expanded = true;
+    } else {
+      a = UcbMaximizingAction();
+    }
+    pairs_[a].pending++;
+    total_pending_++;
+    return a;
+  }
+
+  int UcbMaximizingAction() const {
+    double lo = lower_, hi = upper_;
+    EstimatedBounds(&lo, &hi);
+    const double n_total = std::max(1.0, (double)(total_visits_ + total_pending_));
+    int best = 0;
+    double best_v = -std::numeric_limits<double>::infinity();
+    for (int a = 0; a < (int)pairs_.size(); ++a) {
+      const Pair& p = pairs_[a];
+      if (!p.expanded) continue;
+      const double n = (double)(p.count + p.pending);
+      double v;
+      if (n <= 0.0) {
+        v = std::numeric_limits<double>::max();
+      } else {
+        const double q = (hi > lo) ? (p.value - lo) / (hi - lo) : 0.0;
+        v = q + 2.0 * c_ * std::sqrt(2.0 * std::log(n_total) / n);
+      }
+      if (v > best_v) {
+        best_v = v;
+        best = a;
+      }
+    }
+    return best;
+  }
+
+  void ReleasePending(int a) {
+    if (pairs_[a].pending) pairs_[a].pending--;
+    if (total_pending_) total_pending_--;
+  }
+
+  // mamcts update_from_heuristic
+  void UpdateFromHeuristic(double heuristic_value) {
+    value_ = heuristic_value;
+    latest_return_ = heuristic_value;
+    total_visits_ += 1;
+  }
+
+  // mamcts update_statistic(changed_child_statistic)
+  void UpdateStatistic(int action, double collected_reward, double child_latest_return) {
+    Pair& p = pairs_[action];
+    latest_return_ = collected_reward + gamma_ * child_latest_return;
+    p.count += 1;
+    p.value += (latest_return_ - p.value) / p.count;
+    total_visits_ += 1;
+    value_ += (latest_return_ - value_) / total_visits_;
+  }
+
+  int BestAction() const {  // highest action value among visited actions
+    int best = 0;
+    double bv = -std::numeric_limits<double>::infinity();
+    for (int a = 0; a < (int)pairs_.size(); ++a)
+      if (pairs_[a].count > 0 && pairs_[a].value > bv) {
+        bv = pairs_[a].value;
+        best = a;
+      }
+    return best;
+  }
+
+  Policy GetPolicy() const {  // action -> action value ("last_return_values")
+    Policy pol;
+    for (int a = 0; a < (int)pairs_.size(); ++a)
+      if (pairs_[a].count > 0) pol[(unsigned)a] = pairs_[a].value;
+    return pol;
+  }
+
+  double Normalized(int a) const {
+    return (upper_ > lower_) ? (pairs_[a].value - lower_) / (upper_ - lower_) : 0.0;
+  }
+
+  // root-parallel merge (mamcts merge_node_statistics): visit-weighted means
+  void MergeRaw(int a, double count, double value_sum) {
+    Pair& p = pairs_[a];
+    p.count = (unsigned)count;
+    p.value = count > 0 ? value_sum / count : 0.0;
+    p.expanded = p.expanded || count > 0;
+  }
+
+ private:
+  void EstimatedBounds(double* lo, double* hi) const {
+    if (!bound_estimation_) return;
+    double mn = std::numeric_limits<double>::infinity(), mx = -mn;
+    int n = 0;
+    for (const Pair& p : pairs_)
+      if (p.count > 0) {
+        mn = std::min(mn, p.value);
+        mx = std::max(mx, p.value);
+        ++n;
+      }
+    if (n >= 2 && mx > mn) {
+      *lo = mn;
+      *hi = mx;
+    }
+  }
+
+  std::vector<Pair> pairs_;
+  std::vector<int> unexpanded_;
+  double lower_ = 0, upper_ = 1, c_ = 0.7, gamma_ = 0.9;
+  bool bound_estimation_ = true;
+  unsigned total_visits_ = 0, total_pending_ = 0;
+  double value_ = 0.0, latest_return_ = 0.0;
+};
+
+// -------------------------------------------------------------- HypothesisStatistic
+// Another agent's node statistic: per hypothesis a widening set of sampled actions
+// (each = one IDM parameter draw) with visit counts and the ego cost they led to.
+class HypothesisStatistic {
+ public:
+  struct Entry {
+    ActionKey key = 0;      // bit pattern of the applied acceleration, once resolved
+    uint64_t draw_id = 0;   // Philox id that reproduces the action (replaces the stored trajectory)
+    unsigned count = 0, pending = 0;
+    double ego_cost = 0.0;  // mean accumulated ego cost after this action
+    bool resolved = false;
+  };
+
+  void Init(int num_hypotheses, const MctsParameters& m) {
+    per_hyp_.assign(std::max(1, num_hypotheses), {});
+    visits_.assign(per_hyp_.size(), 0);
+    pending_.assign(per_hyp_.size(), 0);
+    k_ = m.hypothesis_statistic.PROGRESSIVE_WIDENING_K;
+    alpha_ = m.hypothesis_statistic.PROGRESSIVE_WIDENING_ALPHA;
+    hyp_based_ = m.hypothesis_statistic.PROGRESSIVE_WIDENING_HYPOTHESIS_BASED;
+    cost_based_ = m.hypothesis_statistic.COST_BASED_ACTION_SELECTION;
+    lo_ = m.hypothesis_statistic.LOWER_COST_BOUND;
+    hi_ = m.hypothesis_statistic.UPPER_COST_BOUND;
+    c_ = m.hypothesis_statistic.EXPLORATION_CONSTANT;
+    gamma_ = m.DISCOUNT_FACTOR;
+  }
+
+  // returns the index of the chosen entry in the table of hypothesis h; *is_new tells the
+  // caller to plan the action (S::plan_action_current_hypothesis) with entry.draw_id
+  int ChooseNextAction(int h, std::mt19937& gen, uint64_t fresh_draw_id, bool* is_new) {
+    std::vector<Entry>& tab = per_hyp_[h];
+    double n_vis, n_act;
+    if (hyp_based_) {
+      n_vis = visits_[h] + pending_[h];
+      n_act = (double)tab.size();
+    } else {
+      n_vis = 0;
+      n_act = 0;
+      for (size_t i = 0; i < per_hyp_.size(); ++i) {
+        n_vis += visits_[i] + pending_[i];
+        n_act += (double)per_hyp_[i].size();
+      }
+    }
+    bool any_resolved = false;
+    for (const Entry& e : tab) any_resolved = any_resolved || e.resolved;
+    // progressive widening: |actions| <= K * N^alpha
+    bool widen = n_act <= k_ * std::pow(n_vis, alpha_);
+    int idx;
+    if (widen || !any_resolved) {
+      Entry e;
+      e.draw_id = fresh_draw_id;
+      tab.push_back(e);
+      idx = (int)tab.size() - 1;
+      *is_new = true;
+    } else if (cost_based_) {
+      // worst case for the ego: UCB on the normalised ego cost (RMDP / RSBG)
+      idx = -1;
+      double best = -std::numeric_limits<double>::infinity();
+      const double n_total = std::max(1.0, n_vis);
+      for (int i = 0; i < (int)tab.size(); ++i) {
+        if (!tab[i].resolved) continue;
+        const double n = tab[i].count + tab[i].pending;
+        double v = (n <= 0) ? std::numeric_limits<double>::max()
+                            : (hi_ > lo_ ? (tab[i].ego_cost - lo_) / (hi_ - lo_) : 0.0) +
+                                  2.0 * c_ * std::sqrt(2.0 * std::log(n_total) / n);
+        if (v > best) {
+          best = v;
+          idx = i;
+        }
+      }
+      *is_new = false;
+    } else {
+      // stochastic behaviour model: re-sample among the expanded actions by visit count
+      std::vector<double> w;
+      for (const Entry& e : tab) w.push_back(e.resolved ? (double)(e.count + e.pending) + 1e-9 : 0.0);
+      std::discrete_distribution<int> d(w.begin(), w.end());
+      idx = d(gen);
+      *is_new = false;
+    }
+    tab[idx].pending++;
+    pending_[h]++;
+    return idx;
+  }
+
+  // the planned action of a new entry is known: resolve its key; merge with an existing
+  // entry that carries the same action (the reference keys the action store by value)
+  int Resolve(int h, int idx, ActionKey key) {
+    std::vector<Entry>& tab = per_hyp_[h];
+    for (int i = 0; i < (int)tab.size(); ++i)
+      if (i != idx && tab[i].resolved && tab[i].key == key) {
+        tab[i].pending += tab[idx].pending;
+        tab[idx].pending = 0;
+        tab[idx].resolved = false;  // dead entry: never selected again
+        tab[idx].key = ~ActionKey(0);
+        dead_++;
+        return i;
+      }
+    tab[idx].key = key;
+    tab[idx].resolved = true;
+    return idx;
+  }
+
+  void ReleasePending(int h, int idx) {
+    if (per_hyp_[h][idx].pending) per_hyp_[h][idx].pending--;
+    if (pending_[h]) pending_[h]--;
+  }
+
+  void UpdateFromHeuristic(double ego_cost) { latest_ego_cost_ = ego_cost; }
+
+  void UpdateStatistic(int h, int idx, double collected_ego_cost, double child_latest_ego_cost) {
+    Entry& e = per_hyp_[h][idx];
+    latest_ego_cost_ = collected_ego_cost + gamma_ * child_latest_ego_cost;
+    e.count += 1;
+    e.ego_cost += (latest_ego_cost_ - e.ego_cost) / e.count;
+    visits_[h] += 1;
+  }
+
+  double latest_ego_cost() const { return latest_ego_cost_; }
+  const std::vector<Entry>& table(int h) const { return per_hyp_[h]; }
+  int num_hypotheses() const { return (int)per_hyp_.size(); }
+  int NumExpandedActions() const {  // distinct resolved actions over all hypotheses
+    std::vector<ActionKey> keys;
+    for (const auto& tab : per_hyp_)
+      for (const Entry& e : tab)
+        if (e.resolved) keys.push_back(e.key);
+    std::sort(keys.begin(), keys.end());
+    return (int)(std::unique(keys.begin(), keys.end()) - keys.begin());
+  }
+
+ private:
+  std::vector<std::vector<Entry>> per_hyp_;
+  std::vector<unsigned> visits_, pending_;
+  double k_ = 4, alpha_ = 0.25, lo_ = 0, hi_ = 1, c_ = 0.7, gamma_ = 0.9;
+  bool hyp_based_ = true, cost_based_ = false;
+  double latest_ego_cost_ = 0.0;
+  unsigned dead_ = 0;
+};
+
+// --------------------------------------------------------- CostConstrainedStatistic
+// Ego statistic of BehaviorUCTRiskConstraint: reward UCT + one UCT per cost channel and
+// a Lagrange multiplier per constraint (cost-constrained MCTS, CC-MCP style).
+class CostConstrainedStatistic {
+ public:
+  void Init(int num_actions, int num_costs, const MctsParameters& m) {
+    const auto& c = m.cost_constrained_statistic;
+    reward_.Init(num_actions, c.REWARD_LOWER_BOUND, c.REWARD_UPPER_BOUND, 0.0, m.DISCOUNT_FACTOR,
+                 false);
+    costs_.assign(num_costs, UctStatistic());
+    for (auto& s : costs_)
+      s.Init(num_actions, c.COST_LOWER_BOUND, c.COST_UPPER_BOUND, 0.0, m.DISCOUNT_FACTOR, false);
+    kappa_ = c.KAPPA;
+    filter_ = c.ACTION_FILTER_FACTOR;
+    constraints_ = c.COST_CONSTRAINTS;
+    constraints_.resize(num_costs, 0.0);
+    step_cost_sum_.assign(num_actions, std::vector<double>(num_costs, 0.0));
+    step_cost_n_.assign(num_actions, 0);
+    min_visits_ready_ = c.MIN_VISITS_POLICY_READY;
+    unexpanded_.resize(num_actions);
+    for (int i = 0; i < num_actions; ++i) unexpanded_[i] = i;
+    pending_.assign(num_actions, 0);
+  }
+
+  int num_actions() const { return reward_.num_actions(); }
+  int num_costs() const { return (int)costs_.size(); }
+  const UctStatistic& reward_statistic() const { return reward_; }
+  const UctStatistic& cost_statistic(int i) const { return costs_[i]; }
+  UctStatistic& reward_statistic() { return reward_; }
+  UctStatistic& cost_statistic(int i) { return costs_[i]; }
+  unsigned total_visits() const { return reward_.total_visits(); }
+
+  bool policy_is_ready() const {
+    if (min_visits_ready_ < 0) return unexpanded_.empty();
+    return (long)reward_.total_visits() >= min_visits_ready_;
+  }
+
+  int ChooseNextAction(const std::vector<double>& lambdas, std::mt19937& gen) {
+    int a;
+    if (!policy_is_ready() && !unexpanded_.empty()) {
+      std::uniform_int_distribution<size_t> d(0, unexpanded_.size() - 1);
+      size_t i = d(gen);
+      a = unexpanded_[i];
+      unexpanded_.erase(unexpanded_.begin() + i);
+    } else {
+      a = GreedyPolicy(kappa_, filter_, lambdas, gen).first;
+      auto it = std::find(unexpanded_.begin(), unexpanded_.end(), a);
+      if (it != unexpanded_.end()) unexpanded_.erase(it);
+    }
+    pending_[a]++;
+    total_pending_++;
+    return a;
+  }
+
+  void ReleasePending(int a) {
+    if (pending_[a]) pending_[a]--;
+    if (total_pending_) total_pending_--;
+  }
+
+  // greedy_policy(kappa, action_filter_factor): near-optimal action set under the
+  // Lagrangian value, then the stochastic mix that meets the first cost constraint
+  // (closed form of the two-action LP the reference solves with OR-tools)
+  std::pair<int, Policy> GreedyPolicy(double kappa, double filter,
+                                      const std::vector<double>& lambdas, std::mt19937& gen) const {
+    const int n = num_actions();
+    const double n_total = std::max(2.0, (double)(reward_.total_visits() + total_pending_));
+    std::vector<double> lag(n, -std::numeric_limits<double>::infinity()), ucb(n, lag[0]);
+    std::vector<double> cnt(n, 0.0);
+    int a_star = -1;
+    for (int a = 0; a < n; ++a) {
+      cnt[a] = reward_.pairs()[a].count + pending_[a];
+      if (reward_.pairs()[a].count == 0) {
+        if (kappa > 0 && cnt[a] == 0) {  // never tried: explore first
+          ucb[a] = std::numeric_limits<double>::max();
+          if (a_star < 0 || ucb[a] > ucb[a_star]) a_star = a;
+        }
+        continue;
+      }
+      double v = reward_.Normalized(a);
+      for (int i = 0; i < num_costs(); ++i)
+        v -= (i < (int)lambdas.size() ? lambdas[i] : 0.0) * costs_[i].Normalized(a);
+      lag[a] = v;
+      ucb[a] = v + kappa * std::sqrt(std::log(n_total) / std::max(1.0, cnt[a]));
+      if (a_star < 0 || ucb[a] > ucb[a_star]) a_star = a;
+    }
+    Policy pol;
+    if (a_star < 0) {  // nothing visited yet: uniform
+      for (int a = 0; a < n; ++a) pol[(unsigned)a] = 1.0 / n;
+      std::uniform_int_distribution<int> d(0, n - 1);
+      return {d(gen), pol};
+    }
+    if (reward_.pairs()[a_star].count == 0) {
+      pol[(unsigned)a_star] = 1.0;
+      return {a_star, pol};
+    }
+    auto conf = [&](int a) { return std::sqrt(std::log(std::max(2.0, cnt[a])) / std::max(1.0, cnt[a])); };
+    std::vector<int> near;
+    for (int a = 0; a < n; ++a) {
+      if (reward_.pairs()[a].count == 0) continue;
+      if (std::fabs(ucb[a] - ucb[a_star]) <= filter * (conf(a) + conf(a_star))) near.push_back(a);
+    }
+    const double c0 = constraints_.empty() ? 0.0 : constraints_[0];
+    auto qc = [&](int a) { return costs_.empty() ? 0.0 : costs_[0].pairs()[a].value; };
+    if (costs_.empty() || qc(a_star) <= c0 || near.size() < 2) {
+      pol[(unsigned)a_star] = 1.0;
+      return {a_star, pol};
+    }
+    int a_min = near[0];
+    for (int a : near)
+      if (qc(a) < qc(a_min)) a_min = a;
+    if (a_min == a_star || qc(a_min) >= c0) {
+      pol[(unsigned)a_min] = 1.0;
+      return {a_min, pol};
+    }
+    const double p_min = (qc(a_star) - c0) / (qc(a_star) - qc(a_min));
+    pol[(unsigned)a_min] = p_min;
+    pol[(unsigned)a_star] = 1.0 - p_min;
+    std::uniform_real_distribution<double> u(0.0, 1.0);
+    return {u(gen) < p_min ? a_min : a_star, pol};
+  }
+
+  std::vector<double> ExpectedPolicyCost(const Policy& pol) const {
+    std::vector<double> e(num_costs(), 0.0);
+    for (const auto& kv : pol)
+      for (int i = 0; i < num_costs(); ++i) e[i] += kv.second * costs_[i].pairs()[kv.first].value;
+    return e;
+  }
+
+  // calc_updated_constraints_based_on_policy: the budget left after executing the sampled
+  // action = its expected cumulative cost plus the unused slack, minus the mean cost of the
+  // step itself, carried one discount step forward
+  std::vector<double> UpdatedConstraints(const std::pair<int, Policy>& sampled,
+                                         const std::vector<double>& current, double gamma) const {
+    std::vector<double> expected = ExpectedPolicyCost(sampled.second);
+    std::vector<double> out(current.size(), 0.0);
+    const int a = sampled.first;
+    for (size_t i = 0; i < current.size() && (int)i < num_costs(); ++i) {
+      const double slack = std::max(0.0, current[i] - expected[i]);
+      const double step = step_cost_n_[a] ? step_cost_sum_[a][i] / step_cost_n_[a] : 0.0;
+      out[i] = (costs_[i].pairs()[a].value + slack - step) / std::max(gamma, 1e-6);
+    }
+    return out;
+  }
+
+  void UpdateFromHeuristic(double ret, const double* cost) {
+    reward_.UpdateFromHeuristic(ret);
+    for (int i = 0; i < num_costs(); ++i) costs_[i].UpdateFromHeuristic(cost[i]);
+  }
+
+  void UpdateStatistic(int action, double reward, const double* cost,
+                       const CostConstrainedStatistic& child) {
+    reward_.UpdateStatistic(action, reward, child.reward_.latest_return());
+    for (int i = 0; i < num_costs(); ++i) {
+      costs_[i].UpdateStatistic(action, cost[i], child.costs_[i].latest_return());
+      step_cost_sum_[action][i] += cost[i];
+    }
+    step_cost_n_[action]++;
+  }
+
+  void set_constraints(const std::vector<double>& c) {
+    constraints_ = c;
+    constraints_.resize(num_costs(), 0.0);
+  }
+
+ private:
+  UctStatistic reward_;
+  std::vector<UctStatistic> costs_;
+  std::vector<double> constraints_;
+  std::vector<std::vector<double>> step_cost_sum_;
+  std::vector<unsigned> step_cost_n_;
+  std::vector<int> unexpanded_;
+  std::vector<unsigned> pending_;
+  unsigned total_pending_ = 0;
+  double kappa_ = 10.0, filter_ = 0.5;
+  long min_visits_ready_ = -1;
+};
+
+// ----------------------------------------------------------- HypothesisBeliefTracker
+class HypothesisBeliefTracker {
+ public:
+  explicit HypothesisBeliefTracker(const MctsParameters& m)
+      : p_(m.hypothesis_belief_tracker), gen_(m.hypothesis_belief_tracker.RANDOM_SEED_HYPOTHESIS_SAMPLING) {}
+
+  bool beliefs_initialized() const { return !beliefs_.empty(); }
+  const Beliefs& get_beliefs() const { return beliefs_; }
+  void update_fixed_hypothesis_set(const std::map<AgentId, unsigned>& fixed) { fixed_ = fixed; }
+
+  // belief_update(prev, cur): probs[agent][h] = prev.get_probability(h, agent, cur.last_action)
+  void belief_update(const std::map<AgentId, std::vector<double>>& probs) {
+    for (const auto& kv : probs) {
+      const AgentId id = kv.first;
+      const size_t H = kv.second.size();
+      auto& hist = history_[id];
+      if (hist.size() != H) hist.assign(H, std::deque<double>());
+      for (size_t h = 0; h < H; ++h) {
+        hist[h].push_back(kv.second[h]);
+        while (hist[h].size() > p_.HISTORY_LENGTH) hist[h].pop_front();
+      }
+      std::vector<double> post(H, 0.0);
+      double sum = 0.0;
+      for (size_t h = 0; h < H; ++h) {
+        const double prior = 1.0 / (double)H;
+        double v;
+        if (p_.POSTERIOR_TYPE == 0) {  // product of the remembered likelihoods
+          v = prior;
+          for (double q : hist[h]) v *= q;
+        } else {  // discounted sum, newest weighted 1
+          v = 0.0;
+          double w = 1.0;
+          for (auto it = hist[h].rbegin(); it != hist[h].rend(); ++it) {
+            v += w * (*it);
+            w *= p_.PROBABILITY_DISCOUNT;
+          }
+          v *= prior;
+        }
+        post[h] = v;
+        sum += v;
+      }
+      for (size_t h = 0; h < H; ++h) post[h] = sum > 0.0 ? post[h] / sum : 1.0 / (double)H;
+      beliefs_[id] = post;
+    }
+  }
+
+  // one hypothesis per agent from its belief (root-belief sampling)
+  const std::map<AgentId, unsigned>& sample_current_hypothesis() {
+    for (const auto& kv : beliefs_) {
+      auto f = fixed_.find(kv.first);
+      if (f != fixed_.end()) {
+        current_[kv.first] = f->second;
+        continue;
+      }
+      std::discrete_distribution<unsigned> d(kv.second.begin(), kv.second.end());
+      current_[kv.first] = d(gen_);
+    }
+    return current_;
+  }
+
+  unsigned sample_for(AgentId id, unsigned num_hypotheses) {
+    auto f = fixed_.find(id);
+    if (f != fixed_.end()) return f->second;
+    auto it = beliefs_.find(id);
+    if (it == beliefs_.end() || it->second.empty()) {
+      std::uniform_int_distribution<unsigned> d(0, std::max(1u, num_hypotheses) - 1);
+      return d(gen_);
+    }
+    std::discrete_distribution<unsigned> d(it->second.begin(), it->second.end());
+    return d(gen_);
+  }
+
+ private:
+  decltype(MctsParameters::hypothesis_belief_tracker) p_;
+  std::mt19937 gen_;
+  Beliefs beliefs_;
+  std::map<AgentId, std::vector<std::deque<double>>> history_;
+  std::map<AgentId, unsigned> fixed_, current_;
+};
+
+}  // namespace bark_mcts_b200

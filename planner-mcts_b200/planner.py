@@ -1,0 +1,271 @@
+"""Python binding of the BehaviorUCT* planners (ctypes over include/bmcts_planner_c.h).
+
+Mirrors the reference's pybind classes (python_wrapper/python_planner_uct.cpp:131-248):
+`BehaviorUCTHypothesis(params, hypotheses)`, `BehaviorUCTRiskConstraint(params, hypotheses)`,
+`BehaviorUCTCooperative(params)`; `Plan(delta_time, observed_world)`; `last_*` debug infos.
+`params` is a dict of BARK ParamServer keys ("BehaviorUctBase::Mcts::MaxNumIterations": 500);
+`observed_world` is an `ObservedWorld` (agents + map geometry).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+
+from . import _abi
+
+PLANNER_HYPOTHESIS, PLANNER_RISK_CONSTRAINT, PLANNER_COOPERATIVE = 0, 1, 2
+PLAN_MAX_TRAJ = 64
+
+
+class AgentState(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("x", C.c_float), ("y", C.c_float), ("theta", C.c_float),
+                ("v", C.c_float), ("length", C.c_float), ("width", C.c_float), ("rear", C.c_float),
+                ("last_acc", C.c_float)]
+
+
+class PlanResult(C.Structure):
+    _fields_ = [
+        ("best_action", C.c_uint32), ("num_iterations", C.c_uint32), ("num_nodes", C.c_uint32),
+        ("num_actions", C.c_uint32), ("solution_time_ms", C.c_double),
+        ("return_values", C.c_double * _abi.MAX_EGO_ACTIONS),
+        ("visit_counts", C.c_double * _abi.MAX_EGO_ACTIONS),
+        ("cost_values", (C.c_double * _abi.MAX_EGO_ACTIONS) * 2),
+        ("policy", C.c_double * _abi.MAX_EGO_ACTIONS),
+        ("expected_risk", C.c_double * 2), ("scenario_risk", C.c_double * 2),
+        ("action_acc", C.c_float), ("action_steering", C.c_float),
+        ("max_tree_depth", C.c_int32), ("root_expanded_actions", C.c_int32 * _abi.MAX_AGENTS),
+        ("n_traj", C.c_int32), ("trajectory", C.c_double * (PLAN_MAX_TRAJ * 5)),
+        ("engine_launches", C.c_uint64),
+    ]
+
+
+PLANNER_SYMBOLS = [
+    "bmcts_planner_create", "bmcts_planner_destroy", "bmcts_planner_set_param",
+    "bmcts_planner_add_hypothesis", "bmcts_planner_set_map", "bmcts_planner_set_tree_index",
+    "bmcts_planner_plan", "bmcts_planner_get_beliefs", "bmcts_planner_root_stats",
+    "bmcts_planner_decide_from_root_stats", "bmcts_planner_parameter_sampling_probability",
+    "bmcts_planner_last_error",
+]
+
+
+def declare_planner_api(lib):
+    P = C.POINTER
+    lib.bmcts_planner_create.argtypes = [C.c_int, C.c_int, P(C.c_void_p)]
+    lib.bmcts_planner_destroy.argtypes = [C.c_void_p]
+    lib.bmcts_planner_destroy.restype = None
+    lib.bmcts_planner_set_param.argtypes = [C.c_void_p, C.c_char_p, P(C.c_double), C.c_int]
+    lib.bmcts_planner_add_hypothesis.argtypes = [C.c_void_p, P(_abi.Hypothesis), C.c_int, C.c_int,
+                                                 C.c_float, C.c_float]
+    lib.bmcts_planner_set_map.argtypes = [C.c_void_p, P(_abi.Scenario)]
+    lib.bmcts_planner_set_tree_index.argtypes = [C.c_void_p, C.c_uint32]
+    lib.bmcts_planner_plan.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint32,
+                                       P(AgentState), C.c_int, P(PlanResult)]
+    lib.bmcts_planner_get_beliefs.argtypes = [C.c_void_p, C.c_uint32, P(C.c_double), C.c_int]
+    lib.bmcts_planner_root_stats.argtypes = [C.c_void_p, P(C.c_double), C.c_int]
+    lib.bmcts_planner_decide_from_root_stats.argtypes = [C.c_void_p, P(C.c_double), C.c_int,
+                                                         P(PlanResult)]
+    lib.bmcts_planner_parameter_sampling_probability.argtypes = [C.c_void_p, C.c_int]
+    lib.bmcts_planner_parameter_sampling_probability.restype = C.c_double
+    lib.bmcts_planner_last_error.argtypes = [C.c_void_p]
+    lib.bmcts_planner_last_error.restype = C.c_char_p
+    return lib
+
+
+@dataclass
+class Agent:
+    id: int
+    x: float
+    y: float
+    theta: float = 0.0
+    v: float = 0.0
+    length: float = 4.0
+    width: float = 2.0
+    rear: float = 1.25
+    last_acc: float = 0.0
+
+
+@dataclass
+class ObservedWorld:
+    ego_id: int
+    agents: List[Agent]
+    map: object  # _abi.Scenario holding corridors, road polygon and goal
+    world_time: float = 0.0
+
+
+@dataclass
+class HypothesisIDM:
+    """BehaviorHypothesisIDM: parameter region + likelihood histogram settings
+    (hypothesis/idm/hypothesis_idm.cpp:27-38)."""
+    region: object  # _abi.Hypothesis
+    num_samples: int = 10000
+    num_buckets: int = 100
+    buckets_lower_bound: float = -10.0
+    buckets_upper_bound: float = 10.0
+
+
+class _BehaviorUCT:
+    KIND = PLANNER_HYPOTHESIS
+
+    def __init__(self, params=None, hypotheses=(), device=0, _lib=None, _create=None):
+        self._lib = declare_planner_api(_lib or _abi.load_library())
+        self._h = C.c_void_p()
+        if _create is not None:
+            st = _create(self.KIND, C.byref(self._h))
+        else:
+            st = self._lib.bmcts_planner_create(self.KIND, int(device), C.byref(self._h))
+        if st != _abi.OK:
+            raise _abi.BmctsError(st, "bmcts_planner_create")
+        self.params = dict(params or {})
+        for key, val in self.params.items():
+            vals = np.atleast_1d(np.asarray(val, dtype=np.float64))
+            arr = (C.c_double * len(vals))(*vals)
+            self._check(self._lib.bmcts_planner_set_param(self._h, key.encode(), arr, len(vals)))
+        self.hypotheses = list(hypotheses)
+        for h in self.hypotheses:
+            self._check(self._lib.bmcts_planner_add_hypothesis(
+                self._h, C.byref(h.region), h.num_samples, h.num_buckets,
+                h.buckets_lower_bound, h.buckets_upper_bound))
+        self._map = None
+        self.last = None
+
+    def _check(self, st):
+        if st != _abi.OK:
+            raise _abi.BmctsError(st, self._lib.bmcts_planner_last_error(self._h).decode())
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                self._lib.bmcts_planner_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def set_tree_index(self, i):
+        self._check(self._lib.bmcts_planner_set_tree_index(self._h, int(i)))
+
+    def Plan(self, delta_time, observed_world):
+        """Plan(min_planning_time, observed_world) -> trajectory ndarray [n, 5] = [t,x,y,theta,v]"""
+        if self._map is not observed_world.map:
+            self._check(self._lib.bmcts_planner_set_map(self._h, C.byref(observed_world.map)))
+            self._map = observed_world.map
+        n = len(observed_world.agents)
+        arr = (AgentState * n)()
+        for i, a in enumerate(observed_world.agents):
+            arr[i] = AgentState(a.id, a.x, a.y, a.theta, a.v, a.length, a.width, a.rear, a.last_acc)
+        res = PlanResult()
+        self._check(self._lib.bmcts_planner_plan(self._h, float(delta_time),
+                                                 float(observed_world.world_time),
+                                                 int(observed_world.ego_id), arr, n, C.byref(res)))
+        self.last = res
+        return self.last_trajectory
+
+    # ---- debug infos (python_planner_uct.cpp:145-166, 206-248)
+    def _vec(self, field_, n=None):
+        n = self.last.num_actions if n is None else n
+        return np.array(list(getattr(self.last, field_))[:n], dtype=np.float64)
+
+    @property
+    def last_trajectory(self):
+        return np.array(self.last.trajectory[:self.last.n_traj * 5]).reshape(-1, 5)
+
+    @property
+    def last_action(self):
+        return np.array([self.last.action_acc, self.last.action_steering])
+
+    @property
+    def last_macro_action(self):
+        return int(self.last.best_action)
+
+    @property
+    def last_return_values(self):
+        v = self._vec("return_values")
+        return {a: float(x) for a, x in enumerate(v) if not np.isnan(x)}
+
+    @property
+    def last_visit_counts(self):
+        return self._vec("visit_counts")
+
+    @property
+    def last_num_iterations(self):
+        return int(self.last.num_iterations)
+
+    @property
+    def last_num_nodes(self):
+        return int(self.last.num_nodes)
+
+    @property
+    def last_solution_time(self):
+        return float(self.last.solution_time_ms)
+
+    @property
+    def last_max_tree_depth(self):
+        return int(self.last.max_tree_depth)
+
+    @property
+    def last_root_expanded_actions(self):
+        return list(self.last.root_expanded_actions)
+
+    @property
+    def engine_launches(self):
+        return int(self.last.engine_launches)
+
+    def root_stats(self):
+        buf = (C.c_double * 128)()
+        n = self._lib.bmcts_planner_root_stats(self._h, buf, 128)
+        return np.array(buf[:n], dtype=np.float64)
+
+    def decide_from_root_stats(self, stats):
+        stats = np.ascontiguousarray(stats, dtype=np.float64)
+        res = PlanResult()
+        self._check(self._lib.bmcts_planner_decide_from_root_stats(
+            self._h, stats.ctypes.data_as(C.POINTER(C.c_double)), len(stats), C.byref(res)))
+        self.last = res
+        return int(res.best_action)
+
+
+class BehaviorUCTHypothesis(_BehaviorUCT):
+    KIND = PLANNER_HYPOTHESIS
+
+    def current_beliefs(self, agent_id):
+        buf = (C.c_double * _abi.MAX_HYPOTHESES)()
+        n = self._lib.bmcts_planner_get_beliefs(self._h, int(agent_id), buf, _abi.MAX_HYPOTHESES)
+        return np.array(buf[:n])
+
+    def parameter_sampling_probability(self, h):
+        return float(self._lib.bmcts_planner_parameter_sampling_probability(self._h, int(h)))
+
+
+class BehaviorUCTRiskConstraint(BehaviorUCTHypothesis):
+    KIND = PLANNER_RISK_CONSTRAINT
+
+    @property
+    def last_cost_values(self):
+        names = ("envelope", "collision")
+        out = {}
+        for i, nm in enumerate(names):
+            v = np.array(list(self.last.cost_values[i])[:self.last.num_actions])
+            d = {a: float(x) for a, x in enumerate(v) if not np.isnan(x)}
+            if d:
+                out[nm] = d
+        return out
+
+    @property
+    def last_expected_risk(self):
+        return list(self.last.expected_risk)
+
+    @property
+    def last_scenario_risk(self):
+        return list(self.last.scenario_risk)
+
+    @property
+    def last_policy_sampled(self):
+        pol = {a: float(p) for a, p in enumerate(self._vec("policy")) if p > 0}
+        return int(self.last.best_action), pol
+
+
+class BehaviorUCTCooperative(_BehaviorUCT):
+    KIND = PLANNER_COOPERATIVE
+
+    def __init__(self, params=None, device=0, _lib=None, _create=None):
+        super().__init__(params, (), device, _lib, _create)
