@@ -10,12 +10,14 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "bmcts_c.h"
 #include "rollout_kernel.cuh"
+#include "rollout_lane_kernel.cuh"
 
 namespace {
 
@@ -41,6 +43,9 @@ struct bmcts_engine {
   uint64_t launches = 0;
   std::string err;
   int max_smem_optin = 0;
+  int sm_count = 0;
+  unsigned int* d_counter = nullptr;  // work counter of the lane kernel
+  int lane_T = 0, lane_W = 0;          // last launch geometry (introspection / bench)
   // staging buffers for host-pointer calls
   DevBuf b_pose, b_alive, b_hyp, b_depth, b_action, b_draw;
   DevBuf b_next_pose, b_next_alive, b_reward, b_cost, b_flags, b_last_action;
@@ -109,11 +114,81 @@ int launch_rollout(bmcts_engine* e, const bmcts::KernelArgs& a) {
   return BMCTS_OK;
 }
 
+// Launch geometry of the lane kernel (rollout_lane_kernel.cuh).  T lanes per rollout: 1 when
+// the batch fills the GPU, more when it does not (an MCTS wave of a few hundred leaves) or
+// when the per-rollout state of a large scenario would leave too few warps resident.
+// W warps per block share one staged scenario; the grid is persistent (blocks/SM x SMs).
+template <int T>
+int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
+  auto kern = bmcts::rollout_lane_kernel<T>;
+  const int NC = 32 / T;
+  const int groups = a.n;
+  int best_W = 1, best_blocks = 1;
+  long best_warps = -1;
+  for (int W = 16; W >= 1; --W) {
+    if (force_W > 0 && W != force_W) continue;
+    const bmcts::LaneLayout lay = bmcts::lane_layout(a.A, a.C, a.H, T, W);
+    if ((int)lay.total > e->max_smem_optin) continue;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    int blocks = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, W * 32, lay.total));
+    if (blocks < 1) continue;
+    // a small batch is spread over the SMs first: never more warps than it can fill
+    const long need_warps = (groups + NC - 1) / NC;
+    long resident = (long)blocks * W * e->sm_count;
+    long useful = resident < need_warps ? resident : need_warps;
+    // blocks needed to hold `useful` warps; prefer the geometry that runs most warps at once,
+    // then the one that spreads them over more SMs (smaller W)
+    long score = useful * 64 - (useful == need_warps ? W : 0);
+    if (score > best_warps) {
+      best_warps = score;
+      best_W = W;
+      best_blocks = blocks;
+    }
+  }
+  if (best_warps < 0)
+    return fail(e, BMCTS_ERR_UNSUPPORTED, "scenario needs more shared memory than the SM offers");
+  const bmcts::LaneLayout lay = bmcts::lane_layout(a.A, a.C, a.H, T, best_W);
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+  const long need_blocks = ((long)groups + (long)NC * best_W - 1) / ((long)NC * best_W);
+  long grid = (long)best_blocks * e->sm_count;
+  if (grid > need_blocks) grid = need_blocks;
+  if (const char* s = std::getenv("BMCTS_LANE_GRID")) {  // tests: force the refill path
+    const long cap = std::atol(s);
+    if (cap > 0 && grid > cap) grid = cap;
+  }
+  CU(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned int), e->stream));
+  kern<<<(unsigned)grid, best_W * 32, lay.total, e->stream>>>(a, e->d_counter);
+  CU(cudaGetLastError());
+  e->launches++;
+  e->lane_T = T;
+  e->lane_W = best_W;
+  return BMCTS_OK;
+}
+
+int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a) {
+  int T = 0, W = 0;
+  if (const char* s = std::getenv("BMCTS_LANE_T")) T = std::atoi(s);
+  if (const char* s = std::getenv("BMCTS_LANE_W")) W = std::atoi(s);
+  if (T != 1 && T != 2 && T != 4) {
+    // lanes the batch would occupy with one lane per rollout vs. what the GPU keeps resident
+    const long lanes_resident = (long)e->sm_count * 32 * 16;
+    T = 1;
+    if ((long)a.n * 2 <= lanes_resident && a.A >= 3) T = 2;
+    if ((long)a.n * 4 <= lanes_resident && a.A >= 5) T = 4;
+  }
+  switch (T) {
+    case 4: return launch_lane_T<4>(e, a, W);
+    case 2: return launch_lane_T<2>(e, a, W);
+    default: return launch_lane_T<1>(e, a, W);
+  }
+}
+
 int launch(bmcts_engine* e, const bmcts::KernelArgs& a) {
   if (a.n <= 0) return BMCTS_OK;
   CU(cudaEventRecord(e->ev_start, e->stream));
   int st = (e->cfg.state_kind == BMCTS_STATE_COOPERATIVE) ? launch_rollout<true>(e, a)
-                                                          : launch_rollout<false>(e, a);
+                                                          : launch_lane(e, a);
   if (st) return st;
   CU(cudaEventRecord(e->ev_stop, e->stream));
   e->timed = true;
@@ -128,6 +203,7 @@ void base_args(bmcts_engine* e, bmcts::KernelArgs& a, int n, uint64_t seed, uint
   a.n = n;
   a.A = e->scn.n_agents;
   a.C = e->scn.n_corridors;
+  a.H = e->scn.n_hypotheses;
   a.key0 = (uint32_t)seed;
   a.key1 = (uint32_t)(seed >> 32) ^ stream;
 }
@@ -202,6 +278,8 @@ int bmcts_create(int device, const bmcts_config* cfg, bmcts_engine** out) {
   if ((ce = cudaMalloc(&e->d_dt_table, sizeof(float) * BMCTS_MAX_DEPTH)) != cudaSuccess)
     return bail(ce);
   cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if ((ce = cudaMalloc(&e->d_counter, sizeof(unsigned int))) != cudaSuccess) return bail(ce);
   if ((ce = cudaMemcpy(e->d_cfg, &e->cfg, sizeof(bmcts_config), cudaMemcpyHostToDevice)) !=
       cudaSuccess)
     return bail(ce);
@@ -226,6 +304,7 @@ void bmcts_destroy(bmcts_engine* e) {
   if (e->d_cfg) cudaFree(e->d_cfg);
   if (e->d_scn) cudaFree(e->d_scn);
   if (e->d_dt_table) cudaFree(e->d_dt_table);
+  if (e->d_counter) cudaFree(e->d_counter);
   if (e->ev_start) cudaEventDestroy(e->ev_start);
   if (e->ev_stop) cudaEventDestroy(e->ev_stop);
   if (e->stream) cudaStreamDestroy(e->stream);

@@ -69,6 +69,7 @@ struct KernelArgs {
   int n;
   int A;
   int C;
+  int H;
   int do_expand;
   int do_rollout;
   uint32_t key0, key1;

@@ -15,6 +15,36 @@ pytestmark = pytest.mark.gpu
 WORKLOADS = ["c1_highway_mdp", "c2_merge_sbg", "c3_merge_risk", "c4_coop", "c5_rsbg"]
 
 
+@pytest.fixture(params=["auto", "1", "2", "4"], autouse=True)
+def lanes_per_rollout(request, monkeypatch):
+    """every test runs with the engine's own choice of lanes per rollout and with each
+    forced value (BMCTS_LANE_T is read at every launch)"""
+    if request.param == "auto":
+        monkeypatch.delenv("BMCTS_LANE_T", raising=False)
+    else:
+        monkeypatch.setenv("BMCTS_LANE_T", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("name", ["c2_merge_sbg", "c3_merge_risk"])
+def test_rollout_parity_with_refill(name, monkeypatch):
+    """a 2-block grid: every lane group pulls several rollouts from the work counter"""
+    monkeypatch.setenv("BMCTS_LANE_GRID", "2")
+    monkeypatch.setenv("BMCTS_LANE_W", "2")
+    cfg, scn, meta = scenarios.workload(name, horizon=20)
+    n = 1500
+    rng = np.random.default_rng(17)
+    pose, alive, hyp = scenarios.sample_leaves(scn, n, meta["lane_of"], meta["s_of"], rng,
+                                               dead_prob=0.05)
+    eng = RolloutEngine(cfg, scn)
+    g = eng.rollout(pose, alive, hyp, seed=5, stream=2, first_rollout_id=1 << 33,
+                    want_agents=True, want_final=True)
+    c = oracle.rollout(cfg, scn, pose, alive, hyp, seed=5, stream=2, first_rollout_id=1 << 33,
+                       n_threads=8)
+    parity.assert_results_match(g, c)
+    assert len(set(g["result"]["n_steps"].tolist())) > 3   # rollouts end at different steps
+
+
 @pytest.mark.parametrize("name", WORKLOADS)
 def test_rollout_parity(name):
     cfg, scn, meta = scenarios.workload(name, horizon=20)
