@@ -70,10 +70,29 @@ BM_HD float bm_sqrt(float a) {
 #endif
 }
 
-/* compare-and-select min/max: identical NaN / signed-zero behaviour on both
- * sides (fminf/fmaxf differ between libm and PTX for -0/+0) */
-BM_HD float bm_min(float a, float b) { return (a < b) ? a : b; }
-BM_HD float bm_max(float a, float b) { return (a > b) ? a : b; }
+/* min / max with the semantics of the PTX min.f32 / max.f32 instructions (one FMNMX on
+ * sm_100a): a NaN operand yields the other operand, and -0 orders below +0.  The host
+ * side spells the same rule out (x86 minss/maxss differ on NaN and signed zeros). */
+BM_HD float bm_min(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return fminf(a, b);
+#else
+  if (a != a) return b;
+  if (b != b) return a;
+  if (a == b) return signbit(a) ? a : b;
+  return (a < b) ? a : b;
+#endif
+}
+BM_HD float bm_max(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return fmaxf(a, b);
+#else
+  if (a != a) return b;
+  if (b != b) return a;
+  if (a == b) return signbit(a) ? b : a;
+  return (a > b) ? a : b;
+#endif
+}
 BM_HD float bm_clamp(float x, float lo, float hi) { return bm_min(bm_max(x, lo), hi); }
 BM_HD float bm_abs(float a) { return fabsf(a); }
 

@@ -124,6 +124,8 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
   const int NC = 32 / T;
   const int groups = a.n;
   int best_W = 1, best_blocks = 1;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          cudaSharedmemCarveoutMaxShared));
   long best_warps = -1;
   for (int W = 16; W >= 1; --W) {
     if (force_W > 0 && W != force_W) continue;

@@ -110,50 +110,55 @@ struct Proj {
   bool in;
 };
 
-// Frenet projection on a corridor centre line (oracle_project)
+// Frenet projection on a corridor centre line (oracle_project).  Corridors have a handful
+// of segments: the loop is kept rolled (an unrolled-by-4 body with its remainder loops
+// costs more than it saves at trip counts of 1-3) and the best-so-far update is selects.
 __device__ __forceinline__ Proj project(const bmcts_corridor& c, float x, float y) {
   const int nseg = c.n_pts - 1;
   float best_d2 = kBig, best_u = 0.0f, best_raw = 0.0f, best_cross = 0.0f;
   int best = 0;
+#pragma unroll 1
   for (int k = 0; k < nseg; ++k) {
-    float tx = c.tx[k], ty = c.ty[k];
-    float rx = x - c.px[k];
-    float ry = y - c.py[k];
-    float u = bm_fma(rx, tx, ry * ty);
-    float uc = bm_clamp(u, 0.0f, c.seg_len[k]);
-    float ex = bm_fma(-uc, tx, rx);
-    float ey = bm_fma(-uc, ty, ry);
-    float d2 = bm_fma(ex, ex, ey * ey);
-    if (d2 < best_d2) {
-      best_d2 = d2;
-      best = k;
-      best_u = uc;
-      best_raw = u;
-      best_cross = bm_fma(tx, ry, -(ty * rx));
-    }
+    const float tx = c.tx[k], ty = c.ty[k];
+    const float rx = x - c.px[k];
+    const float ry = y - c.py[k];
+    const float u = bm_fma(rx, tx, ry * ty);
+    const float uc = bm_clamp(u, 0.0f, c.seg_len[k]);
+    const float ex = bm_fma(-uc, tx, rx);
+    const float ey = bm_fma(-uc, ty, ry);
+    const float d2 = bm_fma(ex, ex, ey * ey);
+    const float cross = bm_fma(tx, ry, -(ty * rx));
+    const bool better = d2 < best_d2;
+    best_d2 = better ? d2 : best_d2;
+    best = better ? k : best;
+    best_u = better ? uc : best_u;
+    best_raw = better ? u : best_raw;
+    best_cross = better ? cross : best_cross;
   }
   Proj p;
   p.s = c.s0[best] + best_u;
   p.d = best_cross;
   p.seg = best;
-  bool in = true;
-  if (best == 0 && best_raw < 0.0f) in = false;
-  if (best == nseg - 1 && best_raw > c.seg_len[best]) in = false;
-  p.in = in;
+  p.in = !((best == 0 && best_raw < 0.0f) || (best == nseg - 1 && best_raw > c.seg_len[best]));
   return p;
 }
 
+// even-odd rule, division free (oracle point_in_polygon)
 __device__ __forceinline__ bool point_in_polygon(const float* px, const float* py, int n, float x,
                                                  float y) {
   int inside = 0;
-  for (int i = 0, j = n - 1; i < n; j = i++) {
-    float yi = py[i], yj = py[j];
+  float xj = px[n - 1], yj = py[n - 1];
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const float xi = px[i], yi = py[i];
     if ((yi > y) != (yj > y)) {
-      float lhs = (x - px[i]) * (yj - yi);
-      float rhs = (px[j] - px[i]) * (y - yi);
-      int cross = (yj > yi) ? (lhs < rhs) : (lhs > rhs);
+      const float lhs = (x - xi) * (yj - yi);
+      const float rhs = (xj - xi) * (y - yi);
+      const int cross = (yj > yi) ? (lhs < rhs) : (lhs > rhs);
       inside ^= cross;
     }
+    xj = xi;
+    yj = yi;
   }
   return inside != 0;
 }

@@ -42,7 +42,7 @@ static_assert(kScnPrefixBytes % 8 == 0, "scenario prefix is staged with 8-byte c
 static_assert(sizeof(bmcts_hypothesis) % 16 == 0, "hypotheses are staged with 16-byte copies");
 
 struct LaneLayout {
-  size_t off_acts, off_cfg, off_segcs, off_segsn, off_state, warp_bytes, total;
+  size_t off_acts, off_cfg, off_segcs, off_segsn, off_hflags, off_state, warp_bytes, total;
 };
 
 __host__ __device__ inline LaneLayout lane_layout(int A, int C, int H, int T, int warps) {
@@ -56,6 +56,8 @@ __host__ __device__ inline LaneLayout lane_layout(int A, int C, int H, int T, in
   b += sizeof(float) * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS;
   l.off_segsn = b;
   b += sizeof(float) * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS;
+  l.off_hflags = b;
+  b += smem_align16(sizeof(uint32_t) * (size_t)(H > 0 ? H : 1));
   l.off_state = b;
   l.warp_bytes = sizeof(float) * (size_t)(L_PROJ + 2 * C) * A * (32 / T);
   l.total = b + l.warp_bytes * warps;
@@ -106,16 +108,24 @@ __device__ __forceinline__ float idm_substeps(const IdmLimits& hl, const IdmPara
   return trav;
 }
 
+#ifndef BMCTS_LANE_MAX_THREADS
+#define BMCTS_LANE_MAX_THREADS 512
+#endif
+#ifndef BMCTS_LANE_MIN_BLOCKS
+#define BMCTS_LANE_MIN_BLOCKS 1
+#endif
+
 template <int T>
-__global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
-                                                            unsigned int* __restrict__ counter) {
+__global__ void __launch_bounds__(BMCTS_LANE_MAX_THREADS, BMCTS_LANE_MIN_BLOCKS)
+rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = 32 / T;  // rollouts (columns) per warp
   const int A = p.A, C = p.C;
   const int warps = blockDim.x >> 5;
   const LaneLayout lay = lane_layout(A, C, p.H, T, warps);
 
-  // ---- stage scenario prefix + used hypotheses, macro actions, config, segment sin/cos
+  // ---- stage scenario prefix + used hypotheses, macro actions, config, segment sin/cos,
+  //      per-hypothesis "which Philox blocks are needed" flags
   {
     const size_t nb = kScnPrefixBytes + sizeof(bmcts_hypothesis) * (size_t)p.H;
     const uint2* src = reinterpret_cast<const uint2*>(p.scn);
@@ -138,6 +148,18 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
       cs[i] = c_;
       sn[i] = s_;
     }
+    uint32_t* hf = reinterpret_cast<uint32_t*>(smem_raw + lay.off_hflags);
+    for (int i = threadIdx.x; i < p.H; i += blockDim.x) {
+      const bmcts_hypothesis& h = p.scn->hypotheses[i];
+      // a FixedValue parameter (hi == lo) does not depend on its uniform: u * 0 + lo == lo
+      // for every u in [0, 1), so a Philox block none of whose words matter is skipped
+      uint32_t f = 0;
+      if (h.hi[0] != h.lo[0] || h.hi[1] != h.lo[1] || h.hi[2] != h.lo[2] || h.hi[3] != h.lo[3])
+        f |= 1u;
+      if (h.hi[4] != h.lo[4]) f |= 2u;
+      if (h.exponent == 4) f |= 4u;
+      hf[i] = f;
+    }
   }
   __syncthreads();  // the only block barrier: staging done
   const bmcts_scenario& scn = *reinterpret_cast<const bmcts_scenario*>(smem_raw);
@@ -145,13 +167,15 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
   const bmcts_config& cfg = *reinterpret_cast<const bmcts_config*>(smem_raw + lay.off_cfg);
   const float* segcs = reinterpret_cast<const float*>(smem_raw + lay.off_segcs);
   const float* segsn = reinterpret_cast<const float*>(smem_raw + lay.off_segsn);
+  const uint32_t* hflags = reinterpret_cast<const uint32_t*>(smem_raw + lay.off_hflags);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = lane % T;  // lane inside the group
   const int g = lane / T;  // column
   float* col = reinterpret_cast<float*>(smem_raw + lay.off_state + lay.warp_bytes * warp) + g;
-#define ST(f, a) col[((f) * A + (a)) * NC]
-#define STI(f, a) (reinterpret_cast<int*>(col)[((f) * A + (a)) * NC])
+  const int fstride = A * NC;  // floats between two fields of the same agent
+#define ST(f, a) col[(f) * fstride + (a) * NC]
+#define STI(f, a) (reinterpret_cast<int*>(col)[(f) * fstride + (a) * NC])
 
   const uint32_t n_groups = gridDim.x * (uint32_t)warps * NC;
   const uint32_t my_group = (blockIdx.x * (uint32_t)warps + warp) * NC + g;
@@ -161,32 +185,11 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
   const bool add_sd = cfg.add_safe_dist != 0;
   const bool goal_poly = scn.goal.kind == BMCTS_GOAL_POLYGON;
   const bool goal_frenet = scn.goal.kind == BMCTS_GOAL_FRENET_LIMITS;
-
-  // projection of one agent on every corridor; writes the Frenet table, returns cur
-  auto publish_agent = [&](int a, float x, float y, float th, bool want_goal, float& goal_d,
-                           bool& goal_in, float& goal_ang) -> int {
-    float best = kBig;
-    int bc = 0;
-    for (int c = 0; c < C; ++c) {
-      Proj pr = project(scn.corridors[c], x, y);
-      float m = pr.in ? bm_abs(pr.d) : kBig;
-      ST(L_PROJ + 2 * c, a) = pr.s;
-      ST(L_PROJ + 2 * c + 1, a) = pr.in ? pr.d : kBig;
-      if (m < best) {
-        best = m;
-        bc = c;
-      }
-      if (want_goal && c == scn.goal.corridor) {
-        goal_d = pr.d;
-        goal_in = pr.in;
-        goal_ang = bm_norm_angle(th - scn.corridors[c].angle[pr.seg]);
-      }
-    }
-    return bc;
-  };
+  const int n_road = scn.n_road_pts;
+  const bool want_final = p.final_pose != nullptr && p.do_rollout != 0;
 
   // ---- per-rollout registers (replicated in the T lanes of a group)
-  bool active = false, done = false, first = true, expand = false;
+  bool active = false, done = false, first = true, expand = false, fresh = false;
   uint32_t rid = 0, am = 0;
   int n = 0, depth = 1, agent_steps = 0;
   float disc = 0.0f, R = 0.0f, C0 = 0.0f, C1 = 0.0f, L = 0.0f;
@@ -197,6 +200,8 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
 
   for (;;) {
     // ------------------------------------------------ acquire the next rollout
+    // A new rollout spends its first pass through the loop in `fresh` mode: only the
+    // publish phase runs (Frenet table of the leaf state), the step phases are skipped.
     if (!active && !done) {
       uint32_t next;
       if (first) {
@@ -215,6 +220,7 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
         depth = p.depth ? (int)p.depth[rid] : 1;
         expand = p.do_expand != 0;
         active = true;
+        fresh = true;
         n = 0;
         agent_steps = 0;
         disc = cfg.discount_factor;
@@ -225,27 +231,12 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
         ey = q0.y;
         eth = q0.z;
         ev = q0.w;
-        for (int a = t; a < A; a += T) {
-          const size_t gi = (size_t)a * p.n + rid;
-          const float4 q = p.pose[gi];
-          if (p.final_pose && p.do_rollout) p.final_pose[gi] = q;
-          int hyp = p.hyp ? (int)p.hyp[gi] : 0;
-          int cur = 0;
-          if ((am >> a) & 1u) {
-            float gd = 0.0f, ga = 0.0f;
-            bool gin = false;
-            cur = publish_agent(a, q.x, q.y, q.z, goal_frenet && a == 0, gd, gin, ga);
-            ST(L_V, a) = q.w;
-          }
-          STI(L_CUR, a) = cur | (hyp << 8);
-        }
         bm_sincos(eth, &esn, &ecs);
-        if (T > 1) __syncwarp(gmask);
       }
     }
     if (__all_sync(0xffffffffu, done)) break;
 
-    // ---------------------------------------------------------------- predict()
+    const bool stepping = active && !fresh;
     const uint32_t pre = am;
     const float Dt = p.dt_table
                          ? p.dt_table[depth < BMCTS_MAX_DEPTH ? depth : BMCTS_MAX_DEPTH - 1]
@@ -253,39 +244,41 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
     const float dt = bm_div(Dt, (float)nsub);
     const uint64_t rollout_id = p.first_rollout_id + (uint64_t)rid;
 
+    // ---------------------------------------------------------------- predict()
     // others: BehaviorIDMStochastic::Plan under the sampled hypothesis, against the
-    // pre-step snapshot; the planned (s, v) are committed in the second pass
-    if (active) {
+    // pre-step snapshot; the planned (s, v) are committed in the publish phase
+    if (stepping) {
+#pragma unroll 1
       for (int i = (t == 0 ? T : t); i < A; i += T) {
         if (!((pre >> i) & 1u)) continue;
-        const int word = STI(L_CUR, i);
+        float* ca = col + i * NC;  // this agent's column entries
+        const int word = __float_as_int(ca[L_CUR * fstride]);
         const int cur = word & 0xff;
-        const bmcts_hypothesis& h = scn.hypotheses[word >> 8];
-        const float s_cur = ST(L_PROJ + 2 * cur, i);
+        const int hyp = word >> 8;
+        const bmcts_hypothesis& h = scn.hypotheses[hyp];
+        const uint32_t hf = hflags[hyp];
+        const float* tab_s = col + (L_PROJ + 2 * cur) * fstride;
+        const float* tab_d = tab_s + fstride;
+        const float s_cur = tab_s[i * NC];
         // BaseIDM::CalcRelativeValues: nearest alive agent ahead inside the corridor
         const float hwc = scn.corridors[cur].half_width;
         int jf = -1;
         float ds_f = kBig;
+#pragma unroll 1
         for (uint32_t m = pre & ~(1u << i); m; m &= m - 1u) {
           const int j = __ffs(m) - 1;
-          const float dj = ST(L_PROJ + 2 * cur + 1, j);
-          const float ds = ST(L_PROJ + 2 * cur, j) - s_cur;
-          if (bm_abs(dj) <= hwc && ds > 0.0f && ds < ds_f) {
-            ds_f = ds;
-            jf = j;
-          }
+          const float dj = tab_d[j * NC];
+          const float ds = tab_s[j * NC] - s_cur;
+          const bool better = bm_abs(dj) <= hwc && ds > 0.0f && ds < ds_f;
+          ds_f = better ? ds : ds_f;
+          jf = better ? j : jf;
         }
         const bool has_leader = jf >= 0;
         float gap = 0.0f, v_l = 0.0f;
         if (has_leader) {
           gap = ds_f - ((scn.agent_length[i] - scn.agent_rear[i]) + scn.agent_rear[jf]);
-          v_l = ST(L_V, jf);
+          v_l = col[L_V * fstride + jf * NC];
         }
-        // parameter draw; a FixedValue parameter (hi == lo) is independent of the uniform
-        // (u * 0 + lo == lo for every u in [0, 1)), so its Philox block is skipped
-        const bool need0 = h.hi[0] != h.lo[0] || h.hi[1] != h.lo[1] || h.hi[2] != h.lo[2] ||
-                           h.hi[3] != h.lo[3];
-        const bool need1 = h.hi[4] != h.lo[4];
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
         {
           uint64_t id = rollout_id;
@@ -295,25 +288,23 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
             dom = BMCTS_RNG_TREE_PARAMS;
             idx = 0u;
           }
-          if (need0) r0 = draw(p.key0, p.key1, id, (uint32_t)i, dom, idx);
-          if (need1) r1 = draw(p.key0, p.key1, id, (uint32_t)i, dom, idx + 1u);
+          if (hf & 1u) r0 = draw(p.key0, p.key1, id, (uint32_t)i, dom, idx);
+          if (hf & 2u) r1 = draw(p.key0, p.key1, id, (uint32_t)i, dom, idx + 1u);
         }
         const IdmParams ip = sample_idm_params(h, r0, r1);
         const IdmLimits hl = idm_limits(h);
-        float nv = ST(L_V, i), acc;
-        const float trav = (hl.exponent == 4)
+        float nv = ca[L_V * fstride], acc;
+        const float trav = (hf & 4u)
                                ? idm_substeps<true>(hl, ip, has_leader, gap, v_l, dt, nsub, nv, acc)
                                : idm_substeps<false>(hl, ip, has_leader, gap, v_l, dt, nsub, nv, acc);
-        ST(L_NS, i) = bm_min(s_cur + trav, scn.corridors[cur].length);
-        ST(L_NV, i) = nv;
+        ca[L_NS * fstride] = bm_min(s_cur + trav, scn.corridors[cur].length);
+        ca[L_NV * fstride] = nv;
         if (expand && p.last_action) p.last_action[(size_t)i * p.n + rid] = acc;
       }
     }
-    group_sync<T>();  // every read of the pre-step Frenet table is done
 
     // ego: BehaviorMPMacroActions primitive on the single-track model (lane 0 of the group)
-    bool ego_alive = (pre & 1u) != 0;
-    if (active && ego_alive && t == 0) {
+    if (stepping && (pre & 1u) && t == 0) {
       int action;
       if (expand) {
         action = p.action[rid];
@@ -329,38 +320,37 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
       else if (act.type == BMCTS_ACT_CHANGE_RIGHT && scn.corridors[tgt].right >= 0)
         tgt = scn.corridors[tgt].right;
       const bmcts_corridor& corr = scn.corridors[tgt];
-      const float inv_wb = bm_div(1.0f, cfg.wheel_base);
+      const float wb = cfg.wheel_base, kct = cfg.crosstrack_gain, dmax = cfg.delta_max;
+      const float vmax = cfg.ego_max_velocity;
+      const float inv_wb = bm_div(1.0f, wb);
       float nx = ex, ny = ey, nth = eth, nv = ev;
       float sn = esn, cs = ecs;  // sin / cos of the current heading (published values)
+#pragma unroll 1
       for (int q = 0; q < nsub; ++q) {
-        if (q > 0) bm_sincos(nth, &sn, &cs);
-        float fx = bm_fma(cfg.wheel_base, cs, nx);
-        float fy = bm_fma(cfg.wheel_base, sn, ny);
-        Proj pr = project(corr, fx, fy);
-        float th_err = bm_norm_angle(corr.angle[pr.seg] - nth);
-        float delta = th_err + bm_atan2(-(cfg.crosstrack_gain * pr.d), nv);
-        delta = bm_clamp(delta, -cfg.delta_max, cfg.delta_max);
-        float tn = bm_tan_small(delta);
-        float dv = dt * nv;
+        const float fx = bm_fma(wb, cs, nx);
+        const float fy = bm_fma(wb, sn, ny);
+        const Proj pr = project(corr, fx, fy);
+        const float th_err = bm_norm_angle(corr.angle[pr.seg] - nth);
+        float delta = th_err + bm_atan2(-(kct * pr.d), nv);
+        delta = bm_clamp(delta, -dmax, dmax);
+        const float tn = bm_tan_small(delta);
+        const float dv = dt * nv;
         nx = bm_fma(dv, cs, nx);
         ny = bm_fma(dv, sn, ny);
         nth = bm_fma(dv, tn * inv_wb, nth);
-        nv = bm_clamp(bm_fma(dt, acc, nv), 0.0f, cfg.ego_max_velocity);
+        nv = bm_clamp(bm_fma(dt, acc, nv), 0.0f, vmax);
+        // heading for the next sub-step; after the last one: of the wrapped final heading
+        if (q + 1 == nsub) nth = bm_norm_angle(nth);
+        bm_sincos(nth, &sn, &cs);
       }
       ex = nx;
       ey = ny;
-      eth = bm_norm_angle(nth);
+      eth = nth;
       ev = nv;
+      esn = sn;
+      ecs = cs;
       if (expand && p.last_action) p.last_action[rid] = acc;
-      // World::RemoveInvalidAgents (spec item 6) and the ego's part of the post-step world
-      ego_alive = point_in_polygon(scn.road_x, scn.road_y, scn.n_road_pts, ex, ey);
-      if (ego_alive) {
-        bm_sincos(eth, &esn, &ecs);
-        const int cur = publish_agent(0, ex, ey, eth, goal_frenet, goal_d, goal_in, goal_ang);
-        STI(L_CUR, 0) = cur;
-        ST(L_V, 0) = ev;
-      }
-    } else if (active && expand && t == 0 && p.last_action) {
+    } else if (stepping && expand && t == 0 && p.last_action) {
       p.last_action[rid] = 0.0f;
     }
     if (T > 1) {
@@ -370,67 +360,99 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
       ev = group_lead<T>(ev, lane);
       ecs = group_lead<T>(ecs, lane);
       esn = group_lead<T>(esn, lane);
-      goal_d = group_lead<T>(goal_d, lane);
-      goal_ang = group_lead<T>(goal_ang, lane);
-      goal_in = __shfl_sync(0xffffffffu, (int)goal_in, lane & ~(T - 1)) != 0;
-      ego_alive = __shfl_sync(0xffffffffu, (int)ego_alive, lane & ~(T - 1)) != 0;
     }
-    if (!ego_alive) am &= ~1u;
-    if (active && expand && t == 0) {
-      if (p.next_pose) p.next_pose[rid] = make_float4(ex, ey, eth, ev);
-    }
-    if (active && t == 0 && p.final_pose && p.do_rollout && (pre & 1u))
-      p.final_pose[rid] = make_float4(ex, ey, eth, ev);
+    group_sync<T>();  // every read of the pre-step Frenet table is done
 
-    // others, second pass: commit the planned (s, v): pose on the centre line, removal,
-    // Frenet table, and the pair tests against the ego's post-step rectangle
+    // ------------------------------------------------------------ publish phase
+    // Every agent of the group: new pose (ego: registers; others: centre-line point of the
+    // planned s; fresh rollout: the leaf pose), World::RemoveInvalidAgents, Frenet table of
+    // the post-step world, and the pair tests against the ego's post-step rectangle.
     const Box be = agent_box(scn, 0, ex, ey, ecs, esn, 0.0f, 0.0f);
     const Box bs = agent_box(scn, 0, ex, ey, ecs, esn, cfg.static_lat_safe_dist,
                              cfg.static_lon_safe_dist);
     uint32_t fl = 0, dead = 0;
     if (active) {
-      for (int i = (t == 0 ? T : t); i < A; i += T) {
-        const size_t gi = (size_t)i * p.n + rid;
-        if (!((pre >> i) & 1u)) {
+#pragma unroll 1
+      for (int a = t; a < A; a += T) {
+        const size_t gi = (size_t)a * p.n + rid;
+        float* ca = col + a * NC;
+        const bool was_alive = (pre >> a) & 1u;
+        float x, y, th, v, cth = 0.0f, sth = 0.0f;
+        int word = 0;
+        if (fresh) {
+          const float4 q = p.pose[gi];
+          x = q.x;
+          y = q.y;
+          th = q.z;
+          v = q.w;
+          word = (p.hyp ? (int)p.hyp[gi] : 0) << 8;
+          if (want_final) p.final_pose[gi] = q;
+          if (!was_alive) ca[L_CUR * fstride] = __int_as_float(word);
+        } else if (!was_alive) {
           if (expand) {
             if (p.next_pose) p.next_pose[gi] = p.pose[gi];
-            if (p.reward) p.reward[gi] = 0.0f;
-            if (p.last_action) p.last_action[gi] = 0.0f;
+            if (p.reward && a > 0) p.reward[gi] = 0.0f;
+            if (p.last_action && a > 0) p.last_action[gi] = 0.0f;
           }
-          continue;
+        } else if (a == 0) {
+          x = ex;
+          y = ey;
+          th = eth;
+          v = ev;
+        } else {
+          word = __float_as_int(ca[L_CUR * fstride]);
+          const int cur = word & 0xff;
+          const bmcts_corridor& corr = scn.corridors[cur];
+          const float s_new = ca[L_NS * fstride];
+          const int nseg = corr.n_pts - 1;
+          int sg = 0;
+#pragma unroll 1
+          for (int q = 1; q < nseg; ++q) sg = (corr.s0[q] <= s_new) ? q : sg;
+          const float ls = s_new - corr.s0[sg];
+          x = bm_fma(ls, corr.tx[sg], corr.px[sg]);
+          y = bm_fma(ls, corr.ty[sg], corr.py[sg]);
+          th = corr.angle[sg];
+          v = ca[L_NV * fstride];
+          cth = segcs[cur * BMCTS_MAX_CORRIDOR_PTS + sg];
+          sth = segsn[cur * BMCTS_MAX_CORRIDOR_PTS + sg];
+          word &= ~0xff;
         }
-        const int word = STI(L_CUR, i);
-        const int cur = word & 0xff;
-        const bmcts_corridor& corr = scn.corridors[cur];
-        const float s_new = ST(L_NS, i);
-        const int nseg = corr.n_pts - 1;
-        int sg = 0;
-        for (int q = 1; q < nseg; ++q)
-          if (corr.s0[q] <= s_new) sg = q;
-        const float ls = s_new - corr.s0[sg];
-        const float nx = bm_fma(ls, corr.tx[sg], corr.px[sg]);
-        const float ny = bm_fma(ls, corr.ty[sg], corr.py[sg]);
-        const float nth = corr.angle[sg];
-        const float nv = ST(L_NV, i);
-        if (expand) {
-          if (p.next_pose) p.next_pose[gi] = make_float4(nx, ny, nth, nv);
-          if (p.reward) p.reward[gi] = 0.0f;
+        if (!was_alive) continue;
+        if (!fresh) {
+          if (expand) {
+            if (p.next_pose) p.next_pose[gi] = make_float4(x, y, th, v);
+            if (p.reward && a > 0) p.reward[gi] = 0.0f;
+          }
+          if (want_final) p.final_pose[gi] = make_float4(x, y, th, v);
+          if (!point_in_polygon(scn.road_x, scn.road_y, n_road, x, y)) {
+            dead |= 1u << a;
+            continue;
+          }
         }
-        if (p.final_pose && p.do_rollout) p.final_pose[gi] = make_float4(nx, ny, nth, nv);
-        if (!point_in_polygon(scn.road_x, scn.road_y, scn.n_road_pts, nx, ny)) {
-          dead |= 1u << i;
-          continue;
+        // Frenet projection on every lane corridor; current corridor = arg min |d|
+        float best = kBig;
+        int bc = 0;
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+          const Proj pr = project(scn.corridors[c], x, y);
+          const float m = pr.in ? bm_abs(pr.d) : kBig;
+          ca[(L_PROJ + 2 * c) * fstride] = pr.s;
+          ca[(L_PROJ + 2 * c + 1) * fstride] = pr.in ? pr.d : kBig;
+          const bool better = m < best;
+          best = better ? m : best;
+          bc = better ? c : bc;
+          if (goal_frenet && a == 0 && c == scn.goal.corridor) {
+            goal_d = pr.d;
+            goal_in = pr.in;
+            goal_ang = bm_norm_angle(th - scn.corridors[c].angle[pr.seg]);
+          }
         }
-        float gd, ga;
-        bool gin;
-        const int ncur = publish_agent(i, nx, ny, nth, false, gd, gin, ga);
-        STI(L_CUR, i) = ncur | (word & ~0xff);
-        ST(L_V, i) = nv;
-        if (ego_alive) {
-          // EvaluatorCollisionEgoAgent / EvaluatorStaticSafeDist pair (ego, i)
-          const float cth = segcs[cur * BMCTS_MAX_CORRIDOR_PTS + sg];
-          const float sth = segsn[cur * BMCTS_MAX_CORRIDOR_PTS + sg];
-          const Box bj = agent_box(scn, i, nx, ny, cth, sth, 0.0f, 0.0f);
+        ca[L_CUR * fstride] = __int_as_float(word | bc);
+        ca[L_V * fstride] = v;
+        if (!fresh && a > 0) {
+          // EvaluatorCollisionEgoAgent / EvaluatorStaticSafeDist pair (ego, a); masked below
+          // when the ego itself left the map
+          const Box bj = agent_box(scn, a, x, y, cth, sth, 0.0f, 0.0f);
           if (boxes_overlap(be, bj)) fl |= BMCTS_F_COLLISION_OTHER;
           if (add_sd && boxes_overlap(bs, bj)) fl |= BMCTS_F_STATIC_SAFE_DIST;
         }
@@ -439,34 +461,40 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
     if (T > 1) {
       dead = group_or<T>(dead);
       fl = group_or<T>(fl);
+      goal_d = group_lead<T>(goal_d, lane);
+      goal_ang = group_lead<T>(goal_ang, lane);
+      goal_in = __shfl_sync(0xffffffffu, (int)goal_in, lane & ~(T - 1)) != 0;
     }
     am &= ~dead;
+    const bool ego_alive = (am & 1u) != 0;
     group_sync<T>();  // post-step Frenet table complete
 
     // --------------------------------------- mcts_observed_world_evaluation (ego view)
     float reward = 0.0f, c0 = 0.0f, c1 = 0.0f;
-    uint32_t f = fl;
-    if (active) {
-      if (!ego_alive) {
-        f |= BMCTS_F_OUT_OF_MAP;
-      } else {
-        // EvaluatorSafeDistDrivableArea / EvaluatorGoalReached: corner-in-polygon tests,
-        // split over the lanes of the group
-        const Box bd = agent_box(scn, 0, ex, ey, ecs, esn, cfg.drivable_lat_safe_dist,
-                                 cfg.drivable_lon_safe_dist);
-        uint32_t fc = 0;
-        for (int q = t; q < 4; q += T) {
-          if (!corner_in_polygon(bd, q, scn.road_x, scn.road_y, scn.n_road_pts))
-            fc |= BMCTS_F_COLLISION_DRIVABLE;
-          if (goal_poly && !corner_in_polygon(be, q, scn.goal.px, scn.goal.py, scn.goal.n_pts))
-            fc |= kGoalFailBit;
-        }
-        f |= fc;
+    uint32_t f = ego_alive ? fl : 0u;
+    if (stepping && ego_alive) {
+      // EvaluatorSafeDistDrivableArea / EvaluatorGoalReached: corner-in-polygon tests,
+      // items 0-3 = inflated shape vs road corridor, 4-7 = shape vs goal polygon, split
+      // over the lanes of the group
+      const Box bd = agent_box(scn, 0, ex, ey, ecs, esn, cfg.drivable_lat_safe_dist,
+                               cfg.drivable_lon_safe_dist);
+      const int n_items = goal_poly ? 8 : 4;
+#pragma unroll 1
+      for (int q = t; q < n_items; q += T) {
+        const bool road = q < 4;
+        float cx, cy;
+        box_corner(road ? bd : be, q & 3, cx, cy);
+        const bool in = point_in_polygon(road ? scn.road_x : scn.goal.px,
+                                         road ? scn.road_y : scn.goal.py,
+                                         road ? n_road : scn.goal.n_pts, cx, cy);
+        if (!in) f |= road ? (uint32_t)BMCTS_F_COLLISION_DRIVABLE : kGoalFailBit;
       }
     }
     if (T > 1) f = group_or<T>(f);
-    if (active) {
-      if (ego_alive) {
+    if (stepping) {
+      if (!ego_alive) {
+        f |= BMCTS_F_OUT_OF_MAP;
+      } else {
         if (goal_poly && !(f & kGoalFailBit)) f |= BMCTS_F_GOAL_REACHED;
         if (goal_frenet) {
           const bmcts_goal& gl = scn.goal;
@@ -478,24 +506,25 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
         if (add_sd) {
           // EvaluatorDynamicSafeDist: nearest agents ahead of / behind the ego in its corridor
           const int cur = STI(L_CUR, 0) & 0xff;
-          const float s_e = ST(L_PROJ + 2 * cur, 0);
+          const float* tab_s = col + (L_PROJ + 2 * cur) * fstride;
+          const float* tab_d = tab_s + fstride;
+          const float s_e = tab_s[0];
           const float hwc = scn.corridors[cur].half_width;
           int jf = -1, jr = -1;
           float ds_f = kBig, ds_r = kBig;
+#pragma unroll 1
           for (uint32_t m = am & ~1u; m; m &= m - 1u) {
             const int j = __ffs(m) - 1;
-            const float dj = ST(L_PROJ + 2 * cur + 1, j);
-            if (!(bm_abs(dj) <= hwc)) continue;
-            const float ds = ST(L_PROJ + 2 * cur, j) - s_e;
-            if (ds > 0.0f && ds < ds_f) {
-              ds_f = ds;
-              jf = j;
-            }
+            const float dj = tab_d[j * NC];
+            const float ds = tab_s[j * NC] - s_e;
             const float dr = -ds;
-            if (dr > 0.0f && dr < ds_r) {
-              ds_r = dr;
-              jr = j;
-            }
+            const bool inc = bm_abs(dj) <= hwc;
+            const bool bf = inc && ds > 0.0f && ds < ds_f;
+            const bool br = inc && dr > 0.0f && dr < ds_r;
+            ds_f = bf ? ds : ds_f;
+            jf = bf ? j : jf;
+            ds_r = br ? dr : ds_r;
+            jr = br ? j : jr;
           }
           bool safe = true;
           if (jf >= 0) {
@@ -521,7 +550,7 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
     }
 
     // ------------------------------------------------ outputs / accumulation
-    if (active) {
+    if (stepping) {
       bool finished = false;
       if (expand) {
         if (t == 0) {
@@ -563,11 +592,15 @@ __global__ void __launch_bounds__(512) rollout_lane_kernel(const KernelArgs p,
                                  __int_as_float(n), __int_as_float(agent_steps),
                                  __uint_as_float(am));
           }
-          if (p.ret_agents)
-            for (int a = t; a < A; a += T) p.ret_agents[(size_t)a * p.n + rid] = (a == 0) ? R : 0.0f;
+          if (p.ret_agents) {
+#pragma unroll 1
+            for (int a = t; a < A; a += T)
+              p.ret_agents[(size_t)a * p.n + rid] = (a == 0) ? R : 0.0f;
+          }
         }
       }
     }
+    fresh = false;
   }
 #undef ST
 #undef STI
