@@ -127,7 +127,7 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
   long best_warps = -1;
-  for (int W = 16; W >= 1; --W) {
+  for (int W = BMCTS_LANE_MAX_THREADS / 32; W >= 1; --W) {
     if (force_W > 0 && W != force_W) continue;
     const bmcts::LaneLayout lay = bmcts::lane_layout(a.A, a.C, a.H, T, W);
     if ((int)lay.total > e->max_smem_optin) continue;
@@ -165,6 +165,9 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
   e->launches++;
   e->lane_T = T;
   e->lane_W = best_W;
+  if (std::getenv("BMCTS_DEBUG"))
+    std::fprintf(stderr, "[bmcts] lane kernel T=%d W=%d blocks/SM=%d grid=%ld smem=%zu n=%d\n", T, best_W,
+                 best_blocks, grid, lay.total, a.n);
   return BMCTS_OK;
 }
 

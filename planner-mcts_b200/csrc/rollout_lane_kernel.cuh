@@ -17,8 +17,10 @@
 // is drained (rollouts end at different steps).
 //
 // Per-rollout state in shared memory, [field][agent][column] with column = group index in
-// the warp (bank = column: conflict free): velocity, Frenet (s, d) on every lane corridor,
-// current corridor + hypothesis id, and the planned (s, v) of the synchronous update.  The
+// the warp (bank = column: conflict free): velocity, arc length s on every lane corridor,
+// current corridor + hypothesis id, and the planned (s, v) of the synchronous update; which
+// agents are inside which corridor (|d| <= half width) is one bit mask per corridor in
+// registers, so the leader search only visits the agents of the own corridor.  The
 // Cartesian pose of an IDM agent is a function of (corridor, s) and is rebuilt when needed;
 // the ego pose lives in registers.  Lane geometry, road polygon, goal, shapes, hypothesis
 // table, macro actions and the config are staged once per block.
@@ -35,7 +37,7 @@
 namespace bmcts {
 
 // per-agent state fields of a column
-enum { L_V = 0, L_NS, L_NV, L_CUR, L_PROJ };  // L_PROJ + 2*c = s, +1 = d_eff on corridor c
+enum { L_V = 0, L_NS, L_NV, L_CUR, L_PROJ };  // L_PROJ + c = arc length s on corridor c
 
 constexpr size_t kScnPrefixBytes = offsetof(bmcts_scenario, hypotheses);
 static_assert(kScnPrefixBytes % 8 == 0, "scenario prefix is staged with 8-byte copies");
@@ -59,7 +61,7 @@ __host__ __device__ inline LaneLayout lane_layout(int A, int C, int H, int T, in
   l.off_hflags = b;
   b += smem_align16(sizeof(uint32_t) * (size_t)(H > 0 ? H : 1));
   l.off_state = b;
-  l.warp_bytes = sizeof(float) * (size_t)(L_PROJ + 2 * C) * A * (32 / T);
+  l.warp_bytes = sizeof(float) * (size_t)(L_PROJ + C) * A * (32 / T);
   l.total = b + l.warp_bytes * warps;
   return l;
 }
@@ -89,15 +91,19 @@ __device__ __forceinline__ float idm_substeps(const IdmLimits& hl, const IdmPara
   const float inv_v0 = bm_div(1.0f, bm_max(ip.v0, 1.0e-3f));
   const float inv_2sab = bm_div(1.0f, 2.0f * bm_sqrt(bm_max(ip.a_max * ip.b, 1.0e-6f)));
   const float half_dt2 = (0.5f * dt) * dt;
+  const uint32_t lead_mask = has_leader ? 0xffffffffu : 0u;
   float trav = 0.0f, acc = 0.0f;
+#pragma unroll 2
   for (int q = 0; q < nsub; ++q) {
     const float xr = nv * inv_v0;
     const float pw = EXP4 ? ((xr * xr) * xr) * xr : bm_powi(xr, hl.exponent);
     const float free_term = 1.0f - pw;
     const float dv = nv - v_l;
     const float s_star = ip.s0 + bm_max(0.0f, bm_fma(nv, ip.T, (nv * dv) * inv_2sab));
-    // without a leader the interaction term is exactly zero: free_term - 0*0 == free_term
-    const float qq = has_leader ? bm_div(s_star, bm_max(gap, kGapEps)) : 0.0f;
+    // without a leader the interaction term is exactly zero: free_term - 0*0 == free_term;
+    // lead_mask is all ones / all zeros, so the quotient is kept or cleared without a branch
+    const float qd = bm_div(s_star, bm_max(gap, kGapEps));
+    const float qq = __uint_as_float(__float_as_uint(qd) & lead_mask);
     acc = bm_clamp(ip.a_max * (free_term - qq * qq), hl.acc_lo, hl.acc_hi);
     const float ds = bm_max(0.0f, bm_fma(acc, half_dt2, nv * dt));
     nv = bm_clamp(bm_fma(acc, dt, nv), hl.v_min, hl.v_max);
@@ -109,10 +115,10 @@ __device__ __forceinline__ float idm_substeps(const IdmLimits& hl, const IdmPara
 }
 
 #ifndef BMCTS_LANE_MAX_THREADS
-#define BMCTS_LANE_MAX_THREADS 512
+#define BMCTS_LANE_MAX_THREADS 384
 #endif
 #ifndef BMCTS_LANE_MIN_BLOCKS
-#define BMCTS_LANE_MIN_BLOCKS 1
+#define BMCTS_LANE_MIN_BLOCKS 2
 #endif
 
 template <int T>
@@ -197,6 +203,8 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
   float ex = 0.0f, ey = 0.0f, eth = 0.0f, ev = 0.0f, ecs = 1.0f, esn = 0.0f;
   float goal_d = 0.0f, goal_ang = 0.0f;
   bool goal_in = false;
+  uint32_t inc0 = 0, inc1 = 0, inc2 = 0, inc3 = 0;  // agents inside corridor 0..3
+#define INC(c) ((c) == 0 ? inc0 : (c) == 1 ? inc1 : (c) == 2 ? inc2 : inc3)
 
   for (;;) {
     // ------------------------------------------------ acquire the next rollout
@@ -226,6 +234,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         disc = cfg.discount_factor;
         R = C0 = C1 = L = 0.0f;
         f_any = f_last = 0;
+        inc0 = inc1 = inc2 = inc3 = 0;
         const float4 q0 = p.pose[rid];  // ego pose (agent slot 0)
         ex = q0.x;
         ey = q0.y;
@@ -257,19 +266,16 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         const int hyp = word >> 8;
         const bmcts_hypothesis& h = scn.hypotheses[hyp];
         const uint32_t hf = hflags[hyp];
-        const float* tab_s = col + (L_PROJ + 2 * cur) * fstride;
-        const float* tab_d = tab_s + fstride;
+        const float* tab_s = col + (L_PROJ + cur) * fstride;
         const float s_cur = tab_s[i * NC];
         // BaseIDM::CalcRelativeValues: nearest alive agent ahead inside the corridor
-        const float hwc = scn.corridors[cur].half_width;
         int jf = -1;
         float ds_f = kBig;
 #pragma unroll 1
-        for (uint32_t m = pre & ~(1u << i); m; m &= m - 1u) {
+        for (uint32_t m = pre & INC(cur) & ~(1u << i); m; m &= m - 1u) {
           const int j = __ffs(m) - 1;
-          const float dj = tab_d[j * NC];
           const float ds = tab_s[j * NC] - s_cur;
-          const bool better = bm_abs(dj) <= hwc && ds > 0.0f && ds < ds_f;
+          const bool better = ds > 0.0f && ds < ds_f;
           ds_f = better ? ds : ds_f;
           jf = better ? j : jf;
         }
@@ -370,7 +376,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
     const Box be = agent_box(scn, 0, ex, ey, ecs, esn, 0.0f, 0.0f);
     const Box bs = agent_box(scn, 0, ex, ey, ecs, esn, cfg.static_lat_safe_dist,
                              cfg.static_lon_safe_dist);
-    uint32_t fl = 0, dead = 0;
+    uint32_t fl = 0, dead = 0, pubs = 0, in0 = 0, in1 = 0, in2 = 0, in3 = 0;
     if (active) {
 #pragma unroll 1
       for (int a = t; a < A; a += T) {
@@ -432,19 +438,27 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         // Frenet projection on every lane corridor; current corridor = arg min |d|
         float best = kBig;
         int bc = 0;
+        const uint32_t bit = 1u << a;
+        pubs |= bit;
 #pragma unroll 1
         for (int c = 0; c < C; ++c) {
-          const Proj pr = project(scn.corridors[c], x, y);
-          const float m = pr.in ? bm_abs(pr.d) : kBig;
-          ca[(L_PROJ + 2 * c) * fstride] = pr.s;
-          ca[(L_PROJ + 2 * c + 1) * fstride] = pr.in ? pr.d : kBig;
+          const bmcts_corridor& cc = scn.corridors[c];
+          const Proj pr = project(cc, x, y);
+          const float ad = bm_abs(pr.d);
+          const float m = pr.in ? ad : kBig;
+          ca[(L_PROJ + c) * fstride] = pr.s;
+          const uint32_t inb = (pr.in && ad <= cc.half_width) ? bit : 0u;
+          if (c == 0) in0 |= inb;
+          if (c == 1) in1 |= inb;
+          if (c == 2) in2 |= inb;
+          if (c == 3) in3 |= inb;
           const bool better = m < best;
           best = better ? m : best;
           bc = better ? c : bc;
           if (goal_frenet && a == 0 && c == scn.goal.corridor) {
             goal_d = pr.d;
             goal_in = pr.in;
-            goal_ang = bm_norm_angle(th - scn.corridors[c].angle[pr.seg]);
+            goal_ang = bm_norm_angle(th - cc.angle[pr.seg]);
           }
         }
         ca[L_CUR * fstride] = __int_as_float(word | bc);
@@ -461,11 +475,20 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
     if (T > 1) {
       dead = group_or<T>(dead);
       fl = group_or<T>(fl);
+      pubs = group_or<T>(pubs);
+      in0 = group_or<T>(in0);
+      if (C > 1) in1 = group_or<T>(in1);
+      if (C > 2) in2 = group_or<T>(in2);
+      if (C > 3) in3 = group_or<T>(in3);
       goal_d = group_lead<T>(goal_d, lane);
       goal_ang = group_lead<T>(goal_ang, lane);
       goal_in = __shfl_sync(0xffffffffu, (int)goal_in, lane & ~(T - 1)) != 0;
     }
     am &= ~dead;
+    inc0 = (inc0 & ~pubs) | in0;
+    inc1 = (inc1 & ~pubs) | in1;
+    inc2 = (inc2 & ~pubs) | in2;
+    inc3 = (inc3 & ~pubs) | in3;
     const bool ego_alive = (am & 1u) != 0;
     group_sync<T>();  // post-step Frenet table complete
 
@@ -506,21 +529,17 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         if (add_sd) {
           // EvaluatorDynamicSafeDist: nearest agents ahead of / behind the ego in its corridor
           const int cur = STI(L_CUR, 0) & 0xff;
-          const float* tab_s = col + (L_PROJ + 2 * cur) * fstride;
-          const float* tab_d = tab_s + fstride;
+          const float* tab_s = col + (L_PROJ + cur) * fstride;
           const float s_e = tab_s[0];
-          const float hwc = scn.corridors[cur].half_width;
           int jf = -1, jr = -1;
           float ds_f = kBig, ds_r = kBig;
 #pragma unroll 1
-          for (uint32_t m = am & ~1u; m; m &= m - 1u) {
+          for (uint32_t m = am & INC(cur) & ~1u; m; m &= m - 1u) {
             const int j = __ffs(m) - 1;
-            const float dj = tab_d[j * NC];
             const float ds = tab_s[j * NC] - s_e;
             const float dr = -ds;
-            const bool inc = bm_abs(dj) <= hwc;
-            const bool bf = inc && ds > 0.0f && ds < ds_f;
-            const bool br = inc && dr > 0.0f && dr < ds_r;
+            const bool bf = ds > 0.0f && ds < ds_f;
+            const bool br = dr > 0.0f && dr < ds_r;
             ds_f = bf ? ds : ds_f;
             jf = bf ? j : jf;
             ds_r = br ? dr : ds_r;
@@ -604,6 +623,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
   }
 #undef ST
 #undef STI
+#undef INC
 }
 
 }  // namespace bmcts
