@@ -266,7 +266,7 @@ def run_ours(args):
                      "peak_def": "2 x 128 FP32 lanes x 148 SMs x SM clock under load (%s MHz); "
                                  "algorithmic FLOPs per agent-step = %.0f (SURVEY.md 8d)" %
                                  (sm_mhz, flop),
-                     "kernel": "bmcts::rollout_kernel", "kernel_ms": k_ms, "traffic": None},
+                     "kernel": "bmcts::rollout_lane_coop_kernel" if coop else "bmcts::rollout_lane_kernel", "kernel_ms": k_ms, "traffic": None},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"),
                          "unit": "GB/s", "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0),
                          "peak_kind": peak_kind, "traffic": None},

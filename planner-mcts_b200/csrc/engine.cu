@@ -16,8 +16,9 @@
 #include <vector>
 
 #include "bmcts_c.h"
-#include "rollout_kernel.cuh"
+#include "rollout_device.cuh"
 #include "rollout_lane_kernel.cuh"
+#include "rollout_lane_coop_kernel.cuh"
 
 namespace {
 
@@ -99,37 +100,25 @@ int upload_dt_table(bmcts_engine* e) {
   return BMCTS_OK;
 }
 
-template <bool COOP>
-int launch_rollout(bmcts_engine* e, const bmcts::KernelArgs& a) {
-  const size_t smem = bmcts::rollout_smem_bytes(a.A, a.C);
-  if ((int)smem > e->max_smem_optin)
-    return fail(e, BMCTS_ERR_UNSUPPORTED, "scenario needs more shared memory than the SM offers");
-  CU(cudaFuncSetAttribute(bmcts::rollout_kernel<COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)smem));
-  const int blocks = (a.n + bmcts::kLanes - 1) / bmcts::kLanes;
-  const int threads = a.A * bmcts::kLanes;
-  bmcts::rollout_kernel<COOP><<<blocks, threads, smem, e->stream>>>(a);
-  CU(cudaGetLastError());
-  e->launches++;
-  return BMCTS_OK;
-}
-
 // Launch geometry of the lane kernel (rollout_lane_kernel.cuh).  T lanes per rollout: 1 when
 // the batch fills the GPU, more when it does not (an MCTS wave of a few hundred leaves) or
 // when the per-rollout state of a large scenario would leave too few warps resident.
 // W warps per block share one staged scenario; the grid is persistent (blocks/SM x SMs).
-template <int T>
+template <int T, bool COOP>
 int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
-  auto kern = bmcts::rollout_lane_kernel<T>;
+  auto kern = COOP ? bmcts::rollout_lane_coop_kernel<T> : bmcts::rollout_lane_kernel<T>;
+  auto layout = [&](int W) {
+    return COOP ? bmcts::lane_coop_layout(a.A, a.C, T, W) : bmcts::lane_layout(a.A, a.C, a.H, T, W);
+  };
   const int NC = 32 / T;
   const int groups = a.n;
   int best_W = 1, best_blocks = 1;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                           cudaSharedmemCarveoutMaxShared));
-  long best_warps = -1;
+  long best_score = -1;
   for (int W = BMCTS_LANE_MAX_THREADS / 32; W >= 1; --W) {
     if (force_W > 0 && W != force_W) continue;
-    const bmcts::LaneLayout lay = bmcts::lane_layout(a.A, a.C, a.H, T, W);
+    const bmcts::LaneLayout lay = layout(W);
     if ((int)lay.total > e->max_smem_optin) continue;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
     int blocks = 0;
@@ -139,18 +128,18 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
     const long need_warps = (groups + NC - 1) / NC;
     long resident = (long)blocks * W * e->sm_count;
     long useful = resident < need_warps ? resident : need_warps;
-    // blocks needed to hold `useful` warps; prefer the geometry that runs most warps at once,
-    // then the one that spreads them over more SMs (smaller W)
+    // prefer the geometry that runs most warps at once, then the one that spreads them
+    // over more SMs (smaller W)
     long score = useful * 64 - (useful == need_warps ? W : 0);
-    if (score > best_warps) {
-      best_warps = score;
+    if (score > best_score) {
+      best_score = score;
       best_W = W;
       best_blocks = blocks;
     }
   }
-  if (best_warps < 0)
+  if (best_score < 0)
     return fail(e, BMCTS_ERR_UNSUPPORTED, "scenario needs more shared memory than the SM offers");
-  const bmcts::LaneLayout lay = bmcts::lane_layout(a.A, a.C, a.H, T, best_W);
+  const bmcts::LaneLayout lay = layout(best_W);
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
   const long need_blocks = ((long)groups + (long)NC * best_W - 1) / ((long)NC * best_W);
   long grid = (long)best_blocks * e->sm_count;
@@ -166,34 +155,47 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
   e->lane_T = T;
   e->lane_W = best_W;
   if (std::getenv("BMCTS_DEBUG"))
-    std::fprintf(stderr, "[bmcts] lane kernel T=%d W=%d blocks/SM=%d grid=%ld smem=%zu n=%d\n", T, best_W,
-                 best_blocks, grid, lay.total, a.n);
+    std::fprintf(stderr, "[bmcts] lane kernel coop=%d T=%d W=%d blocks/SM=%d grid=%ld smem=%zu n=%d\n",
+                 (int)COOP, T, best_W, best_blocks, grid, lay.total, a.n);
   return BMCTS_OK;
 }
 
+// Lanes per rollout: the smallest T whose per-warp state (32/T rollouts) leaves about 20
+// warps resident per SM; more when the batch is too small to fill the GPU with one lane per
+// rollout (an MCTS wave of a few hundred leaves).
+template <bool COOP>
 int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a) {
   int T = 0, W = 0;
   if (const char* s = std::getenv("BMCTS_LANE_T")) T = std::atoi(s);
   if (const char* s = std::getenv("BMCTS_LANE_W")) W = std::atoi(s);
   if (T != 1 && T != 2 && T != 4) {
-    // lanes the batch would occupy with one lane per rollout vs. what the GPU keeps resident
-    const long lanes_resident = (long)e->sm_count * 32 * 16;
+    const size_t budget = 11 * 1024 + 512;
+    auto warp_bytes = [&](int t) {
+      return COOP ? bmcts::lane_coop_layout(a.A, a.C, t, 1).warp_bytes
+                  : bmcts::lane_layout(a.A, a.C, a.H, t, 1).warp_bytes;
+    };
     T = 1;
-    if ((long)a.n * 2 <= lanes_resident && a.A >= 3) T = 2;
-    if ((long)a.n * 4 <= lanes_resident && a.A >= 5) T = 4;
+    if (warp_bytes(1) > budget) T = 2;
+    if (warp_bytes(2) > budget) T = 4;
+    const long lanes_resident = (long)e->sm_count * 32 * 16;
+    if (T < 2 && (long)a.n * 2 <= lanes_resident && a.A >= 3) T = 2;
+    if (T < 4 && (long)a.n * 4 <= lanes_resident && a.A >= 5) T = 4;
   }
   switch (T) {
-    case 4: return launch_lane_T<4>(e, a, W);
-    case 2: return launch_lane_T<2>(e, a, W);
-    default: return launch_lane_T<1>(e, a, W);
+    case 4: return launch_lane_T<4, COOP>(e, a, W);
+    case 2: return launch_lane_T<2, COOP>(e, a, W);
+    default: return launch_lane_T<1, COOP>(e, a, W);
   }
 }
 
 int launch(bmcts_engine* e, const bmcts::KernelArgs& a) {
   if (a.n <= 0) return BMCTS_OK;
   CU(cudaEventRecord(e->ev_start, e->stream));
-  int st = (e->cfg.state_kind == BMCTS_STATE_COOPERATIVE) ? launch_rollout<true>(e, a)
-                                                          : launch_lane(e, a);
+  int st;
+  if (e->cfg.state_kind == BMCTS_STATE_COOPERATIVE)
+    st = launch_lane<true>(e, a);
+  else
+    st = launch_lane<false>(e, a);
   if (st) return st;
   CU(cudaEventRecord(e->ev_stop, e->stream));
   e->timed = true;

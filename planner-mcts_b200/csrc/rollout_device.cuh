@@ -1,0 +1,430 @@
+// rollout_device.cuh -- device functions shared by the sm_100a kernels of the MCTS
+// leaf-evaluation path (Philox, Frenet projection, rectangle / polygon predicates, IDM,
+// flags -> reward / cost / terminal) and the hypothesis-likelihood kernel (K4).
+//
+// The rollout kernels themselves are rollout_lane_kernel.cuh (hypothesis / risk-constraint
+// states) and rollout_lane_coop_kernel.cuh (cooperative state).  Every float operation
+// mirrors oracle/bmcts_oracle.c operation by operation (compile with --fmad=false; FMAs only
+// where bm_fma is written).  Paths cited are relative to
+// /root/reference/bark_mcts/models/behavior/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bmcts_c.h"
+#include "bmcts_math.h"
+
+namespace bmcts {
+
+constexpr float kBig = 1.0e30f;
+constexpr float kGapEps = 1.0e-3f;
+constexpr uint32_t kGoalFailBit = 1u << 16;  // scratch bit: a goal-polygon corner is outside
+
+static_assert(sizeof(bmcts_scenario) % 16 == 0, "scenario is staged with 16-byte copies");
+static_assert(sizeof(bmcts_config) % 4 == 0, "config is staged with 4-byte copies");
+
+struct KernelArgs {
+  // inputs (agent-major SoA, see bmcts_c.h)
+  const float4* pose;
+  const uint32_t* alive;
+  const uint8_t* hyp;
+  const uint16_t* depth;
+  const uint8_t* action;     // expansion only
+  const uint64_t* draw_id;   // expansion only
+  // step outputs (expansion), each may be null
+  float4* next_pose;
+  uint32_t* next_alive;
+  float* reward;
+  float* cost;
+  uint32_t* flags;
+  float* last_action;
+  // rollout outputs
+  bmcts_rollout_result* result;
+  float* ret_agents;
+  float4* final_pose;
+  // device copies of scenario / config / prediction-time table
+  const bmcts_scenario* scn;
+  const bmcts_config* cfg;
+  const float* dt_table;  // null when prediction_alpha == 0
+  int n;
+  int A;
+  int C;
+  int H;
+  int do_expand;
+  int do_rollout;
+  uint32_t key0, key1;
+  uint64_t first_rollout_id;
+};
+
+__host__ __device__ inline size_t smem_align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint4 draw(uint32_t k0, uint32_t k1, uint64_t id, uint32_t agent,
+                                      uint32_t domain, uint32_t index) {
+  return philox4x32_10(
+      make_uint4((uint32_t)id, (uint32_t)(id >> 32), agent | (domain << 16), index), k0, k1);
+}
+
+struct Proj {
+  float s, d;
+  int seg;
+  bool in;
+};
+
+// Frenet projection on a corridor centre line (oracle_project).  Corridors have a handful
+// of segments: the loop is kept rolled (an unrolled-by-4 body with its remainder loops
+// costs more than it saves at trip counts of 1-3) and the best-so-far update is selects.
+__device__ __forceinline__ Proj project(const bmcts_corridor& c, float x, float y) {
+  const int nseg = c.n_pts - 1;
+  float best_d2 = kBig, best_u = 0.0f, best_raw = 0.0f, best_cross = 0.0f;
+  int best = 0;
+#pragma unroll 1
+  for (int k = 0; k < nseg; ++k) {
+    const float tx = c.tx[k], ty = c.ty[k];
+    const float rx = x - c.px[k];
+    const float ry = y - c.py[k];
+    const float u = bm_fma(rx, tx, ry * ty);
+    const float uc = bm_clamp(u, 0.0f, c.seg_len[k]);
+    const float ex = bm_fma(-uc, tx, rx);
+    const float ey = bm_fma(-uc, ty, ry);
+    const float d2 = bm_fma(ex, ex, ey * ey);
+    const float cross = bm_fma(tx, ry, -(ty * rx));
+    const bool better = d2 < best_d2;
+    best_d2 = better ? d2 : best_d2;
+    best = better ? k : best;
+    best_u = better ? uc : best_u;
+    best_raw = better ? u : best_raw;
+    best_cross = better ? cross : best_cross;
+  }
+  Proj p;
+  p.s = c.s0[best] + best_u;
+  p.d = best_cross;
+  p.seg = best;
+  p.in = !((best == 0 && best_raw < 0.0f) || (best == nseg - 1 && best_raw > c.seg_len[best]));
+  return p;
+}
+
+// even-odd rule, division free (oracle point_in_polygon)
+__device__ __forceinline__ bool point_in_polygon(const float* px, const float* py, int n, float x,
+                                                 float y) {
+  int inside = 0;
+  float xj = px[n - 1], yj = py[n - 1];
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const float xi = px[i], yi = py[i];
+    if ((yi > y) != (yj > y)) {
+      const float lhs = (x - xi) * (yj - yi);
+      const float rhs = (xj - xi) * (y - yi);
+      const int cross = (yj > yi) ? (lhs < rhs) : (lhs > rhs);
+      inside ^= cross;
+    }
+    xj = xi;
+    yj = yi;
+  }
+  return inside != 0;
+}
+
+struct Box {
+  float cx, cy, c, s, hl, hw;
+};
+
+__device__ __forceinline__ Box agent_box(const bmcts_scenario& scn, int a, float x, float y,
+                                         float c, float s, float lat, float lon) {
+  float front = (scn.agent_length[a] - scn.agent_rear[a]) + lon;
+  float back = scn.agent_rear[a] + lon;
+  Box b;
+  b.hl = 0.5f * (front + back);
+  float off = 0.5f * (front - back);
+  b.cx = bm_fma(off, c, x);
+  b.cy = bm_fma(off, s, y);
+  b.c = c;
+  b.s = s;
+  b.hw = bm_fma(0.5f, scn.agent_width[a], lat);
+  return b;
+}
+
+__device__ __forceinline__ bool boxes_overlap(const Box& A, const Box& B) {
+  float tx = B.cx - A.cx;
+  float ty = B.cy - A.cy;
+  float cd = bm_fma(A.c, B.c, A.s * B.s);
+  float sd = bm_fma(A.c, B.s, -(A.s * B.c));
+  float acd = bm_abs(cd), asd = bm_abs(sd);
+  float p0 = bm_abs(bm_fma(tx, A.c, ty * A.s));
+  bool sep = p0 >= A.hl + bm_fma(B.hl, acd, B.hw * asd);
+  float p1 = bm_abs(bm_fma(ty, A.c, -(tx * A.s)));
+  sep = sep || (p1 >= A.hw + bm_fma(B.hl, asd, B.hw * acd));
+  float p2 = bm_abs(bm_fma(tx, B.c, ty * B.s));
+  sep = sep || (p2 >= B.hl + bm_fma(A.hl, acd, A.hw * asd));
+  float p3 = bm_abs(bm_fma(ty, B.c, -(tx * B.s)));
+  sep = sep || (p3 >= B.hw + bm_fma(A.hl, asd, A.hw * acd));
+  return !sep;
+}
+
+__device__ __forceinline__ void box_corner(const Box& b, int k, float& x, float& y) {
+  float lx = (k == 0 || k == 1) ? b.hl : -b.hl;
+  float ly = (k == 0 || k == 3) ? b.hw : -b.hw;
+  x = b.cx + (lx * b.c - ly * b.s);
+  y = b.cy + (lx * b.s + ly * b.c);
+}
+
+__device__ __forceinline__ bool corner_in_polygon(const Box& b, int k, const float* px,
+                                                  const float* py, int n) {
+  float x, y;
+  box_corner(b, k, x, y);
+  return point_in_polygon(px, py, n, x, y);
+}
+
+// Rizaldi et al. longitudinal safe distance (oracle safe_dist_longitudinal)
+__device__ __forceinline__ bool safe_dist_longitudinal(float v_f, float v_r, float dist, float a_r,
+                                                       float a_f, float delta) {
+  if (dist < 0.0f) return false;
+  float t_stop_f = bm_div(-v_f, a_f);
+  float v_f_star = (delta <= t_stop_f) ? bm_fma(a_f, delta, v_f) : 0.0f;
+  float t_stop_f_star = bm_div(-v_f_star, a_r);
+  float t_stop_r = bm_div(-v_r, a_r);
+  float sd0 = v_r * delta - bm_div(v_r * v_r, 2.0f * a_r);
+  float sd1 = sd0 + bm_div(v_f * v_f, 2.0f * a_f);
+  float front_react = v_f * delta + (0.5f * a_f) * (delta * delta);
+  float sd3 = sd0 - front_react;
+  if (dist > sd0 || (delta <= t_stop_f && dist > sd3)) return true;
+  if (delta <= t_stop_f && a_f > a_r && v_f_star < v_r && t_stop_r < t_stop_f_star) {
+    float rel = v_f_star - v_r;
+    float sd2 = bm_div(rel * rel, 2.0f * (a_f - a_r)) - front_react + v_r * delta;
+    return dist > sd2;
+  }
+  return dist > sd1;
+}
+
+// mcts_state_base.hpp:107-118
+__device__ __forceinline__ float reward_from_flags(const bmcts_config& cfg, uint32_t f, float dt) {
+  int coll = (f & BMCTS_F_COLLISION_OTHER) != 0;
+  int stat = (f & BMCTS_F_STATIC_SAFE_DIST) != 0;
+  int dyn = (f & BMCTS_F_DYNAMIC_SAFE_DIST) != 0;
+  int driv = (f & BMCTS_F_COLLISION_DRIVABLE) != 0;
+  int goal = (f & BMCTS_F_GOAL_REACHED) != 0;
+  int oom = (f & BMCTS_F_OUT_OF_MAP) != 0;
+  int sd_pred = cfg.static_safe_dist_is_terminal ? dyn : (dyn || stat);
+  float safe_dist_reward = ((float)sd_pred * cfg.safe_dist_violated_reward) * dt;
+  int coll_pred = coll || (cfg.static_safe_dist_is_terminal ? stat : 0);
+  float collision_reward =
+      (float)coll_pred * cfg.collision_reward + (float)(driv || oom) * cfg.out_of_drivable_reward;
+  float r = bm_max(collision_reward, cfg.collision_reward);
+  r = r + (cfg.add_safe_dist ? safe_dist_reward : 0.0f);
+  r = r + (float)goal * cfg.goal_reward;
+  r = r + cfg.step_reward;
+  return r;
+}
+
+// mcts_state_base.hpp:120-142
+__device__ __forceinline__ void costs_from_flags(const bmcts_config& cfg, uint32_t f, float dt,
+                                                 float& c0, float& c1) {
+  int coll = (f & BMCTS_F_COLLISION_OTHER) != 0;
+  int stat = (f & BMCTS_F_STATIC_SAFE_DIST) != 0;
+  int dyn = (f & BMCTS_F_DYNAMIC_SAFE_DIST) != 0;
+  int driv = (f & BMCTS_F_COLLISION_DRIVABLE) != 0;
+  int goal = (f & BMCTS_F_GOAL_REACHED) != 0;
+  int oom = (f & BMCTS_F_OUT_OF_MAP) != 0;
+  int sd_pred = cfg.static_safe_dist_is_terminal ? dyn : (dyn || stat);
+  float safe_dist_cost = ((float)sd_pred * cfg.safe_dist_violated_cost) * dt;
+  int coll_pred = coll || (cfg.static_safe_dist_is_terminal ? stat : 0) ||
+                  (cfg.dynamic_safe_dist_is_terminal ? dyn : 0);
+  float total = (float)coll_pred * cfg.collision_cost;
+  total = total + (float)(driv || oom) * cfg.out_of_drivable_cost;
+  total = total + ((cfg.add_safe_dist && !cfg.split_safe_dist_collision) ? safe_dist_cost : 0.0f);
+  total = total + (float)goal * cfg.goal_cost;
+  if (cfg.split_safe_dist_collision) {
+    c0 = cfg.chance_costs ? bm_min(safe_dist_cost, 1.0f) : safe_dist_cost;
+    c1 = bm_min(total, cfg.collision_cost) * dt;
+  } else {
+    c0 = cfg.chance_costs ? bm_min(total, 1.0f) : total;
+    c1 = 0.0f;
+  }
+}
+
+// mcts_state_base.hpp:273-277
+__device__ __forceinline__ uint32_t terminal_from_flags(const bmcts_config& cfg, uint32_t f) {
+  bool t = (f & (BMCTS_F_COLLISION_OTHER | BMCTS_F_OUT_OF_MAP | BMCTS_F_GOAL_REACHED)) != 0;
+  t = t || ((f & BMCTS_F_COLLISION_DRIVABLE) && cfg.out_of_drivable_is_terminal);
+  t = t || ((f & BMCTS_F_STATIC_SAFE_DIST) && cfg.static_safe_dist_is_terminal);
+  t = t || ((f & BMCTS_F_DYNAMIC_SAFE_DIST) && cfg.dynamic_safe_dist_is_terminal);
+  return t ? (uint32_t)BMCTS_F_TERMINAL : 0u;
+}
+
+struct IdmParams {
+  float T, s0, a_max, v0, b;
+};
+
+__device__ __forceinline__ IdmParams sample_idm_params(const bmcts_hypothesis& h, uint4 r0,
+                                                       uint4 r1) {
+  IdmParams p;
+  p.T = bm_fma(bm_u01(r0.x), h.hi[0] - h.lo[0], h.lo[0]);
+  p.s0 = bm_fma(bm_u01(r0.y), h.hi[1] - h.lo[1], h.lo[1]);
+  p.a_max = bm_fma(bm_u01(r0.z), h.hi[2] - h.lo[2], h.lo[2]);
+  p.v0 = bm_fma(bm_u01(r0.w), h.hi[3] - h.lo[3], h.lo[3]);
+  p.b = bm_fma(bm_u01(r1.x), h.hi[4] - h.lo[4], h.lo[4]);
+  return p;  // coolness (r1.y) is validated to be 0: no blend
+}
+
+struct IdmLimits {  // per-hypothesis constants hoisted out of the sub-step loop
+  float acc_lo, acc_hi, v_min, v_max;
+  int exponent;
+};
+
+__device__ __forceinline__ IdmLimits idm_limits(const bmcts_hypothesis& h) {
+  IdmLimits l;
+  l.acc_lo = h.acc_lower_bound;
+  l.acc_hi = h.acc_upper_bound;
+  l.v_min = h.min_velocity;
+  l.v_max = h.max_velocity;
+  l.exponent = h.exponent;
+  return l;
+}
+
+__device__ __forceinline__ float idm_acc(const IdmLimits& h, const IdmParams& p, float inv_v0,
+                                         float inv_2sab, bool has_leader, float v, float v_l,
+                                         float gap) {
+  float free_term = 1.0f - bm_powi(v * inv_v0, h.exponent);
+  float acc;
+  if (has_leader) {
+    float dv = v - v_l;
+    float s_star = p.s0 + bm_max(0.0f, bm_fma(v, p.T, (v * dv) * inv_2sab));
+    float q = bm_div(s_star, bm_max(gap, kGapEps));
+    acc = p.a_max * (free_term - q * q);
+  } else {
+    acc = p.a_max * free_term;
+  }
+  return bm_clamp(acc, h.acc_lo, h.acc_hi);
+}
+
+// ---------------------------------------------------------------------------
+// K4: BehaviorHypothesisIDM::GetProbability (hypothesis/idm/hypothesis_idm.cpp:40-126)
+// one block per (agent a, hypothesis h, world w); threads stride over the samples and
+// count those that fall into the bucket of the observed action.
+struct LikelihoodArgs {
+  const float4* pose;     // [A][n_worlds]
+  const uint32_t* alive;  // [n_worlds]
+  const float* action;    // [A][n_worlds]
+  float* prob;            // [(a*H + h)*n_worlds + w]
+  const bmcts_scenario* scn;
+  int n_worlds, A, C, H;
+  int n_samples, n_buckets;
+  float lower, upper;
+  uint32_t key0, key1;
+};
+
+__global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p) {
+  __shared__ float s_s[BMCTS_MAX_AGENTS], s_d[BMCTS_MAX_AGENTS], s_v[BMCTS_MAX_AGENTS];
+  __shared__ int s_cur;
+  __shared__ float s_gap, s_vl, s_vown;
+  __shared__ int s_has_leader, s_skip, s_bucket;
+  __shared__ unsigned s_count;
+  const bmcts_scenario& scn = *p.scn;  // read through L1/L2 (few KB, hot)
+  const int w = blockIdx.x;
+  const int h = blockIdx.y;
+  const int a = blockIdx.z;
+  const int t = threadIdx.x;
+  const uint32_t am = p.alive[w];
+  const size_t out_idx = ((size_t)a * p.H + h) * p.n_worlds + w;
+  if (t == 0) {
+    s_count = 0;
+    s_skip = 0;
+    // current corridor of agent a (publish(): argmin |d| over in-range corridors)
+    float4 q = p.pose[(size_t)a * p.n_worlds + w];
+    float best = kBig;
+    int bc = 0;
+    for (int c = 0; c < p.C; ++c) {
+      Proj pr = project(scn.corridors[c], q.x, q.y);
+      float m = pr.in ? bm_abs(pr.d) : kBig;
+      if (m < best) {
+        best = m;
+        bc = c;
+      }
+    }
+    s_cur = bc;
+    s_vown = q.w;
+    if (!((am >> a) & 1u)) s_skip = 1;
+    const float act = p.action[(size_t)a * p.n_worlds + w];
+    if (act > p.upper || act < p.lower) s_skip = 1;
+    const float bucket_size = bm_div(p.upper - p.lower, (float)p.n_buckets);
+    int b = (int)floorf(bm_div(act - p.lower, bucket_size));
+    if (b > p.n_buckets - 1) b = p.n_buckets - 1;
+    if (b < 0) b = 0;
+    s_bucket = b;
+  }
+  __syncthreads();
+  if (s_skip) {
+    if (t == 0) p.prob[out_idx] = 0.0f;
+    return;
+  }
+  const int cur = s_cur;
+  if (t < p.A) {
+    float4 q = p.pose[(size_t)t * p.n_worlds + w];
+    Proj pr = project(scn.corridors[cur], q.x, q.y);
+    s_s[t] = pr.s;
+    s_d[t] = pr.in ? pr.d : kBig;
+    s_v[t] = q.w;
+  }
+  __syncthreads();
+  if (t == 0) {
+    // BaseIDM::CalcRelativeValues (find_leader)
+    float best = kBig;
+    int lead = -1;
+    const float hwc = scn.corridors[cur].half_width;
+    for (int j = 0; j < p.A; ++j) {
+      if (j == a || !((am >> j) & 1u)) continue;
+      if (!(bm_abs(s_d[j]) <= hwc)) continue;
+      float ds = s_s[j] - s_s[a];
+      if (ds > 0.0f && ds < best) {
+        best = ds;
+        lead = j;
+      }
+    }
+    s_has_leader = lead >= 0;
+    s_gap = 0.0f;
+    s_vl = 0.0f;
+    if (lead >= 0) {
+      s_gap = best - ((scn.agent_length[a] - scn.agent_rear[a]) + scn.agent_rear[lead]);
+      s_vl = s_v[lead];
+    }
+  }
+  __syncthreads();
+  const bmcts_hypothesis hy = scn.hypotheses[h];
+  const IdmLimits hl = idm_limits(hy);
+  const bool has_leader = s_has_leader != 0;
+  const float gap = s_gap, v_l = s_vl, v_own = s_vown;
+  const float bucket_size = bm_div(p.upper - p.lower, (float)p.n_buckets);
+  const int target = s_bucket;
+  unsigned cnt = 0;
+  for (int smp = t; smp < p.n_samples; smp += blockDim.x) {
+    uint64_t id = (uint64_t)(uint32_t)smp | ((uint64_t)(uint32_t)w << 32);
+    uint4 r0 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h);
+    uint4 r1 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h + 1u);
+    IdmParams ip = sample_idm_params(hy, r0, r1);
+    float inv_v0 = bm_div(1.0f, bm_max(ip.v0, 1.0e-3f));
+    float inv_2sab = bm_div(1.0f, 2.0f * bm_sqrt(bm_max(ip.a_max * ip.b, 1.0e-6f)));
+    float acc = idm_acc(hl, ip, inv_v0, inv_2sab, has_leader, v_own, v_l, gap);
+    if (acc < p.lower || acc > p.upper) continue;
+    int b = (int)floorf(bm_div(acc - p.lower, bucket_size));
+    if (b > p.n_buckets - 1) b = p.n_buckets - 1;
+    if (b < 0) b = 0;
+    cnt += (b == target);
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((t & 31) == 0 && cnt) atomicAdd(&s_count, cnt);
+  __syncthreads();
+  if (t == 0) p.prob[out_idx] = bm_div((float)s_count, (float)p.n_samples);
+}
+
+}  // namespace bmcts

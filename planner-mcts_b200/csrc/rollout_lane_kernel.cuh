@@ -6,7 +6,7 @@
 //             (mcts_state/mcts_state_hypothesis.cpp:62-114)
 //   rollout = mamcts RandomHeuristic::calculate_heuristic_values
 // (paths relative to /root/reference/bark_mcts/models/behavior/).  The cooperative state
-// keeps the agent-per-warp kernel of rollout_kernel.cuh.
+// has its own kernel with the same mapping (rollout_lane_coop_kernel.cuh).
 //
 // Mapping: T consecutive lanes (T = 1, 2 or 4) own one rollout; a warp carries 32/T
 // rollouts and never talks to another warp, so there is no block barrier in the step
@@ -26,13 +26,12 @@
 // table, macro actions and the config are staged once per block.
 //
 // Every float operation mirrors oracle/bmcts_oracle.c operation by operation (compile with
-// --fmad=false; FMAs only where bm_fma is written); the results are bit-identical to the
-// agent-per-warp kernel.
+// --fmad=false; FMAs only where bm_fma is written).
 #pragma once
 
 #include <cstddef>
 
-#include "rollout_kernel.cuh"
+#include "rollout_device.cuh"
 
 namespace bmcts {
 
@@ -59,7 +58,7 @@ __host__ __device__ inline LaneLayout lane_layout(int A, int C, int H, int T, in
   l.off_segsn = b;
   b += sizeof(float) * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS;
   l.off_hflags = b;
-  b += smem_align16(sizeof(uint32_t) * (size_t)(H > 0 ? H : 1));
+  b += smem_align16(sizeof(uint32_t) * 4 * (size_t)(H > 0 ? H : 1));  // flags, 1/v0, 1/(2 sqrt(ab))
   l.off_state = b;
   l.warp_bytes = sizeof(float) * (size_t)(L_PROJ + C) * A * (32 / T);
   l.total = b + l.warp_bytes * warps;
@@ -86,10 +85,9 @@ __device__ __forceinline__ void group_sync() {
 // IDM sub-step loop (BaseIDM::Plan, spec item 4): returns the travelled distance
 template <bool EXP4>
 __device__ __forceinline__ float idm_substeps(const IdmLimits& hl, const IdmParams& ip,
-                                              bool has_leader, float gap, float v_l, float dt,
-                                              int nsub, float& nv, float& acc_out) {
-  const float inv_v0 = bm_div(1.0f, bm_max(ip.v0, 1.0e-3f));
-  const float inv_2sab = bm_div(1.0f, 2.0f * bm_sqrt(bm_max(ip.a_max * ip.b, 1.0e-6f)));
+                                              float inv_v0, float inv_2sab, bool has_leader,
+                                              float gap, float v_l, float dt, int nsub, float& nv,
+                                              float& acc_out) {
   const float half_dt2 = (0.5f * dt) * dt;
   const uint32_t lead_mask = has_leader ? 0xffffffffu : 0u;
   float trav = 0.0f, acc = 0.0f;
@@ -164,7 +162,19 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         f |= 1u;
       if (h.hi[4] != h.lo[4]) f |= 2u;
       if (h.exponent == 4) f |= 4u;
-      hf[i] = f;
+      // the per-step constants of a hypothesis whose desired velocity / (max acc, comfortable
+      // braking) are FixedValues do not depend on the draw: computed once here
+      if (h.hi[3] == h.lo[3]) {
+        f |= 8u;
+        hf[4 * i + 1] = __float_as_uint(bm_div(1.0f, bm_max(bm_fma(0.0f, h.hi[3] - h.lo[3], h.lo[3]), 1.0e-3f)));
+      }
+      if (h.hi[2] == h.lo[2] && h.hi[4] == h.lo[4]) {
+        f |= 16u;
+        const float am_ = bm_fma(0.0f, h.hi[2] - h.lo[2], h.lo[2]);
+        const float b_ = bm_fma(0.0f, h.hi[4] - h.lo[4], h.lo[4]);
+        hf[4 * i + 2] = __float_as_uint(bm_div(1.0f, 2.0f * bm_sqrt(bm_max(am_ * b_, 1.0e-6f))));
+      }
+      hf[4 * i] = f;
     }
   }
   __syncthreads();  // the only block barrier: staging done
@@ -265,7 +275,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         const int cur = word & 0xff;
         const int hyp = word >> 8;
         const bmcts_hypothesis& h = scn.hypotheses[hyp];
-        const uint32_t hf = hflags[hyp];
+        const uint32_t hf = hflags[4 * hyp];
         const float* tab_s = col + (L_PROJ + cur) * fstride;
         const float s_cur = tab_s[i * NC];
         // BaseIDM::CalcRelativeValues: nearest alive agent ahead inside the corridor
@@ -299,10 +309,17 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         }
         const IdmParams ip = sample_idm_params(h, r0, r1);
         const IdmLimits hl = idm_limits(h);
+        const float inv_v0 = (hf & 8u) ? __uint_as_float(hflags[4 * hyp + 1])
+                                       : bm_div(1.0f, bm_max(ip.v0, 1.0e-3f));
+        const float inv_2sab =
+            (hf & 16u) ? __uint_as_float(hflags[4 * hyp + 2])
+                       : bm_div(1.0f, 2.0f * bm_sqrt(bm_max(ip.a_max * ip.b, 1.0e-6f)));
         float nv = ca[L_V * fstride], acc;
-        const float trav = (hf & 4u)
-                               ? idm_substeps<true>(hl, ip, has_leader, gap, v_l, dt, nsub, nv, acc)
-                               : idm_substeps<false>(hl, ip, has_leader, gap, v_l, dt, nsub, nv, acc);
+        const float trav =
+            (hf & 4u) ? idm_substeps<true>(hl, ip, inv_v0, inv_2sab, has_leader, gap, v_l, dt, nsub,
+                                           nv, acc)
+                      : idm_substeps<false>(hl, ip, inv_v0, inv_2sab, has_leader, gap, v_l, dt, nsub,
+                                            nv, acc);
         ca[L_NS * fstride] = bm_min(s_cur + trav, scn.corridors[cur].length);
         ca[L_NV * fstride] = nv;
         if (expand && p.last_action) p.last_action[(size_t)i * p.n + rid] = acc;
