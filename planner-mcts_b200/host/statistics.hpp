@@ -192,6 +192,7 @@ class HypothesisStatistic {
     unsigned count = 0, pending = 0;
     double ego_cost = 0.0;  // mean accumulated ego cost after this action
     bool resolved = false;
+    bool dead = false;      // merged into another entry with the same action: never selected
   };
 
   void Init(int num_hypotheses, const MctsParameters& m) {
@@ -224,42 +225,48 @@ class HypothesisStatistic {
         n_act += (double)per_hyp_[i].size();
       }
     }
-    bool any_resolved = false;
-    for (const Entry& e : tab) any_resolved = any_resolved || e.resolved;
-    // progressive widening: |actions| <= K * N^alpha
+    // progressive widening: |actions| <= K * N^alpha.  Inside a wave an entry may be chosen
+    // again before its action is known (unresolved): it is re-planned with the same draw id,
+    // which yields the same action and therefore the same child.
     bool widen = n_act <= k_ * std::pow(n_vis, alpha_);
-    int idx;
-    if (widen || !any_resolved) {
+    int idx = -1;
+    if (!widen) {
+      if (cost_based_) {
+        // worst case for the ego: UCB on the normalised ego cost (RMDP / RSBG)
+        double best = -std::numeric_limits<double>::infinity();
+        const double n_total = std::max(1.0, n_vis);
+        for (int i = 0; i < (int)tab.size(); ++i) {
+          if (tab[i].dead) continue;
+          const double n = tab[i].count + tab[i].pending;
+          double v = (n <= 0) ? std::numeric_limits<double>::max()
+                              : (hi_ > lo_ ? (tab[i].ego_cost - lo_) / (hi_ - lo_) : 0.0) +
+                                    2.0 * c_ * std::sqrt(2.0 * std::log(n_total) / n);
+          if (v > best) {
+            best = v;
+            idx = i;
+          }
+        }
+      } else {
+        // stochastic behaviour model: re-sample among the expanded actions by visit count
+        std::vector<double> w;
+        double tot = 0.0;
+        for (const Entry& e : tab) {
+          w.push_back(e.dead ? 0.0 : (double)(e.count + e.pending) + 1e-9);
+          tot += w.back();
+        }
+        if (tot > 0.0) {
+          std::discrete_distribution<int> d(w.begin(), w.end());
+          idx = d(gen);
+        }
+      }
+    }
+    if (idx < 0) {  // widening allowed, or nothing to choose from yet
       Entry e;
       e.draw_id = fresh_draw_id;
       tab.push_back(e);
       idx = (int)tab.size() - 1;
-      *is_new = true;
-    } else if (cost_based_) {
-      // worst case for the ego: UCB on the normalised ego cost (RMDP / RSBG)
-      idx = -1;
-      double best = -std::numeric_limits<double>::infinity();
-      const double n_total = std::max(1.0, n_vis);
-      for (int i = 0; i < (int)tab.size(); ++i) {
-        if (!tab[i].resolved) continue;
-        const double n = tab[i].count + tab[i].pending;
-        double v = (n <= 0) ? std::numeric_limits<double>::max()
-                            : (hi_ > lo_ ? (tab[i].ego_cost - lo_) / (hi_ - lo_) : 0.0) +
-                                  2.0 * c_ * std::sqrt(2.0 * std::log(n_total) / n);
-        if (v > best) {
-          best = v;
-          idx = i;
-        }
-      }
-      *is_new = false;
-    } else {
-      // stochastic behaviour model: re-sample among the expanded actions by visit count
-      std::vector<double> w;
-      for (const Entry& e : tab) w.push_back(e.resolved ? (double)(e.count + e.pending) + 1e-9 : 0.0);
-      std::discrete_distribution<int> d(w.begin(), w.end());
-      idx = d(gen);
-      *is_new = false;
     }
+    *is_new = !tab[idx].resolved;
     tab[idx].pending++;
     pending_[h]++;
     return idx;
@@ -269,13 +276,14 @@ class HypothesisStatistic {
   // entry that carries the same action (the reference keys the action store by value)
   int Resolve(int h, int idx, ActionKey key) {
     std::vector<Entry>& tab = per_hyp_[h];
+    if (tab[idx].resolved) return idx;  // resolved by an earlier backup of the same wave
     for (int i = 0; i < (int)tab.size(); ++i)
       if (i != idx && tab[i].resolved && tab[i].key == key) {
         tab[i].pending += tab[idx].pending;
         tab[idx].pending = 0;
-        tab[idx].resolved = false;  // dead entry: never selected again
-        tab[idx].key = ~ActionKey(0);
-        dead_++;
+        if (!tab[idx].dead) dead_++;
+        tab[idx].dead = true;  // never selected again
+        tab[idx].key = key;
         return i;
       }
     tab[idx].key = key;

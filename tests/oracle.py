@@ -161,3 +161,28 @@ def likelihood(cfg, scn, pose, alive, action, n_samples=10000, n_buckets=100, lo
                             int(n_buckets), float(lower), float(upper), int(seed), int(stream), 0)
     _check(lib.oracle_likelihood_batch(C.byref(cfg), C.byref(scn), C.byref(inb), _p(prob)))
     return prob
+
+
+# ---- CPU-backed planner (the host tree search of planner-mcts_b200/host on top of the oracle)
+
+ORACLE_PLANNER_LIB = os.path.join(ORACLE_DIR, "_build", "liboracle_planner.so")
+_planner_lib = None
+
+
+def planner_lib():
+    """liboracle_planner.so: same planner C ABI as libbmcts.so, leaf evaluation by the oracle"""
+    global _planner_lib
+    if _planner_lib is None:
+        build()
+        _planner_lib = C.CDLL(ORACLE_PLANNER_LIB)
+        _planner_lib.oracle_planner_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    return _planner_lib
+
+
+def make_planner(cls, params=None, hypotheses=None):
+    """cls = planner_mcts_b200.planner.BehaviorUCT*; returns the CPU-backed twin"""
+    lib = planner_lib()
+    kw = dict(params=params, _lib=lib, _create=lambda kind, out: lib.oracle_planner_create(kind, out))
+    if hypotheses is not None:
+        kw["hypotheses"] = hypotheses
+    return cls(**kw)

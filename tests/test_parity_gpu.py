@@ -45,6 +45,26 @@ def test_rollout_parity_with_refill(name, monkeypatch):
     assert len(set(g["result"]["n_steps"].tolist())) > 3   # rollouts end at different steps
 
 
+@pytest.mark.parametrize("name", ["c2_merge_sbg", "c4_coop"])
+def test_host_batch_pipeline_parity(name, monkeypatch):
+    """a host-memory batch cut into chunks (copy / compute pipeline): ragged last chunk,
+    depth array, per-agent returns and final poses scattered back into agent-major arrays"""
+    monkeypatch.setenv("BMCTS_PIPE_CHUNK", "64")
+    cfg, scn, meta = scenarios.workload(name, horizon=12)
+    n = 333
+    rng = np.random.default_rng(23)
+    pose, alive, hyp = scenarios.sample_leaves(scn, n, meta["lane_of"], meta["s_of"], rng,
+                                               dead_prob=0.05)
+    depth = rng.integers(1, 4, size=n).astype(np.uint16)
+    eng = RolloutEngine(cfg, scn)
+    g = eng.rollout(pose, alive, hyp, depth=depth, seed=8, stream=1, first_rollout_id=5000,
+                    want_agents=True, want_final=True)
+    c = oracle.rollout(cfg, scn, pose, alive, hyp, depth=depth, seed=8, stream=1,
+                       first_rollout_id=5000, n_threads=8)
+    parity.assert_results_match(g, c)
+    assert eng.launch_count() == 6   # ceil(333 / 64) chunks
+
+
 @pytest.mark.parametrize("name", WORKLOADS)
 def test_rollout_parity(name):
     cfg, scn, meta = scenarios.workload(name, horizon=20)
