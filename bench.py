@@ -43,39 +43,77 @@ def hbm_bytes_per_rollout(A):
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks and throttle reasons during the timed region"""
+    """samples SM clock and throttle reasons of one GPU during the timed region (NVML; falls
+    back to nvidia-smi when pynvml is missing)"""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+        return [sm, self.max_mhz] + [bool(r & b) for b in bits]
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        c = [x.strip() for x in out.split(",")]
+        return [float(c[0]), float(c[1])] + [x == "Active" for x in c[2:6]]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.rows.append(self._sample_nvml() if self.nvml else self._sample_smi())
             except Exception:
                 pass
-            self.stop_flag.wait(0.15)
+            self.stop_flag.wait(0.02 if self.nvml else 0.15)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_traffic(workload, n):
+    """dram bytes (read + write) of one launch of the dominant kernel from the committed
+    `ncu --set full` capture of this workload at this batch size (profiles/traffic.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            for row in json.load(f):
+                if row["workload"] == workload and row["rollouts"] == n:
+                    return row["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 def measured_peaks():
@@ -84,6 +122,50 @@ def measured_peaks():
             return json.load(f), "measured"
     except Exception:
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_index=0):
+    """MCTS iterations/s of one BehaviorUCT*::Plan() on the workload's scenario (second half of
+    BASELINE.json's metric).  backend 'gpu' = the product (host tree search, waves of leaves on
+    the GPU); 'cpu' = the same tree search on the CPU oracle, sequential (wave 1) like the
+    reference's mcts::Mcts::search."""
+    from planner_mcts_b200 import _abi, planner as P, scenarios
+    cfg, scn, meta = scenarios.workload(workload, horizon=horizon)
+    pose, alive, _ = scenarios.leaves_for(scn, meta, 1, seed=3)
+    A, H = meta["A"], meta["H"]
+    agents = [P.Agent(id=1 + a, x=float(pose[a, 0, 0]), y=float(pose[a, 0, 1]),
+                      theta=float(pose[a, 0, 2]), v=float(pose[a, 0, 3])) for a in range(A)]
+    world = P.ObservedWorld(ego_id=1, agents=agents, map=scn)
+    b = "BehaviorUctBase::"
+    params = {b + "Mcts::MaxNumIterations": iterations, b + "Mcts::MaxSearchTime": 1e9,
+              b + "Mcts::MaxNumNodes": max(2000, iterations), b + "Mcts::Engine::WaveSize": wave,
+              b + "MaxNearestAgents": A - 1, b + "Mcts::RandomHeuristic::MaxNumIterations": horizon,
+              b + "EgoBehavior::AccelerationInputs": [0.0, 1.0, 4.0, -1.0, -8.0]}
+    if cfg.add_safe_dist:
+        params[b + "Mcts::State::EvaluationParameters::AddSafeDist"] = 1
+        params[b + "Mcts::State::SplitSafeDistCollision"] = 1
+        params["BehaviorUctRiskConstraint::DefaultAvailableRisk"] = [0.1, 0.0]
+    hyps = [P.HypothesisIDM(scn.hypotheses[h], num_samples=1000) for h in range(H)]
+    if cfg.state_kind == _abi.STATE_COOPERATIVE:
+        cls, hyp_arg = P.BehaviorUCTCooperative, None
+    elif cfg.state_kind == _abi.STATE_RISK_CONSTRAINT:
+        cls, hyp_arg = P.BehaviorUCTRiskConstraint, hyps
+    else:
+        cls, hyp_arg = P.BehaviorUCTHypothesis, hyps
+    if backend == "cpu":
+        import oracle
+        pl = oracle.make_planner(cls, params, hyp_arg)
+    else:
+        pl = cls(params, hyp_arg, device=device) if hyp_arg is not None else cls(params, device=device)
+    pl.set_tree_index(tree_index)
+    pl.Plan(0.2, world)   # warm-up: buffers, first launches
+    t0 = time.perf_counter()
+    pl.Plan(0.2, world)
+    wall = time.perf_counter() - t0
+    return {"iterations_per_s": pl.last_num_iterations / wall, "iterations": pl.last_num_iterations,
+            "plan_ms": wall * 1e3, "search_ms": pl.last_solution_time, "wave": wave,
+            "nodes": pl.last_num_nodes, "best_action": pl.last_macro_action,
+            "root_stats": pl.root_stats().tolist()}
 
 
 def run_reference(args):
@@ -118,6 +200,8 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "plan": None if args.no_plan else {k: v for k, v in plan_benchmark(
+            args.workload, args.horizon, args.cpu_plan_iterations, 1, "cpu").items() if k != "root_stats"},
         "note": "reference cannot be compiled here (Bazel + BARK + mamcts absent); this is the "
                 "in-repo CPU oracle, which has none of BARK's heap cloning and is therefore "
                 "faster than the real reference would be",
@@ -224,6 +308,28 @@ def run_ours(args):
     last = h_res.numpy().view(RESULT_DTYPE).reshape(-1)
     assert np.array_equal(last, res), "host-memory path and device-resident path disagree"
 
+    # ---- Plan() arm: one BehaviorUCT*::Plan per rank (root-parallel: tree index = rank), root
+    # statistics merged with an NCCL all-reduce
+    plan = None
+    if not args.no_plan:
+        g = plan_benchmark(args.workload, args.horizon, args.plan_iterations, args.plan_wave, "gpu",
+                           device=local_rank, tree_index=rank)
+        from planner_mcts_b200 import root_parallel
+        ms = torch.tensor([g["plan_ms"]], dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        t_merge = time.perf_counter()
+        st = root_parallel.merge_root_stats(g.pop("root_stats"), device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        torch.cuda.synchronize()
+        merge_ms = (time.perf_counter() - t_merge) * 1e3
+        n_act = (len(st) - 2) // 4
+        cnt, ret = st[:n_act], st[n_act:2 * n_act]
+        mean = np.where(cnt > 0, ret / np.maximum(cnt, 1), -np.inf)
+        plan = dict(g, iterations=int(st[-2]), plan_ms=float(ms[0]), merge_ms=merge_ms,
+                    iterations_per_s=float(st[-2]) / (float(ms[0]) * 1e-3),
+                    merged_best_action=int(np.argmax(mean)), trees=world)
+
     # ---- reduce over ranks: time = max, work = sum
     t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     w = torch.tensor([float(total_steps), float(e2e_steps), float(launches)], dtype=torch.float64,
@@ -269,13 +375,20 @@ def run_ours(args):
                      "peak_def": "2 x 128 FP32 lanes x 148 SMs x SM clock under load (%s MHz); "
                                  "algorithmic FLOPs per agent-step = %.0f (SURVEY.md 8d)" %
                                  (sm_mhz, flop),
-                     "kernel": "bmcts::rollout_lane_coop_kernel" if coop else "bmcts::rollout_lane_kernel", "kernel_ms": k_ms, "traffic": None},
+                     "kernel": "bmcts::rollout_lane_coop_kernel" if coop else "bmcts::rollout_lane_kernel", "kernel_ms": k_ms, "traffic": measured_traffic(args.workload, n),
+                     "traffic_algorithmic": n * hbm_bytes_per_rollout(A)},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"),
                          "unit": "GB/s", "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0),
                          "peak_kind": peak_kind, "traffic": None},
     }
+    if plan is not None:
+        line["plan"] = plan
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cfg, scn, meta)
+        if plan is not None:
+            c = plan_benchmark(args.workload, args.horizon, args.cpu_plan_iterations, 1, "cpu")
+            c.pop("root_stats")
+            line["cpu_baseline"]["plan"] = c
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -312,7 +425,7 @@ def cpu_baseline(args, cfg, scn, meta):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_merge_sbg")
@@ -320,6 +433,10 @@ def main():
     ap.add_argument("--rollouts", type=int, default=1 << 20, help="leaf states per step per GPU")
     ap.add_argument("--cpu-rollouts", type=int, default=65536, help="reference arm: leaves per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-plan", action="store_true", help="skip the Plan() iterations/s arm")
+    ap.add_argument("--plan-iterations", type=int, default=32768)
+    ap.add_argument("--plan-wave", type=int, default=1024)
+    ap.add_argument("--cpu-plan-iterations", type=int, default=4000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)
