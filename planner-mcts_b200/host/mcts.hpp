@@ -9,6 +9,8 @@
 #pragma once
 
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <memory>
@@ -100,6 +102,7 @@ class Mcts {
     const auto t0 = clock::now();
     nodes_.clear();
     root_ = NewNode(nullptr, root_pose, root_alive, root_depth, false);
+    t_select_ = t_fill_ = t_engine_ = t_backup_ = 0.0;
     iterations_ = 0;
     max_tree_depth_ = 0;
     const long wave = std::max<long>(1, p_.WAVE_SIZE);
@@ -110,6 +113,9 @@ class Mcts {
       RunWave(w, sample_hypotheses);
     }
     search_time_ms_ = std::chrono::duration<double, std::milli>(clock::now() - t0).count();
+    if (std::getenv("BMCTS_DEBUG"))
+      std::fprintf(stderr, "[bmcts] search %.2f ms: select %.2f, fill %.2f, engine %.2f, backup %.2f (%ld iterations, %zu nodes)\n",
+                   search_time_ms_, t_select_, t_fill_, t_engine_, t_backup_, iterations_, nodes_.size());
   }
 
   RootStats GetRootStats() const {
@@ -255,9 +261,16 @@ class Mcts {
   }
 
   void RunWave(int w, const HypothesisSampler& sample_hypotheses) {
+    using clock = std::chrono::steady_clock;
+    auto ms = [](clock::time_point a, clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t0 = clock::now();
     std::vector<Selection> sels;
     sels.reserve(w);
     for (int i = 0; i < w; ++i) sels.push_back(Select(sample_hypotheses));
+    const auto t1 = clock::now();
+    t_select_ += ms(t0, t1);
     std::vector<int> slot(w, -1);
     int n_engine = 0;
     for (int i = 0; i < w; ++i)
@@ -285,17 +298,22 @@ class Mcts {
           }
         }
       }
+      const auto t2 = clock::now();
+      t_fill_ += ms(t1, t2);
       const uint64_t first_id = rollout_counter_;
       rollout_counter_ += (uint64_t)n_engine;
       int stc = eval_->ExpandRollout(wave_, p_.RANDOM_SEED, tree_index_, first_id);
       if (stc != BMCTS_OK)
         throw std::runtime_error("rollout engine failed: " + eval_->LastError());
+      t_engine_ += ms(t2, clock::now());
     }
+    const auto t3 = clock::now();
     for (int i = 0; i < w; ++i) {
       Backup(sels[i], slot[i]);
       iterations_++;
       if (ego_mode_ == EgoMode::kCostConstrained) UpdateLambdas();
     }
+    t_backup_ += ms(t3, clock::now());
   }
 
   void SetHeuristic(Node* n, double ret, const double* cost, const float* ret_agents, int k) {
@@ -431,6 +449,7 @@ class Mcts {
   long iterations_ = 0;
   int max_tree_depth_ = 0;
   double search_time_ms_ = 0.0;
+  double t_select_ = 0.0, t_fill_ = 0.0, t_engine_ = 0.0, t_backup_ = 0.0;
   uint64_t next_draw_id_ = 1, rollout_counter_ = 0;
 };
 
