@@ -65,6 +65,23 @@ struct RootStats {  // what root-parallel trees / ranks merge (mamcts merge_node
   }
 };
 
+// joint action of one expansion: ActionKey per agent slot, fixed capacity (no allocation on
+// look-ups); compared over the first `n` slots
+struct JointKey {
+  int n = 0;
+  ActionKey k[BMCTS_MAX_AGENTS];
+  explicit JointKey(int n_ = 0) : n(n_) {
+    for (int i = 0; i < n; ++i) k[i] = 0;
+  }
+  ActionKey& operator[](int i) { return k[i]; }
+  const ActionKey& operator[](int i) const { return k[i]; }
+  bool operator<(const JointKey& o) const {
+    for (int i = 0; i < n; ++i)
+      if (k[i] != o.k[i]) return k[i] < o.k[i];
+    return false;
+  }
+};
+
 struct Node {
   Node* parent = nullptr;
   unsigned state_depth = 1;  // MctsStateBase::depth_
@@ -72,11 +89,16 @@ struct Node {
   std::vector<float> pose;   // [A][4]
   uint32_t alive = 0;
   bool terminal = false;
+  bool stats_ready = false;  // action tables built (first time the node is selected through)
   UctStatistic ego_uct;
   CostConstrainedStatistic ego_cc;
-  std::vector<HypothesisStatistic> other_hyp;  // per agent slot (slot 0 unused)
+  std::vector<HypothesisStatistic> other_hyp;  // per agent slot (slot 0 unused); built lazily
   std::vector<UctStatistic> other_uct;
-  std::map<std::vector<ActionKey>, Node*> children;
+  // latest back-propagated value seen by the other agents' statistics of this node: the ego
+  // cost (hypothesis states: the same for every agent) / the agent's own return (cooperative)
+  double latest_cost_other = 0.0;
+  std::vector<double> latest_ret_other;
+  std::map<JointKey, Node*> children;
   std::vector<double> edge_reward;  // rewards[] of the execute() that created this node
   double edge_cost[2] = {0.0, 0.0};
 };
@@ -101,7 +123,10 @@ class Mcts {
     using clock = std::chrono::steady_clock;
     const auto t0 = clock::now();
     nodes_.clear();
+    cc_params_ = p_;
+    cc_params_.cost_constrained_statistic.COST_CONSTRAINTS = constraints_;
     root_ = NewNode(nullptr, root_pose, root_alive, root_depth, false);
+    EnsureStats(root_);
     t_select_ = t_fill_ = t_engine_ = t_backup_ = 0.0;
     iterations_ = 0;
     max_tree_depth_ = 0;
@@ -164,8 +189,8 @@ class Mcts {
   struct PathStep {
     Node* node = nullptr;
     int ego_action = 0;
-    std::vector<int> other_idx;       // HypothesisStatistic entry index / UCT action per slot
-    std::vector<uint8_t> other_new;   // entry was created by this selection
+    int other_idx[BMCTS_MAX_AGENTS];      // HypothesisStatistic entry index / UCT action per slot
+    uint8_t other_new[BMCTS_MAX_AGENTS];  // the entry's action is not known yet (plan it)
   };
   struct Selection {
     std::vector<PathStep> path;  // path.back() is the expansion step (unless no_expand)
@@ -186,14 +211,22 @@ class Mcts {
     n->alive = alive;
     n->terminal = terminal;
     n->edge_reward.assign(A_, 0.0);
+    // Most nodes are leaves that only ever receive one heuristic estimate: the statistics
+    // objects exist (they hold the latest return / cost), their action tables do not yet.
+    if (ego_mode_ == EgoMode::kCostConstrained) n->ego_cc.InitLight(n_costs_);
+    if (other_mode_ == OtherMode::kUct) n->latest_ret_other.assign(A_, 0.0);
+    return n;
+  }
+
+  void EnsureStats(Node* n) {
+    if (n->stats_ready) return;
+    n->stats_ready = true;
     if (ego_mode_ == EgoMode::kUct) {
       n->ego_uct.Init(n_actions_, p_.uct_statistic.LOWER_BOUND, p_.uct_statistic.UPPER_BOUND,
                       p_.uct_statistic.EXPLORATION_CONSTANT, p_.DISCOUNT_FACTOR,
                       p_.USE_BOUND_ESTIMATION);
     } else {
-      MctsParameters q = p_;
-      q.cost_constrained_statistic.COST_CONSTRAINTS = constraints_;
-      n->ego_cc.Init(n_actions_, n_costs_, q);
+      n->ego_cc.Init(n_actions_, n_costs_, cc_params_);
     }
     if (other_mode_ == OtherMode::kHypothesis) {
       n->other_hyp.assign(A_, HypothesisStatistic());
@@ -205,7 +238,6 @@ class Mcts {
                              p_.uct_statistic.EXPLORATION_CONSTANT, p_.DISCOUNT_FACTOR,
                              p_.USE_BOUND_ESTIMATION);
     }
-    return n;
   }
 
   // StageNode::select_or_expand down the tree for one iteration
@@ -219,13 +251,16 @@ class Mcts {
         sel.reached = node;
         return sel;
       }
+      EnsureStats(node);
       PathStep st;
       st.node = node;
-      st.other_idx.assign(A_, -1);
-      st.other_new.assign(A_, 0);
+      for (int s = 0; s < A_; ++s) {
+        st.other_idx[s] = -1;
+        st.other_new[s] = 0;
+      }
       st.ego_action = ego_mode_ == EgoMode::kUct ? node->ego_uct.ChooseNextAction(gen_)
                                                  : node->ego_cc.ChooseNextAction(lambdas_, gen_);
-      std::vector<ActionKey> joint(A_, 0);
+      JointKey joint(A_);
       joint[0] = (ActionKey)st.ego_action;
       bool all_resolved = true;
       for (int s = 1; s < A_; ++s) {
@@ -321,11 +356,11 @@ class Mcts {
       n->ego_uct.UpdateFromHeuristic(ret);
     else
       n->ego_cc.UpdateFromHeuristic(ret, cost);
-    for (int s = 1; s < A_; ++s) {
-      if (other_mode_ == OtherMode::kHypothesis)
-        n->other_hyp[s].UpdateFromHeuristic(cost[0]);
-      else
-        n->other_uct[s].UpdateFromHeuristic(ret_agents ? (double)ret_agents[wave_.at(s, k)] : 0.0);
+    if (other_mode_ == OtherMode::kHypothesis) {
+      n->latest_cost_other = cost[0];
+    } else {
+      for (int s = 1; s < A_; ++s)
+        n->latest_ret_other[s] = ret_agents ? (double)ret_agents[wave_.at(s, k)] : 0.0;
     }
   }
 
@@ -336,7 +371,7 @@ class Mcts {
       PathStep& st = sel.path.back();
       Node* parent = st.node;
       // resolve the others' newly planned actions and build the joint action key
-      std::vector<ActionKey> joint(A_, 0);
+      JointKey joint(A_);
       joint[0] = (ActionKey)st.ego_action;
       for (int s = 1; s < A_; ++s) {
         if (st.other_idx[s] < 0) {
@@ -396,13 +431,16 @@ class Mcts {
           const int h = sel.hyp[s];
           n->other_hyp[s].ReleasePending(h, st.other_idx[s]);
           n->other_hyp[s].UpdateStatistic(h, st.other_idx[s], child->edge_cost[0],
-                                          child->other_hyp[s].latest_ego_cost());
+                                          child->latest_cost_other);
         } else {
           n->other_uct[s].ReleasePending(st.other_idx[s]);
           n->other_uct[s].UpdateStatistic(st.other_idx[s], child->edge_reward[s],
-                                          child->other_uct[s].latest_return());
+                                          child->latest_ret_other[s]);
+          n->latest_ret_other[s] = n->other_uct[s].latest_return();
         }
       }
+      if (other_mode_ == OtherMode::kHypothesis)
+        n->latest_cost_other = child->edge_cost[0] + p_.DISCOUNT_FACTOR * child->latest_cost_other;
       child = n;
     }
   }
@@ -412,12 +450,8 @@ class Mcts {
       n->ego_uct.UpdateFromHeuristic(0.0);
     else
       n->ego_cc.UpdateFromHeuristic(0.0, zero);
-    for (int s = 1; s < A_; ++s) {
-      if (other_mode_ == OtherMode::kHypothesis)
-        n->other_hyp[s].UpdateFromHeuristic(0.0);
-      else
-        n->other_uct[s].UpdateFromHeuristic(0.0);
-    }
+    n->latest_cost_other = 0.0;
+    for (double& v : n->latest_ret_other) v = 0.0;
   }
 
   // CostConstrainedStatistic::update_statistic_parameters: sub-gradient step on lambda
@@ -435,7 +469,7 @@ class Mcts {
     }
   }
 
-  MctsParameters p_;
+  MctsParameters p_, cc_params_;
   EgoMode ego_mode_;
   OtherMode other_mode_;
   int A_, n_actions_, H_, n_costs_;

@@ -83,6 +83,7 @@ class UctStatistic {
     double lo = lower_, hi = upper_;
     EstimatedBounds(&lo, &hi);
     const double n_total = std::max(1.0, (double)(total_visits_ + total_pending_));
+    const double two_log_n = 2.0 * std::log(n_total);
     int best = 0;
     double best_v = -std::numeric_limits<double>::infinity();
     for (int a = 0; a < (int)pairs_.size(); ++a) {
@@ -94,7 +95,7 @@ class UctStatistic {
         v = std::numeric_limits<double>::max();
       } else {
         const double q = (hi > lo) ? (p.value - lo) / (hi - lo) : 0.0;
-        v = q + 2.0 * c_ * std::sqrt(2.0 * std::log(n_total) / n);
+        v = q + 2.0 * c_ * std::sqrt(two_log_n / n);
       }
       if (v > best_v) {
         best_v = v;
@@ -228,19 +229,27 @@ class HypothesisStatistic {
     // progressive widening: |actions| <= K * N^alpha.  Inside a wave an entry may be chosen
     // again before its action is known (unresolved): it is re-planned with the same draw id,
     // which yields the same action and therefore the same child.
-    bool widen = n_act <= k_ * std::pow(n_vis, alpha_);
+    // n_act <= K * N^alpha  <=>  N >= (n_act / K)^(1 / alpha); the right-hand side only
+    // changes when an action is added, so it is cached (pow is the most expensive call of a
+    // selection step)
+    if (n_act != widen_cache_n_) {
+      widen_cache_n_ = n_act;
+      widen_cache_v_ = (k_ > 0.0 && alpha_ > 0.0) ? std::pow(n_act / k_, 1.0 / alpha_)
+                                                   : std::numeric_limits<double>::infinity();
+    }
+    bool widen = n_vis >= widen_cache_v_;
     int idx = -1;
     if (!widen) {
       if (cost_based_) {
         // worst case for the ego: UCB on the normalised ego cost (RMDP / RSBG)
         double best = -std::numeric_limits<double>::infinity();
-        const double n_total = std::max(1.0, n_vis);
+        const double two_log_n = 2.0 * std::log(std::max(1.0, n_vis));
         for (int i = 0; i < (int)tab.size(); ++i) {
           if (tab[i].dead) continue;
           const double n = tab[i].count + tab[i].pending;
           double v = (n <= 0) ? std::numeric_limits<double>::max()
                               : (hi_ > lo_ ? (tab[i].ego_cost - lo_) / (hi_ - lo_) : 0.0) +
-                                    2.0 * c_ * std::sqrt(2.0 * std::log(n_total) / n);
+                                    2.0 * c_ * std::sqrt(two_log_n / n);
           if (v > best) {
             best = v;
             idx = i;
@@ -248,15 +257,16 @@ class HypothesisStatistic {
         }
       } else {
         // stochastic behaviour model: re-sample among the expanded actions by visit count
-        std::vector<double> w;
         double tot = 0.0;
-        for (const Entry& e : tab) {
-          w.push_back(e.dead ? 0.0 : (double)(e.count + e.pending) + 1e-9);
-          tot += w.back();
-        }
+        for (const Entry& e : tab) tot += e.dead ? 0.0 : (double)(e.count + e.pending) + 1e-9;
         if (tot > 0.0) {
-          std::discrete_distribution<int> d(w.begin(), w.end());
-          idx = d(gen);
+          double u = std::generate_canonical<double, 53>(gen) * tot;
+          for (int i = 0; i < (int)tab.size(); ++i) {
+            if (tab[i].dead) continue;
+            idx = i;
+            u -= (double)(tab[i].count + tab[i].pending) + 1e-9;
+            if (u < 0.0) break;
+          }
         }
       }
     }
@@ -324,6 +334,7 @@ class HypothesisStatistic {
   double k_ = 4, alpha_ = 0.25, lo_ = 0, hi_ = 1, c_ = 0.7, gamma_ = 0.9;
   bool hyp_based_ = true, cost_based_ = false;
   double latest_ego_cost_ = 0.0;
+  double widen_cache_n_ = -1.0, widen_cache_v_ = 0.0;
   unsigned dead_ = 0;
 };
 
@@ -336,7 +347,7 @@ class CostConstrainedStatistic {
     const auto& c = m.cost_constrained_statistic;
     reward_.Init(num_actions, c.REWARD_LOWER_BOUND, c.REWARD_UPPER_BOUND, 0.0, m.DISCOUNT_FACTOR,
                  false);
-    costs_.assign(num_costs, UctStatistic());
+    InitLight(num_costs);  // keeps heuristic values set before the tables were needed
     for (auto& s : costs_)
       s.Init(num_actions, c.COST_LOWER_BOUND, c.COST_UPPER_BOUND, 0.0, m.DISCOUNT_FACTOR, false);
     kappa_ = c.KAPPA;
@@ -349,6 +360,12 @@ class CostConstrainedStatistic {
     unexpanded_.resize(num_actions);
     for (int i = 0; i < num_actions; ++i) unexpanded_[i] = i;
     pending_.assign(num_actions, 0);
+  }
+
+  // what a freshly expanded node needs to receive its heuristic estimate; the action tables
+  // (Init) are built when the node is first selected through
+  void InitLight(int num_costs) {
+    if ((int)costs_.size() != num_costs) costs_.assign(num_costs, UctStatistic());
   }
 
   int num_actions() const { return reward_.num_actions(); }
@@ -572,8 +589,19 @@ class HypothesisBeliefTracker {
       std::uniform_int_distribution<unsigned> d(0, std::max(1u, num_hypotheses) - 1);
       return d(gen_);
     }
-    std::discrete_distribution<unsigned> d(it->second.begin(), it->second.end());
-    return d(gen_);
+    // one hypothesis drawn from the agent's belief (allocation free)
+    const std::vector<double>& b = it->second;
+    double tot = 0.0;
+    for (double v : b) tot += v;
+    double u = std::generate_canonical<double, 53>(gen_) * tot;
+    unsigned h = 0;
+    for (unsigned i = 0; i < b.size(); ++i) {
+      if (b[i] <= 0.0) continue;
+      h = i;
+      u -= b[i];
+      if (u < 0.0) break;
+    }
+    return h;
   }
 
  private:
