@@ -57,6 +57,9 @@ struct bmcts_engine {
   static const int kPipeSlots = 3;
   PipeSlot pipe[kPipeSlots];
   cudaEvent_t ev_pipe = nullptr;
+  unsigned int* d_ready = nullptr;   // [0] chunks uploaded, [1] wait timed out
+  unsigned int* h_ready = nullptr;   // pinned: h_ready[c] = c + 1
+  int h_ready_cap = 0;
   // staging buffers for host-pointer calls
   DevBuf b_pose, b_alive, b_hyp, b_depth, b_action, b_draw;
   DevBuf b_next_pose, b_next_alive, b_reward, b_cost, b_flags, b_last_action;
@@ -267,6 +270,109 @@ int pipeline_chunk(int n) {
   return (int)c;
 }
 
+// chunk size of the streamed upload (0 = off)
+int stream_chunk(int n) {
+  long chunk = 65536;
+  if (const char* s = std::getenv("BMCTS_STREAM_CHUNK")) chunk = std::atol(s);
+  if (chunk <= 0 || n < 4 * chunk) return 0;
+  return (int)((chunk + 31) & ~31L);
+}
+
+// Large host-memory rollout batch, streamed: ONE persistent kernel over the whole batch is
+// launched as soon as the first chunk of the leaf arrays is on its way; the remaining chunks
+// are uploaded by the copy engine while the kernel runs, each followed by a 4-byte counter
+// update, and a lane group only starts rollout k once the chunk holding k has arrived
+// (wait_chunk in rollout_device.cuh).  Row-wise 1-D copies keep the upload on the DMA engines:
+// nothing the spinning kernel could starve.  Results are downloaded after the kernel.
+int rollout_host_streamed(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts_rollout_out* out,
+                          const bmcts::KernelArgs& base) {
+  const int n = in->n_leaves, A = e->scn.n_agents;
+  const int chunk = stream_chunk(n);
+  const int n_chunks = (n + chunk - 1) / chunk;
+  int st;
+  if ((st = ensure(e, e->b_pose, sizeof(float) * 4 * (size_t)n * A))) return st;
+  if ((st = ensure(e, e->b_alive, sizeof(uint32_t) * (size_t)n))) return st;
+  if ((st = ensure(e, e->b_result, sizeof(bmcts_rollout_result) * (size_t)n))) return st;
+  if (in->hyp_id && (st = ensure(e, e->b_hyp, (size_t)n * A))) return st;
+  if (in->depth && (st = ensure(e, e->b_depth, sizeof(uint16_t) * (size_t)n))) return st;
+  if (out->ret_agents && (st = ensure(e, e->b_ret_agents, sizeof(float) * (size_t)n * A))) return st;
+  if (out->final_pose && (st = ensure(e, e->b_final_pose, sizeof(float) * 4 * (size_t)n * A)))
+    return st;
+  if (n_chunks > e->h_ready_cap) {
+    if (e->h_ready) CU(cudaFreeHost(e->h_ready));
+    e->h_ready = nullptr;
+    CU(cudaHostAlloc((void**)&e->h_ready, sizeof(unsigned int) * (size_t)(n_chunks + 64),
+                     cudaHostAllocDefault));
+    e->h_ready_cap = n_chunks + 64;
+    for (int c = 0; c < e->h_ready_cap; ++c) e->h_ready[c] = (unsigned int)(c + 1);
+  }
+  cudaStream_t ks = e->stream, cs = e->pipe[0].stream;
+  CU(cudaMemsetAsync(e->d_ready, 0, 2 * sizeof(unsigned int), ks));
+  CU(cudaEventRecord(e->ev_pipe, ks));
+  CU(cudaStreamWaitEvent(cs, e->ev_pipe, 0));  // uploads start after the counter reset
+  bmcts::KernelArgs a = base;
+  a.pose = (const float4*)e->b_pose.ptr;
+  a.alive = (const uint32_t*)e->b_alive.ptr;
+  a.hyp = in->hyp_id ? (const uint8_t*)e->b_hyp.ptr : nullptr;
+  a.depth = in->depth ? (const uint16_t*)e->b_depth.ptr : nullptr;
+  a.result = (bmcts_rollout_result*)e->b_result.ptr;
+  // result records go straight into the caller's buffer when it is pinned host memory the
+  // device can address (32-byte posted writes over PCIe while the kernel runs): no download
+  bool zero_copy_result = false;
+  if (!std::getenv("BMCTS_NO_ZERO_COPY")) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, out->result) == cudaSuccess &&
+        at.type == cudaMemoryTypeHost && at.devicePointer != nullptr) {
+      a.result = (bmcts_rollout_result*)at.devicePointer;
+      zero_copy_result = true;
+    } else {
+      (void)cudaGetLastError();  // an unregistered (pageable) pointer is not an error here
+    }
+  }
+  a.ret_agents = out->ret_agents ? (float*)e->b_ret_agents.ptr : nullptr;
+  a.final_pose = out->final_pose ? (float4*)e->b_final_pose.ptr : nullptr;
+  a.ready = e->d_ready;
+  a.chunk = (unsigned int)chunk;
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t k0 = (size_t)c * chunk;
+    const size_t m = (n - k0 < (size_t)chunk) ? n - k0 : (size_t)chunk;
+    for (int ag = 0; ag < A; ++ag) {
+      const size_t row = (size_t)ag * n + k0;
+      CU(cudaMemcpyAsync((char*)e->b_pose.ptr + row * 16, in->pose + row * 4, m * 16,
+                         cudaMemcpyHostToDevice, cs));
+      if (in->hyp_id)
+        CU(cudaMemcpyAsync((char*)e->b_hyp.ptr + row, in->hyp_id + row, m, cudaMemcpyHostToDevice, cs));
+    }
+    CU(cudaMemcpyAsync((char*)e->b_alive.ptr + k0 * 4, in->alive + k0, m * 4, cudaMemcpyHostToDevice,
+                       cs));
+    if (in->depth)
+      CU(cudaMemcpyAsync((char*)e->b_depth.ptr + k0 * 2, in->depth + k0, m * 2,
+                         cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(e->d_ready, e->h_ready + c, sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
+    if (c == 0) {  // the kernel starts while the first chunk is in flight
+      CU(cudaEventRecord(e->ev_start, ks));
+      if ((st = launch_on(e, a, ks, e->d_counter))) return st;
+      CU(cudaEventRecord(e->ev_stop, ks));
+      e->timed = true;
+    }
+  }
+  unsigned int flags[2] = {0, 0};
+  if (!zero_copy_result)
+    CU(cudaMemcpyAsync(out->result, a.result, sizeof(bmcts_rollout_result) * (size_t)n,
+                       cudaMemcpyDeviceToHost, ks));
+  if (out->ret_agents)
+    CU(cudaMemcpyAsync(out->ret_agents, a.ret_agents, sizeof(float) * (size_t)n * A,
+                       cudaMemcpyDeviceToHost, ks));
+  if (out->final_pose)
+    CU(cudaMemcpyAsync(out->final_pose, a.final_pose, sizeof(float) * 4 * (size_t)n * A,
+                       cudaMemcpyDeviceToHost, ks));
+  CU(cudaMemcpyAsync(flags, e->d_ready, sizeof(flags), cudaMemcpyDeviceToHost, ks));
+  CU(cudaStreamSynchronize(ks));
+  CU(cudaStreamSynchronize(cs));
+  if (flags[1]) return fail(e, BMCTS_ERR_CUDA, "streamed upload stalled: a chunk never arrived");
+  return BMCTS_OK;
+}
+
 // Large host-memory rollout batch: the batch is cut into chunks of rollouts; every chunk is
 // uploaded (strided 2-D copies out of the agent-major host arrays), rolled out and downloaded
 // on its own stream, three chunks in flight, so the PCIe copies of one chunk overlap the kernel
@@ -375,6 +481,7 @@ int bmcts_create(int device, const bmcts_config* cfg, bmcts_engine** out) {
   if ((ce = cudaMalloc(&e->d_counter, sizeof(unsigned int))) != cudaSuccess) return bail(ce);
   if ((ce = cudaEventCreateWithFlags(&e->ev_pipe, cudaEventDisableTiming)) != cudaSuccess)
     return bail(ce);
+  if ((ce = cudaMalloc(&e->d_ready, 2 * sizeof(unsigned int))) != cudaSuccess) return bail(ce);
   for (auto& sl : e->pipe) {
     if ((ce = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) != cudaSuccess)
       return bail(ce);
@@ -413,6 +520,8 @@ void bmcts_destroy(bmcts_engine* e) {
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
   if (e->ev_pipe) cudaEventDestroy(e->ev_pipe);
+  if (e->d_ready) cudaFree(e->d_ready);
+  if (e->h_ready) cudaFreeHost(e->h_ready);
   if (e->ev_start) cudaEventDestroy(e->ev_start);
   if (e->ev_stop) cudaEventDestroy(e->ev_stop);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -471,6 +580,7 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
     a.final_pose = (float4*)out->final_pose;
     return launch(e, a);
   }
+  if (stream_chunk(n) > 0) return rollout_host_streamed(e, in, out, a);
   if (pipeline_chunk(n) > 0) return rollout_host_pipelined(e, in, out, a);
   const void* d;
   void* o;

@@ -55,6 +55,11 @@ struct KernelArgs {
   int do_rollout;
   uint32_t key0, key1;
   uint64_t first_rollout_id;
+  // streamed host batch (engine.cu rollout_host_streamed): rollout k may start once
+  // ready[0] > k / chunk, i.e. its chunk of the leaf arrays has been uploaded; ready[1] is
+  // set when a wait times out.  Null for every other call.
+  unsigned int* ready;
+  unsigned int chunk;
 };
 
 __host__ __device__ inline size_t smem_align16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -75,6 +80,22 @@ __device__ __forceinline__ uint4 draw(uint32_t k0, uint32_t k1, uint64_t id, uin
                                       uint32_t domain, uint32_t index) {
   return philox4x32_10(
       make_uint4((uint32_t)id, (uint32_t)(id >> 32), agent | (domain << 16), index), k0, k1);
+}
+
+// wait until the chunk that holds rollout `rid` has arrived (acquire load at system scope:
+// the data is written by the copy engine, then the counter).  Gives up after a few seconds
+// instead of hanging the GPU if the upload stalled.
+__device__ __forceinline__ bool wait_chunk(const KernelArgs& p, uint32_t rid) {
+  if (!p.ready) return true;
+  const unsigned int need = rid / p.chunk + 1u;
+  for (unsigned int spins = 0; spins < 30000000u; ++spins) {
+    unsigned int have;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(p.ready) : "memory");
+    if (have >= need) return true;
+    __nanosleep(100);
+  }
+  atomicExch(p.ready + 1, 1u);
+  return false;
 }
 
 struct Proj {

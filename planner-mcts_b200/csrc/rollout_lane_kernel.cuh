@@ -230,7 +230,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         if (t == 0) next = n_groups + atomicAdd(counter, 1u);
         if (T > 1) next = __shfl_sync(gmask, next, lane & ~(T - 1));
       }
-      if (next >= (uint32_t)p.n) {
+      if (next >= (uint32_t)p.n || !wait_chunk(p, next)) {
         done = true;
       } else {
         rid = next;

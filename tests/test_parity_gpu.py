@@ -63,6 +63,13 @@ def test_host_batch_pipeline_parity(name, monkeypatch):
                        first_rollout_id=5000, n_threads=8)
     parity.assert_results_match(g, c)
     assert eng.launch_count() == 6   # ceil(333 / 64) chunks
+    # the streamed variant: ONE kernel that starts while the first chunk is in flight and
+    # picks rollouts up as their chunks arrive
+    monkeypatch.setenv("BMCTS_STREAM_CHUNK", "32")
+    g = eng.rollout(pose, alive, hyp, depth=depth, seed=8, stream=1, first_rollout_id=5000,
+                    want_agents=True, want_final=True)
+    parity.assert_results_match(g, c)
+    assert eng.launch_count() == 7
 
 
 @pytest.mark.parametrize("name", WORKLOADS)

@@ -39,7 +39,12 @@ print("D2H result %.1f MB: %.2f ms" % (h_res.numel() * 4 / 1e6, timed(lambda: h_
 d_alive = torch.from_numpy(alive.view(np.int32)).to(dev)
 d_hyp = torch.from_numpy(hyp).to(dev)
 print("kernel device-resident: %.2f ms" % timed(lambda: (eng.rollout_raw(n, _abi.MEM_DEVICE, d_pose, d_alive, d_hyp, None, d_res), eng.sync())))
-for chunk in (0, 524288, 262144, 131072, 65536):
+for chunk in (16384, 32768, 65536, 131072):
+    os.environ["BMCTS_STREAM_CHUNK"] = str(chunk)
+    ms = timed(lambda: eng.rollout_raw(n, _abi.MEM_HOST, h_pose, h_alive, h_hyp, None, h_res))
+    print("host call, streamed chunk %7d: %.2f ms" % (chunk, ms))
+os.environ["BMCTS_STREAM_CHUNK"] = "0"
+for chunk in (0, 262144):
     os.environ["BMCTS_PIPE_CHUNK"] = str(chunk)
     ms = timed(lambda: eng.rollout_raw(n, _abi.MEM_HOST, h_pose, h_alive, h_hyp, None, h_res))
     print("host call, chunk %7d: %.2f ms" % (chunk, ms))
