@@ -52,11 +52,15 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
     const uint32_t* s2 = reinterpret_cast<const uint32_t*>(p.cfg);
     uint32_t* d2 = reinterpret_cast<uint32_t*>(smem_raw + lay.off_cfg);
     for (int i = threadIdx.x; i < (int)(sizeof(bmcts_config) / 4); i += blockDim.x) d2[i] = s2[i];
+    stage_reach(p.scn, p.cfg, A, reinterpret_cast<float*>(smem_raw + lay.off_rad), threadIdx.x,
+                blockDim.x);
   }
   __syncthreads();  // the only block barrier: staging done
   const bmcts_scenario& scn = *reinterpret_cast<const bmcts_scenario*>(smem_raw);
   const bmcts_ego_action* acts = reinterpret_cast<const bmcts_ego_action*>(smem_raw + lay.off_acts);
   const bmcts_config& cfg = *reinterpret_cast<const bmcts_config*>(smem_raw + lay.off_cfg);
+  const float* reach = reinterpret_cast<const float*>(smem_raw + lay.off_rad);
+  const float* goal_bb = reach + 2 * BMCTS_MAX_AGENTS;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = lane % T;
@@ -253,11 +257,15 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
 #pragma unroll 1
         for (int q = 0; q < n_items; ++q) {
           const bool road = q < 4;
+          if (!road && (f & kGoalFailBit)) continue;  // one corner outside: goal not reached
           float cx, cy;
           box_corner(road ? bd : be, q & 3, cx, cy);
-          const bool in = point_in_polygon(road ? scn.road_x : scn.goal.px,
-                                           road ? scn.road_y : scn.goal.py,
-                                           road ? n_road : scn.goal.n_pts, cx, cy);
+          bool in;
+          if (!road && (cx < goal_bb[0] || cx > goal_bb[1] || cy < goal_bb[2] || cy > goal_bb[3]))
+            in = false;  // outside the goal's bounding box (1 cm margin)
+          else
+            in = point_in_polygon(road ? scn.road_x : scn.goal.px, road ? scn.road_y : scn.goal.py,
+                                  road ? n_road : scn.goal.n_pts, cx, cy);
           if (!in) f |= road ? (uint32_t)BMCTS_F_COLLISION_DRIVABLE : kGoalFailBit;
         }
         if (goal_poly && !(f & kGoalFailBit)) f |= BMCTS_F_GOAL_REACHED;
@@ -303,8 +311,20 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
           const Box be = agent_box(scn, a, x, y, cs, sn, 0.0f, 0.0f);
           const Box bs = agent_box(scn, a, x, y, cs, sn, cfg.static_lat_safe_dist,
                                    cfg.static_lon_safe_dist);
+          // only agents within reach of this agent's (inflated) rectangle need the
+          // separating-axis tests (stage_reach): first collect them, then test them
+          uint32_t near = 0;
+          const float ra = reach[BMCTS_MAX_AGENTS + a];
 #pragma unroll 1
           for (uint32_t m = am & ~(1u << a); m; m &= m - 1u) {
+            const int j = __ffs(m) - 1;
+            const float thr = ra + reach[j];
+            if (bm_abs(col[K_X * fstride + j * NC] - x) <= thr &&
+                bm_abs(col[K_Y * fstride + j * NC] - y) <= thr)
+              near |= 1u << j;
+          }
+#pragma unroll 1
+          for (uint32_t m = near; m; m &= m - 1u) {
             const int j = __ffs(m) - 1;
             const float* cj = col + j * NC;
             const Box bj = agent_box(scn, j, cj[K_X * fstride], cj[K_Y * fstride],

@@ -43,7 +43,7 @@ static_assert(kScnPrefixBytes % 8 == 0, "scenario prefix is staged with 8-byte c
 static_assert(sizeof(bmcts_hypothesis) % 16 == 0, "hypotheses are staged with 16-byte copies");
 
 struct LaneLayout {
-  size_t off_acts, off_cfg, off_segcs, off_segsn, off_hflags, off_state, warp_bytes, total;
+  size_t off_acts, off_cfg, off_segcs, off_segsn, off_hflags, off_rad, off_state, warp_bytes, total;
 };
 
 __host__ __device__ inline LaneLayout lane_layout(int A, int C, int H, int T, int warps) {
@@ -59,6 +59,8 @@ __host__ __device__ inline LaneLayout lane_layout(int A, int C, int H, int T, in
   b += sizeof(float) * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS;
   l.off_hflags = b;
   b += smem_align16(sizeof(uint32_t) * 4 * (size_t)(H > 0 ? H : 1));  // flags, 1/v0, 1/(2 sqrt(ab))
+  l.off_rad = b;  // per agent: plain / static-inflated bounding radius; then the goal's AABB
+  b += smem_align16(sizeof(float) * (2 * BMCTS_MAX_AGENTS + 4));
   l.off_state = b;
   l.warp_bytes = sizeof(float) * (size_t)(L_PROJ + C) * A * (32 / T);
   l.total = b + l.warp_bytes * warps;
@@ -80,6 +82,38 @@ __device__ __forceinline__ float group_lead(float x, int lane) {
 template <int T>
 __device__ __forceinline__ void group_sync() {
   if (T > 1) __syncwarp();
+}
+
+// Conservative reach of an agent's rectangle around its reference point.  Two rectangles whose
+// reference points are farther apart than the sum of their reaches (+1 cm) in x or in y are
+// separated on one of the first rectangle's own axes with a margin far above FP32 rounding, so
+// the separating-axis test is skipped for such pairs without changing any result:
+// |t| > sqrt(2) (hlA + hwA + hlB + hwB) puts max(|t.a1|, |t.a2|) above every SAT threshold.
+__device__ __forceinline__ void stage_reach(const bmcts_scenario* scn, const bmcts_config* cfg,
+                                            int A, float* rad, int tid, int nthreads) {
+  for (int a = tid; a < A; a += nthreads) {
+    const float hl = 0.5f * scn->agent_length[a], hw = 0.5f * scn->agent_width[a];
+    const float off = bm_abs(0.5f * (scn->agent_length[a] - 2.0f * scn->agent_rear[a]));
+    const float plain = 1.42f * (hl + hw) + off + 0.005f;
+    rad[a] = plain;
+    rad[BMCTS_MAX_AGENTS + a] =
+        plain + (cfg->add_safe_dist ? 1.42f * (cfg->static_lat_safe_dist + cfg->static_lon_safe_dist)
+                                    : 0.0f);
+  }
+  if (tid == 0) {  // goal polygon AABB, grown by 1 cm: a point outside it is outside the goal
+    float x0 = kBig, x1 = -kBig, y0 = kBig, y1 = -kBig;
+    for (int i = 0; i < scn->goal.n_pts && i < BMCTS_MAX_GOAL_PTS; ++i) {
+      x0 = bm_min(x0, scn->goal.px[i]);
+      x1 = bm_max(x1, scn->goal.px[i]);
+      y0 = bm_min(y0, scn->goal.py[i]);
+      y1 = bm_max(y1, scn->goal.py[i]);
+    }
+    float* bb = rad + 2 * BMCTS_MAX_AGENTS;
+    bb[0] = x0 - 0.01f;
+    bb[1] = x1 + 0.01f;
+    bb[2] = y0 - 0.01f;
+    bb[3] = y1 + 0.01f;
+  }
 }
 
 // IDM sub-step loop (BaseIDM::Plan, spec item 4): returns the travelled distance
@@ -152,6 +186,8 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
       cs[i] = c_;
       sn[i] = s_;
     }
+    stage_reach(p.scn, p.cfg, A, reinterpret_cast<float*>(smem_raw + lay.off_rad), threadIdx.x,
+                blockDim.x);
     uint32_t* hf = reinterpret_cast<uint32_t*>(smem_raw + lay.off_hflags);
     for (int i = threadIdx.x; i < p.H; i += blockDim.x) {
       const bmcts_hypothesis& h = p.scn->hypotheses[i];
@@ -184,6 +220,8 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
   const float* segcs = reinterpret_cast<const float*>(smem_raw + lay.off_segcs);
   const float* segsn = reinterpret_cast<const float*>(smem_raw + lay.off_segsn);
   const uint32_t* hflags = reinterpret_cast<const uint32_t*>(smem_raw + lay.off_hflags);
+  const float* reach = reinterpret_cast<const float*>(smem_raw + lay.off_rad);
+  const float* goal_bb = reach + 2 * BMCTS_MAX_AGENTS;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = lane % T;  // lane inside the group
@@ -272,7 +310,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         if (!((pre >> i) & 1u)) continue;
         float* ca = col + i * NC;  // this agent's column entries
         const int word = __float_as_int(ca[L_CUR * fstride]);
-        const int cur = word & 0xff;
+        const int cur = word & 0xf;
         const int hyp = word >> 8;
         const bmcts_hypothesis& h = scn.hypotheses[hyp];
         const uint32_t hf = hflags[4 * hyp];
@@ -337,7 +375,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
       }
       const bmcts_ego_action act = acts[action];
       const float acc = bm_clamp(act.acceleration, cfg.lon_acc_min, cfg.lon_acc_max);
-      int tgt = STI(L_CUR, 0) & 0xff;
+      int tgt = STI(L_CUR, 0) & 0xf;
       if (act.type == BMCTS_ACT_CHANGE_LEFT && scn.corridors[tgt].left >= 0)
         tgt = scn.corridors[tgt].left;
       else if (act.type == BMCTS_ACT_CHANGE_RIGHT && scn.corridors[tgt].right >= 0)
@@ -393,14 +431,14 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
     const Box be = agent_box(scn, 0, ex, ey, ecs, esn, 0.0f, 0.0f);
     const Box bs = agent_box(scn, 0, ex, ey, ecs, esn, cfg.static_lat_safe_dist,
                              cfg.static_lon_safe_dist);
-    uint32_t fl = 0, dead = 0, pubs = 0, in0 = 0, in1 = 0, in2 = 0, in3 = 0;
+    uint32_t fl = 0, dead = 0, pubs = 0, near = 0, in0 = 0, in1 = 0, in2 = 0, in3 = 0;
     if (active) {
 #pragma unroll 1
       for (int a = t; a < A; a += T) {
         const size_t gi = (size_t)a * p.n + rid;
         float* ca = col + a * NC;
         const bool was_alive = (pre >> a) & 1u;
-        float x, y, th, v, cth = 0.0f, sth = 0.0f;
+        float x, y, th, v;
         int word = 0;
         if (fresh) {
           const float4 q = p.pose[gi];
@@ -424,7 +462,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
           v = ev;
         } else {
           word = __float_as_int(ca[L_CUR * fstride]);
-          const int cur = word & 0xff;
+          const int cur = word & 0xf;
           const bmcts_corridor& corr = scn.corridors[cur];
           const float s_new = ca[L_NS * fstride];
           const int nseg = corr.n_pts - 1;
@@ -436,9 +474,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
           y = bm_fma(ls, corr.ty[sg], corr.py[sg]);
           th = corr.angle[sg];
           v = ca[L_NV * fstride];
-          cth = segcs[cur * BMCTS_MAX_CORRIDOR_PTS + sg];
-          sth = segsn[cur * BMCTS_MAX_CORRIDOR_PTS + sg];
-          word &= ~0xff;
+          word = (word & ~0xff) | (cur << 4);  // bits 4-7: the corridor the pose was built on
         }
         if (!was_alive) continue;
         if (!fresh) {
@@ -481,12 +517,33 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         ca[L_CUR * fstride] = __int_as_float(word | bc);
         ca[L_V * fstride] = v;
         if (!fresh && a > 0) {
-          // EvaluatorCollisionEgoAgent / EvaluatorStaticSafeDist pair (ego, a); masked below
-          // when the ego itself left the map
-          const Box bj = agent_box(scn, a, x, y, cth, sth, 0.0f, 0.0f);
-          if (boxes_overlap(be, bj)) fl |= BMCTS_F_COLLISION_OTHER;
-          if (add_sd && boxes_overlap(bs, bj)) fl |= BMCTS_F_STATIC_SAFE_DIST;
+          // pair (ego, a): only agents within reach of the ego's (inflated) rectangle need
+          // the separating-axis tests; they are done in a second, compacted loop
+          const float thr = reach[BMCTS_MAX_AGENTS] + reach[a];
+          if (bm_abs(x - ex) <= thr && bm_abs(y - ey) <= thr) near |= bit;
         }
+      }
+      // EvaluatorCollisionEgoAgent / EvaluatorStaticSafeDist for the agents in reach; the pose
+      // is rebuilt from the planned s on the corridor it was built on.  Masked below when the
+      // ego itself left the map.
+#pragma unroll 1
+      for (uint32_t m = near; m; m &= m - 1u) {
+        const int a = __ffs(m) - 1;
+        const float* ca = col + a * NC;
+        const int oc = (__float_as_int(ca[L_CUR * fstride]) >> 4) & 0xf;
+        const bmcts_corridor& corr = scn.corridors[oc];
+        const float s_new = ca[L_NS * fstride];
+        const int nseg = corr.n_pts - 1;
+        int sg = 0;
+#pragma unroll 1
+        for (int q = 1; q < nseg; ++q) sg = (corr.s0[q] <= s_new) ? q : sg;
+        const float ls = s_new - corr.s0[sg];
+        const float x = bm_fma(ls, corr.tx[sg], corr.px[sg]);
+        const float y = bm_fma(ls, corr.ty[sg], corr.py[sg]);
+        const Box bj = agent_box(scn, a, x, y, segcs[oc * BMCTS_MAX_CORRIDOR_PTS + sg],
+                                 segsn[oc * BMCTS_MAX_CORRIDOR_PTS + sg], 0.0f, 0.0f);
+        if (boxes_overlap(be, bj)) fl |= BMCTS_F_COLLISION_OTHER;
+        if (add_sd && boxes_overlap(bs, bj)) fl |= BMCTS_F_STATIC_SAFE_DIST;
       }
     }
     if (T > 1) {
@@ -522,11 +579,15 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
 #pragma unroll 1
       for (int q = t; q < n_items; q += T) {
         const bool road = q < 4;
+        if (!road && (f & kGoalFailBit)) continue;  // one corner outside: goal not reached
         float cx, cy;
         box_corner(road ? bd : be, q & 3, cx, cy);
-        const bool in = point_in_polygon(road ? scn.road_x : scn.goal.px,
-                                         road ? scn.road_y : scn.goal.py,
-                                         road ? n_road : scn.goal.n_pts, cx, cy);
+        bool in;
+        if (!road && (cx < goal_bb[0] || cx > goal_bb[1] || cy < goal_bb[2] || cy > goal_bb[3]))
+          in = false;  // outside the goal's bounding box (1 cm margin)
+        else
+          in = point_in_polygon(road ? scn.road_x : scn.goal.px, road ? scn.road_y : scn.goal.py,
+                                road ? n_road : scn.goal.n_pts, cx, cy);
         if (!in) f |= road ? (uint32_t)BMCTS_F_COLLISION_DRIVABLE : kGoalFailBit;
       }
     }
@@ -545,7 +606,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         }
         if (add_sd) {
           // EvaluatorDynamicSafeDist: nearest agents ahead of / behind the ego in its corridor
-          const int cur = STI(L_CUR, 0) & 0xff;
+          const int cur = STI(L_CUR, 0) & 0xf;
           const float* tab_s = col + (L_PROJ + cur) * fstride;
           const float s_e = tab_s[0];
           int jf = -1, jr = -1;
