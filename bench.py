@@ -124,7 +124,7 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_index=0):
+def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_index=0, trees=1):
     """MCTS iterations/s of one BehaviorUCT*::Plan() on the workload's scenario (second half of
     BASELINE.json's metric).  backend 'gpu' = the product (host tree search, waves of leaves on
     the GPU); 'cpu' = the same tree search on the CPU oracle, sequential (wave 1) like the
@@ -140,7 +140,8 @@ def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_
     params = {b + "Mcts::MaxNumIterations": iterations, b + "Mcts::MaxSearchTime": 1e9,
               b + "Mcts::MaxNumNodes": max(2000, iterations), b + "Mcts::Engine::WaveSize": wave,
               b + "MaxNearestAgents": A - 1, b + "Mcts::RandomHeuristic::MaxNumIterations": horizon,
-              b + "EgoBehavior::AccelerationInputs": [0.0, 1.0, 4.0, -1.0, -8.0]}
+              b + "EgoBehavior::AccelerationInputs": [0.0, 1.0, 4.0, -1.0, -8.0],
+              b + "Mcts::NumParallelMcts": trees, b + "Mcts::UseMultiThreading": 1 if trees > 1 else 0}
     if cfg.add_safe_dist:
         params[b + "Mcts::State::EvaluationParameters::AddSafeDist"] = 1
         params[b + "Mcts::State::SplitSafeDistCollision"] = 1
@@ -164,6 +165,7 @@ def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_
     wall = time.perf_counter() - t0
     return {"iterations_per_s": pl.last_num_iterations / wall, "iterations": pl.last_num_iterations,
             "plan_ms": wall * 1e3, "search_ms": pl.last_solution_time, "wave": wave,
+            "trees_per_process": trees, "iterations_per_tree": iterations,
             "nodes": pl.last_num_nodes, "best_action": pl.last_macro_action,
             "root_stats": pl.root_stats().tolist()}
 
@@ -313,7 +315,7 @@ def run_ours(args):
     plan = None
     if not args.no_plan:
         g = plan_benchmark(args.workload, args.horizon, args.plan_iterations, args.plan_wave, "gpu",
-                           device=local_rank, tree_index=rank)
+                           device=local_rank, tree_index=rank, trees=args.plan_trees)
         from planner_mcts_b200 import root_parallel
         ms = torch.tensor([g["plan_ms"]], dtype=torch.float64, device=dev)
         torch.cuda.synchronize()
@@ -388,7 +390,11 @@ def run_ours(args):
         if plan is not None:
             c = plan_benchmark(args.workload, args.horizon, args.cpu_plan_iterations, 1, "cpu")
             c.pop("root_stats")
-            line["cpu_baseline"]["plan"] = c
+            line["cpu_baseline"]["plan"] = c   # the reference's default: one sequential tree
+            cores = os.cpu_count() or 1
+            c = plan_benchmark(args.workload, args.horizon, args.cpu_plan_iterations, 1, "cpu", trees=cores)
+            c.pop("root_stats")
+            line["cpu_baseline"]["plan_all_cores"] = c   # NumParallelMcts = cores, UseMultiThreading
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -436,6 +442,8 @@ def main():
     ap.add_argument("--no-plan", action="store_true", help="skip the Plan() iterations/s arm")
     ap.add_argument("--plan-iterations", type=int, default=32768)
     ap.add_argument("--plan-wave", type=int, default=1024)
+    ap.add_argument("--plan-trees", type=int, default=8,
+                    help="root-parallel trees per process (Mcts::NumParallelMcts, one thread each)")
     ap.add_argument("--cpu-plan-iterations", type=int, default=4000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -2,6 +2,9 @@
 // Paths cited are relative to /root/reference/bark_mcts/models/behavior/.
 #include "behavior_uct.hpp"
 
+#include <atomic>
+#include <thread>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -66,7 +69,9 @@ int CurrentCorridor(const bmcts_scenario& scn, float x, float y) {
 // ------------------------------------------------------------------ BehaviorUCTBase
 
 BehaviorUCTBase::BehaviorUCTBase(const ParamsPtr& params, int state_kind, int device)
-    : BehaviorUCTBase(params, state_kind, std::shared_ptr<LeafEvaluator>(MakeDefaultEvaluator(device))) {}
+    : BehaviorUCTBase(params, state_kind, std::shared_ptr<LeafEvaluator>(MakeDefaultEvaluator(device))) {
+  evaluator_factory_ = [device]() { return std::shared_ptr<LeafEvaluator>(MakeDefaultEvaluator(device)); };
+}
 
 BehaviorUCTBase::BehaviorUCTBase(const ParamsPtr& params, int state_kind,
                                  std::shared_ptr<LeafEvaluator> evaluator)
@@ -229,6 +234,60 @@ void BehaviorUCTBase::DecideFromRootStats(const RootStats& merged) {
   last_num_nodes_ = (unsigned)merged.nodes;
 }
 
+RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees,
+                                    const std::function<TreeResult(long, LeafEvaluator*)>& run_tree,
+                                    std::vector<double>* mean_lambdas) {
+  std::vector<TreeResult> results((size_t)trees);
+  long n_threads = 1;
+  if (mcts_parameters_.USE_MULTI_THREADING && trees > 1 && evaluator_factory_) {
+    n_threads = std::min<long>(trees, std::max(1u, std::thread::hardware_concurrency()));
+    n_threads = std::min<long>(n_threads, 64);
+  }
+  if (n_threads <= 1) {
+    for (long t = 0; t < trees; ++t) results[t] = run_tree(t, evaluator_.get());
+  } else {
+    // one engine (CUDA stream + buffers) per tree thread; engines are kept between Plan() calls
+    while ((long)tree_evaluators_.size() < n_threads) tree_evaluators_.push_back(evaluator_factory_());
+    for (long i = 0; i < n_threads; ++i) {
+      int st = tree_evaluators_[i]->Configure(engine_config_, sw.scenario);
+      if (st != BMCTS_OK)
+        throw std::runtime_error("engine configure failed: " + tree_evaluators_[i]->LastError());
+    }
+    std::atomic<long> next(0);
+    std::vector<std::string> errors((size_t)n_threads);
+    std::vector<std::thread> pool;
+    for (long i = 0; i < n_threads; ++i)
+      pool.emplace_back([&, i]() {
+        try {
+          for (long t = next.fetch_add(1); t < trees; t = next.fetch_add(1))
+            results[t] = run_tree(t, tree_evaluators_[i].get());
+        } catch (const std::exception& ex) {
+          errors[i] = ex.what();
+        }
+      });
+    for (auto& th : pool) th.join();
+    for (const auto& err : errors)
+      if (!err.empty()) throw std::runtime_error(err);
+  }
+  RootStats merged;
+  merged.Resize(sw.scenario.n_ego_actions);
+  double time_ms = 0.0;
+  if (mean_lambdas) mean_lambdas->clear();
+  for (long t = 0; t < trees; ++t) {  // merge_node_statistics, in tree order (deterministic)
+    merged.Add(results[t].stats);
+    time_ms = n_threads > 1 ? std::max(time_ms, results[t].time_ms) : time_ms + results[t].time_ms;
+    if (mean_lambdas) {  // merge_mcts_parameters: mean lambda
+      if (mean_lambdas->size() < results[t].lambdas.size()) mean_lambdas->resize(results[t].lambdas.size(), 0.0);
+      for (size_t i = 0; i < results[t].lambdas.size(); ++i)
+        (*mean_lambdas)[i] += results[t].lambdas[i] / (double)trees;
+    }
+  }
+  last_solution_time_ = time_ms;
+  last_max_tree_depth_ = results[trees - 1].max_depth;
+  last_root_expanded_actions_ = results[trees - 1].root_expanded;
+  return merged;
+}
+
 // ------------------------------------------------------- BehaviorUCTHypothesisBase
 
 BehaviorUCTHypothesisBase::BehaviorUCTHypothesisBase(const ParamsPtr& params,
@@ -284,11 +343,13 @@ void BehaviorUCTHypothesisBase::UpdateBeliefs(const ObservedWorld& observed_worl
   current_beliefs_ = belief_tracker_.get_beliefs();
 }
 
-Mcts::HypothesisSampler BehaviorUCTHypothesisBase::MakeSampler(const SearchWorld& sw) {
+Mcts::HypothesisSampler BehaviorUCTHypothesisBase::MakeSampler(const SearchWorld& sw,
+                                                               unsigned tree_index) {
   std::vector<AgentId> ids = sw.slot_ids;
   const unsigned H = (unsigned)sw.scenario.n_hypotheses;
-  return [this, ids, H](std::vector<uint8_t>* hyp) {
-    for (size_t s = 1; s < ids.size(); ++s) (*hyp)[s] = (uint8_t)belief_tracker_.sample_for(ids[s], H);
+  auto tracker = std::make_shared<HypothesisBeliefTracker>(belief_tracker_.SamplerForTree(tree_index));
+  return [tracker, ids, H](std::vector<uint8_t>* hyp) {
+    for (size_t s = 1; s < ids.size(); ++s) (*hyp)[s] = (uint8_t)tracker->sample_for(ids[s], H);
   };
 }
 
@@ -304,21 +365,19 @@ Trajectory BehaviorUCTHypothesis::Plan(double min_planning_time, const ObservedW
   last_num_actions_ = sw.scenario.n_ego_actions;
   int st = evaluator_->Configure(engine_config_, sw.scenario);
   if (st != BMCTS_OK) throw std::runtime_error("engine configure failed: " + evaluator_->LastError());
-  RootStats merged;
-  merged.Resize(sw.scenario.n_ego_actions);
-  double time_ms = 0.0;
   const long trees = std::max<long>(1, mcts_parameters_.NUM_PARALLEL_MCTS);
-  for (long t = 0; t < trees; ++t) {
+  RootStats merged = RunTrees(sw, trees, [&](long t, LeafEvaluator* ev) {
+    const unsigned tree = tree_index_ * (unsigned)trees + (unsigned)t;
     Mcts mcts(mcts_parameters_, EgoMode::kUct, OtherMode::kHypothesis, sw.scenario.n_agents,
-              sw.scenario.n_ego_actions, sw.scenario.n_hypotheses, 1, evaluator_.get(),
-              tree_index_ * (unsigned)trees + (unsigned)t);
-    mcts.Search(sw.pose, sw.alive, 1, MakeSampler(sw));
-    merged.Add(mcts.GetRootStats());
-    time_ms += mcts.searchTime();
-    last_max_tree_depth_ = mcts.maxTreeDepth();
-    last_root_expanded_actions_ = mcts.RootExpandedActions();
-  }
-  last_solution_time_ = time_ms;
+              sw.scenario.n_ego_actions, sw.scenario.n_hypotheses, 1, ev, tree);
+    mcts.Search(sw.pose, sw.alive, 1, MakeSampler(sw, tree));
+    TreeResult r;
+    r.stats = mcts.GetRootStats();
+    r.time_ms = mcts.searchTime();
+    r.max_depth = mcts.maxTreeDepth();
+    r.root_expanded = mcts.RootExpandedActions();
+    return r;
+  });
   DecideFromRootStats(merged);
   FinishPlan(sw, observed_world, last_motion_idx_, min_planning_time);
   return last_trajectory_;
@@ -385,25 +444,22 @@ Trajectory BehaviorUCTRiskConstraint::Plan(double min_planning_time, const Obser
   const int n_costs = engine_config_.split_safe_dist_collision ? 2 : 1;  // get_num_costs
   MctsParameters current = mcts_parameters_;
   current.cost_constrained_statistic.COST_CONSTRAINTS = current_scenario_risk_;  // :145-146
-  RootStats merged;
-  merged.Resize(sw.scenario.n_ego_actions);
-  double time_ms = 0.0;
-  last_lambdas_.assign(n_costs, 0.0);
   const long trees = std::max<long>(1, mcts_parameters_.NUM_PARALLEL_MCTS);
-  for (long t = 0; t < trees; ++t) {
+  RootStats merged = RunTrees(sw, trees, [&](long t, LeafEvaluator* ev) {
+    const unsigned tree = tree_index_ * (unsigned)trees + (unsigned)t;
     Mcts mcts(current, EgoMode::kCostConstrained, OtherMode::kHypothesis, sw.scenario.n_agents,
-              sw.scenario.n_ego_actions, sw.scenario.n_hypotheses, n_costs, evaluator_.get(),
-              tree_index_ * (unsigned)trees + (unsigned)t);
+              sw.scenario.n_ego_actions, sw.scenario.n_hypotheses, n_costs, ev, tree);
     mcts.set_cost_constraints(current_scenario_risk_);
-    mcts.Search(sw.pose, sw.alive, 1, MakeSampler(sw));
-    merged.Add(mcts.GetRootStats());
-    time_ms += mcts.searchTime();
-    for (int i = 0; i < n_costs && i < (int)mcts.lambdas().size(); ++i)
-      last_lambdas_[i] += mcts.lambdas()[i] / (double)trees;  // merge_mcts_parameters: mean lambda
-    last_max_tree_depth_ = mcts.maxTreeDepth();
-    last_root_expanded_actions_ = mcts.RootExpandedActions();
-  }
-  last_solution_time_ = time_ms;
+    mcts.Search(sw.pose, sw.alive, 1, MakeSampler(sw, tree));
+    TreeResult r;
+    r.stats = mcts.GetRootStats();
+    r.time_ms = mcts.searchTime();
+    r.max_depth = mcts.maxTreeDepth();
+    r.root_expanded = mcts.RootExpandedActions();
+    r.lambdas = mcts.lambdas();
+    r.lambdas.resize(n_costs, 0.0);
+    return r;
+  }, &last_lambdas_);
   DecideFromRootStats(merged);
   FinishPlan(sw, observed_world, last_motion_idx_, min_planning_time);
   return last_trajectory_;
@@ -463,21 +519,19 @@ Trajectory BehaviorUCTCooperative::Plan(double min_planning_time, const Observed
   last_num_actions_ = sw.scenario.n_ego_actions;
   int st = evaluator_->Configure(engine_config_, sw.scenario);
   if (st != BMCTS_OK) throw std::runtime_error("engine configure failed: " + evaluator_->LastError());
-  RootStats merged;
-  merged.Resize(sw.scenario.n_ego_actions);
-  double time_ms = 0.0;
   const long trees = std::max<long>(1, mcts_parameters_.NUM_PARALLEL_MCTS);
-  for (long t = 0; t < trees; ++t) {
+  RootStats merged = RunTrees(sw, trees, [&](long t, LeafEvaluator* ev) {
+    const unsigned tree = tree_index_ * (unsigned)trees + (unsigned)t;
     Mcts mcts(mcts_parameters_, EgoMode::kUct, OtherMode::kUct, sw.scenario.n_agents,
-              sw.scenario.n_ego_actions, 0, 1, evaluator_.get(),
-              tree_index_ * (unsigned)trees + (unsigned)t);
+              sw.scenario.n_ego_actions, 0, 1, ev, tree);
     mcts.Search(sw.pose, sw.alive, 1, nullptr);
-    merged.Add(mcts.GetRootStats());
-    time_ms += mcts.searchTime();
-    last_max_tree_depth_ = mcts.maxTreeDepth();
-    last_root_expanded_actions_ = mcts.RootExpandedActions();
-  }
-  last_solution_time_ = time_ms;
+    TreeResult r;
+    r.stats = mcts.GetRootStats();
+    r.time_ms = mcts.searchTime();
+    r.max_depth = mcts.maxTreeDepth();
+    r.root_expanded = mcts.RootExpandedActions();
+    return r;
+  });
   DecideFromRootStats(merged);
   FinishPlan(sw, observed_world, last_motion_idx_, min_planning_time);
   return last_trajectory_;

@@ -81,9 +81,18 @@ class BehaviorUCTBase : public UctBaseDebugInfos {
   RootStats GetLastRootStats() const { return last_root_stats_; }
   // re-decide from externally merged statistics (NCCL all-reduce over ranks)
   virtual void DecideFromRootStats(const RootStats& merged);
-  uint64_t EngineLaunchCount() const { return evaluator_ ? evaluator_->LaunchCount() : 0; }
+  uint64_t EngineLaunchCount() const {
+    uint64_t n = evaluator_ ? evaluator_->LaunchCount() : 0;
+    for (const auto& ev : tree_evaluators_) n += ev->LaunchCount();
+    return n;
+  }
   const MctsParameters& mcts_parameters() const { return mcts_parameters_; }
   void set_tree_index(unsigned i) { tree_index_ = i; }
+  // how further rollout engines are made for Mcts::UseMultiThreading (one engine, i.e. one
+  // CUDA stream, per tree thread); without a factory the trees run one after the other
+  void set_evaluator_factory(std::function<std::shared_ptr<LeafEvaluator>()> f) {
+    evaluator_factory_ = std::move(f);
+  }
 
  protected:
   struct SearchWorld {
@@ -100,10 +109,25 @@ class BehaviorUCTBase : public UctBaseDebugInfos {
                                    double t0, Action* last_action) const;
   void FinishPlan(const SearchWorld& sw, const ObservedWorld& observed_world, unsigned best_action,
                   double min_planning_time);
+  // result of one root-parallel tree
+  struct TreeResult {
+    RootStats stats;
+    double time_ms = 0.0;
+    int max_depth = 0;
+    std::vector<int> root_expanded;
+    std::vector<double> lambdas;
+  };
+  // runs `trees` independent searches (Mcts::NumParallelMcts) -- on threads with one engine
+  // each when Mcts::UseMultiThreading is set -- and merges their root statistics in tree order
+  RootStats RunTrees(const SearchWorld& sw, long trees,
+                     const std::function<TreeResult(long, LeafEvaluator*)>& run_tree,
+                     std::vector<double>* mean_lambdas = nullptr);
 
   ParamsPtr params_;
   int state_kind_;
   std::shared_ptr<LeafEvaluator> evaluator_;
+  std::function<std::shared_ptr<LeafEvaluator>()> evaluator_factory_;
+  std::vector<std::shared_ptr<LeafEvaluator>> tree_evaluators_;  // engines of the tree threads
   MctsParameters mcts_parameters_;
   bmcts_config engine_config_;
   unsigned max_nearest_agents_;
@@ -129,7 +153,7 @@ class BehaviorUCTHypothesisBase : public BehaviorUCTBase, public UctHypothesisDe
   void UpdateBeliefs(const ObservedWorld& observed_world);
 
  protected:
-  Mcts::HypothesisSampler MakeSampler(const SearchWorld& sw);
+  Mcts::HypothesisSampler MakeSampler(const SearchWorld& sw, unsigned tree_index);
   std::vector<BehaviorHypothesisIDM> behavior_hypotheses_;
   bool use_true_behaviors_as_hypothesis_;
   HypothesisBeliefTracker belief_tracker_;

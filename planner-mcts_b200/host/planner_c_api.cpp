@@ -34,6 +34,13 @@ void EnsurePlanner(bmcts_planner* p) {
       throw std::runtime_error("unknown planner kind");
   }
   p->planner->set_tree_index(p->tree_index);
+  if (p->evaluator_factory) {
+    p->planner->set_evaluator_factory(p->evaluator_factory);
+  } else {
+    const int device = p->device;
+    p->planner->set_evaluator_factory(
+        [device]() { return std::shared_ptr<LeafEvaluator>(MakeDefaultEvaluator(device)); });
+  }
 }
 
 void FillResult(bmcts_planner* p, bmcts_plan_result* out) {

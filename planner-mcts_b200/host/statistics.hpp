@@ -581,6 +581,15 @@ class HypothesisBeliefTracker {
     return current_;
   }
 
+  // Independent sampler of one root-parallel tree: a snapshot of the beliefs with its own
+  // generator (seed + tree index), so trees can run on different threads / ranks
+  HypothesisBeliefTracker SamplerForTree(unsigned tree_index) const {
+    HypothesisBeliefTracker t(*this);
+    t.history_.clear();
+    t.gen_.seed((unsigned)p_.RANDOM_SEED_HYPOTHESIS_SAMPLING + 7919u * tree_index);
+    return t;
+  }
+
   unsigned sample_for(AgentId id, unsigned num_hypotheses) {
     auto f = fixed_.find(id);
     if (f != fixed_.end()) return f->second;

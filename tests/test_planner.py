@@ -167,6 +167,24 @@ def test_root_parallel_merge_of_two_trees():
     assert best[0] == int(np.argmax(np.where(merged[:n_act] > 0, values, -np.inf)))
 
 
+@pytest.mark.parametrize("make", BACKENDS)
+def test_multi_threaded_trees_equal_sequential_trees(make):
+    """Mcts::NumParallelMcts trees on threads (Mcts::UseMultiThreading, one engine per thread)
+    give exactly the statistics of the same trees run one after the other"""
+    world = W.observed_world(2, 4.0, 6.0, 3.0, goal_center=(150.0, -1.75))
+    out = []
+    for threaded in (0, 1):
+        params = W.base_params(300)
+        params[P0 + "Mcts::NumParallelMcts"] = 4
+        params[P0 + "Mcts::UseMultiThreading"] = threaded
+        pl = make(P.BehaviorUCTHypothesis, params, W.hypotheses())
+        pl.Plan(0.2, world)
+        out.append((pl.root_stats(), pl.last_macro_action, pl.last_num_iterations))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1:] == out[1][1:]
+    assert out[0][2] == 4 * 300
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cls,wave", [(P.BehaviorUCTHypothesis, 1), (P.BehaviorUCTHypothesis, 64),
                                       (P.BehaviorUCTRiskConstraint, 32),
