@@ -15,8 +15,8 @@ from planner_mcts_b200 import _abi, scenarios
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_functions():
-    text = open(os.path.join(ROOT, "include", "bmcts_c.h")).read()
+def _declared_functions(header="bmcts_c.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(bmcts_[a-z_0-9]+)\s*\(", text)))
 
@@ -29,6 +29,15 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libbmcts.so does not export {name}"
     assert sorted(_abi.EXPORTED_SYMBOLS) == declared
     assert lib.bmcts_abi_version() == 1
+    # the planner ABI (include/bmcts_planner_c.h)
+    from planner_mcts_b200 import planner
+    declared = [f for f in _declared_functions("bmcts_planner_c.h") if f.startswith("bmcts_planner_")]
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), f"libbmcts.so does not export {name}"
+    assert sorted(planner.PLANNER_SYMBOLS) == sorted(declared)
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["bmcts_c.h", "bmcts_math.h",
+                                                                 "bmcts_planner_c.h"]
 
 
 def test_struct_sizes_match_header():
@@ -109,6 +118,16 @@ def test_create_fails_loudly_without_a_gpu():
     with pytest.raises(BmctsError) as ei:
         RolloutEngine(cfg, scn)
     assert ei.value.status == _abi.ERR_NO_DEVICE
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a GPU")
+def test_planner_fails_loudly_without_a_gpu():
+    """the BehaviorUCT* planners refuse to plan without the CUDA engine"""
+    import planner_worlds as W
+    from planner_mcts_b200 import BmctsError, planner as P
+    pl = P.BehaviorUCTHypothesis(W.base_params(10), W.hypotheses())
+    with pytest.raises(BmctsError):
+        pl.Plan(0.2, W.observed_world(1, 5.0, 5.0, 0.0))
 
 
 def test_product_does_not_reference_the_oracle():
