@@ -176,7 +176,19 @@ BM_HD float bm_atan2(float y, float x) {
     if (y < 0.0f) return -BM_PIO2_HI;
     return 0.0f;
   }
-  float a = bm_atan(bm_div(y, x));
+  /* y == 0 (an agent exactly on its lane centre line) would send the device's IEEE division
+   * through its slow path; 0 / x is a zero with the XOR of the signs, spelled out instead */
+  float q;
+  if (y == 0.0f) {
+    union { float f; uint32_t u; } uy, ux, uq;
+    uy.f = y;
+    ux.f = x;
+    uq.u = (uy.u ^ ux.u) & 0x80000000u;
+    q = uq.f;
+  } else {
+    q = bm_div(y, x);
+  }
+  float a = bm_atan(q);
   if (x < 0.0f) a = (y >= 0.0f) ? (a + BM_PI_F) : (a - BM_PI_F);
   return a;
 }
