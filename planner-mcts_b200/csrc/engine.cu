@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "bmcts_c.h"
+#include "inner_rects.hpp"
 #include "rollout_device.cuh"
 #include "rollout_lane_kernel.cuh"
 #include "rollout_lane_coop_kernel.cuh"
@@ -37,6 +38,7 @@ struct bmcts_engine {
   bmcts_config cfg;
   bmcts_scenario scn;
   bool has_scenario = false;
+  bmcts::InnerRects rects{};
   bmcts_config* d_cfg = nullptr;
   bmcts_scenario* d_scn = nullptr;
   float* d_dt_table = nullptr;
@@ -473,7 +475,9 @@ int bmcts_create(int device, const bmcts_config* cfg, bmcts_engine** out) {
   if ((ce = cudaEventCreate(&e->ev_start)) != cudaSuccess) return bail(ce);
   if ((ce = cudaEventCreate(&e->ev_stop)) != cudaSuccess) return bail(ce);
   if ((ce = cudaMalloc(&e->d_cfg, sizeof(bmcts_config))) != cudaSuccess) return bail(ce);
-  if ((ce = cudaMalloc(&e->d_scn, sizeof(bmcts_scenario))) != cudaSuccess) return bail(ce);
+  // the scenario is followed by the derived inner rectangles of the road polygon
+  if ((ce = cudaMalloc(&e->d_scn, sizeof(bmcts_scenario) + sizeof(bmcts::InnerRects))) != cudaSuccess)
+    return bail(ce);
   if ((ce = cudaMalloc(&e->d_dt_table, sizeof(float) * BMCTS_MAX_DEPTH)) != cudaSuccess)
     return bail(ce);
   cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -547,9 +551,27 @@ int bmcts_set_scenario(bmcts_engine* e, const bmcts_scenario* scn) {
     return fail(e, BMCTS_ERR_INVALID_ARG, "hypothesis states need at least one hypothesis");
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->stream));
+  // inner rectangles: recomputed only when the road polygon changes (a planner sets the same
+  // map at every Plan())
+  const bool same_road = e->has_scenario && e->scn.n_road_pts == scn->n_road_pts &&
+                         std::memcmp(e->scn.road_x, scn->road_x, sizeof(scn->road_x)) == 0 &&
+                         std::memcmp(e->scn.road_y, scn->road_y, sizeof(scn->road_y)) == 0;
   e->scn = *scn;
+  if (!same_road) e->rects = bmcts::find_inner_rects(e->scn);
+  bmcts::InnerRects up = e->rects;
+  if (std::getenv("BMCTS_DEBUG"))
+    for (int r = 0; r < up.n; ++r)
+      std::fprintf(stderr, "[bmcts] inner rect %d: x [%g, %g] y [%g, %g]\n", r, up.rect[r][0],
+                   up.rect[r][1], up.rect[r][2], up.rect[r][3]);
+  if (std::getenv("BMCTS_NO_RECTS")) up.n = 0;  // tests: the scan-only path
+  for (int r = up.n; r < 2; ++r) {  // unused rectangles are empty
+    up.rect[r][0] = up.rect[r][2] = 1.0e30f;
+    up.rect[r][1] = up.rect[r][3] = -1.0e30f;
+  }
   CU(cudaMemcpyAsync(e->d_scn, &e->scn, sizeof(bmcts_scenario), cudaMemcpyHostToDevice,
                      e->stream));
+  CU(cudaMemcpyAsync(reinterpret_cast<char*>(e->d_scn) + sizeof(bmcts_scenario), &up,
+                     sizeof(bmcts::InnerRects), cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   e->has_scenario = true;
   return BMCTS_OK;

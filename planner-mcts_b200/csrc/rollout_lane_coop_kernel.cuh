@@ -61,6 +61,7 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
   const bmcts_config& cfg = *reinterpret_cast<const bmcts_config*>(smem_raw + lay.off_cfg);
   const float* reach = reinterpret_cast<const float*>(smem_raw + lay.off_rad);
   const float* goal_bb = reach + 2 * BMCTS_MAX_AGENTS;
+  const float* rects = goal_bb + 4;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = lane % T;
@@ -208,7 +209,8 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
           }
           if (want_final) p.final_pose[gi] = make_float4(x, y, th, v);
           // World::RemoveInvalidAgents (spec item 6)
-          if (!point_in_polygon(scn.road_x, scn.road_y, n_road, x, y)) {
+          if (!in_rects(rects, x, y) &&
+              !point_in_polygon(scn.road_x, scn.road_y, n_road, x, y)) {
             dead |= 1u << a;
             continue;
           }
@@ -263,6 +265,8 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
           bool in;
           if (!road && (cx < goal_bb[0] || cx > goal_bb[1] || cy < goal_bb[2] || cy > goal_bb[3]))
             in = false;  // outside the goal's bounding box (1 cm margin)
+          else if (road && in_rects(rects, cx, cy))
+            in = true;  // inside an inner rectangle of the road polygon
           else
             in = point_in_polygon(road ? scn.road_x : scn.goal.px, road ? scn.road_y : scn.goal.py,
                                   road ? n_road : scn.goal.n_pts, cx, cy);

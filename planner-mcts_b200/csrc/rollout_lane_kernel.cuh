@@ -60,7 +60,7 @@ __host__ __device__ inline LaneLayout lane_layout(int A, int C, int H, int T, in
   l.off_hflags = b;
   b += smem_align16(sizeof(uint32_t) * 4 * (size_t)(H > 0 ? H : 1));  // flags, 1/v0, 1/(2 sqrt(ab))
   l.off_rad = b;  // per agent: plain / static-inflated bounding radius; then the goal's AABB
-  b += smem_align16(sizeof(float) * (2 * BMCTS_MAX_AGENTS + 4));
+  b += smem_align16(sizeof(float) * (2 * BMCTS_MAX_AGENTS + 4 + 8));  // + goal AABB + 2 inner rects
   l.off_state = b;
   l.warp_bytes = sizeof(float) * (size_t)(L_PROJ + C) * A * (32 / T);
   l.total = b + l.warp_bytes * warps;
@@ -113,7 +113,17 @@ __device__ __forceinline__ void stage_reach(const bmcts_scenario* scn, const bmc
     bb[1] = x1 + 0.01f;
     bb[2] = y0 - 0.01f;
     bb[3] = y1 + 0.01f;
+    // inner rectangles of the road polygon (engine.cu stores them behind the scenario)
+    const float* rc = reinterpret_cast<const float*>(scn + 1);
+    for (int i = 0; i < 8; ++i) bb[4 + i] = rc[i];
   }
+}
+
+// inside one of the road polygon's inner rectangles (inner_rects.hpp): certainly drivable
+__device__ __forceinline__ bool in_rects(const float* rc, float x, float y) {
+  const bool a = x >= rc[0] && x <= rc[1] && y >= rc[2] && y <= rc[3];
+  const bool b = x >= rc[4] && x <= rc[5] && y >= rc[6] && y <= rc[7];
+  return a || b;
 }
 
 // IDM sub-step loop (BaseIDM::Plan, spec item 4): returns the travelled distance
@@ -222,6 +232,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
   const uint32_t* hflags = reinterpret_cast<const uint32_t*>(smem_raw + lay.off_hflags);
   const float* reach = reinterpret_cast<const float*>(smem_raw + lay.off_rad);
   const float* goal_bb = reach + 2 * BMCTS_MAX_AGENTS;
+  const float* rects = goal_bb + 4;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = lane % T;  // lane inside the group
@@ -483,7 +494,9 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
             if (p.reward && a > 0) p.reward[gi] = 0.0f;
           }
           if (want_final) p.final_pose[gi] = make_float4(x, y, th, v);
-          if (!point_in_polygon(scn.road_x, scn.road_y, n_road, x, y)) {
+          // World::RemoveInvalidAgents; a point inside an inner rectangle of the road polygon
+          // needs no scan
+          if (!in_rects(rects, x, y) && !point_in_polygon(scn.road_x, scn.road_y, n_road, x, y)) {
             dead |= 1u << a;
             continue;
           }
@@ -585,6 +598,8 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         bool in;
         if (!road && (cx < goal_bb[0] || cx > goal_bb[1] || cy < goal_bb[2] || cy > goal_bb[3]))
           in = false;  // outside the goal's bounding box (1 cm margin)
+        else if (road && in_rects(rects, cx, cy))
+          in = true;  // inside an inner rectangle of the road polygon
         else
           in = point_in_polygon(road ? scn.road_x : scn.goal.px, road ? scn.road_y : scn.goal.py,
                                 road ? n_road : scn.goal.n_pts, cx, cy);

@@ -35,6 +35,12 @@ def test_full_size_batch_properties(name, n, monkeypatch):
     monkeypatch.setenv("BMCTS_PIPE_CHUNK", "100000")
     assert np.array_equal(a, _run(eng, pose, alive, hyp)["result"]), "chunked host batch"
     monkeypatch.setenv("BMCTS_PIPE_CHUNK", "0")
+    # the exact early-out of the drivable-area scan (inner rectangles of the road polygon,
+    # found at bmcts_set_scenario) changes nothing
+    monkeypatch.setenv("BMCTS_NO_RECTS", "1")
+    plain = RolloutEngine(cfg, scn)
+    monkeypatch.delenv("BMCTS_NO_RECTS")
+    assert np.array_equal(a, _run(plain, pose, alive, hyp)["result"]), "scan-only path"
     # 3. record consistency
     A, H = meta["A"], cfg.max_rollout_steps
     term = (a["flags"] & _abi.F_TERMINAL) != 0
