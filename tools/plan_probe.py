@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Plan() time split (host select / fill / engine / backup) at several wave sizes."""
+"""Plan() time split (host select / fill / engine / backup per tree) at several wave sizes and
+tree counts -- run on the GPU box."""
 import os
 import sys
 
@@ -10,7 +11,7 @@ os.environ["BMCTS_DEBUG"] = "1"
 import bench  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2_merge_sbg"
-for wave in (256, 1024, 4096):
-    r = bench.plan_benchmark(wl, 20, 32768, wave, "gpu")
+for trees, wave in ((1, 1024), (1, 4096), (8, 1024), (8, 4096), (16, 1024)):
+    r = bench.plan_benchmark(wl, 20, 32768, wave, "gpu", trees=trees)
     r.pop("root_stats")
-    print(wave, r, flush=True)
+    print(f"trees {trees} wave {wave}:", r, flush=True)
