@@ -442,7 +442,7 @@ def main():
     ap.add_argument("--no-plan", action="store_true", help="skip the Plan() iterations/s arm")
     ap.add_argument("--plan-iterations", type=int, default=32768)
     ap.add_argument("--plan-wave", type=int, default=1024)
-    ap.add_argument("--plan-trees", type=int, default=8,
+    ap.add_argument("--plan-trees", type=int, default=min(16, os.cpu_count() or 1),
                     help="root-parallel trees per process (Mcts::NumParallelMcts, one thread each)")
     ap.add_argument("--cpu-plan-iterations", type=int, default=4000)
     args = ap.parse_args()

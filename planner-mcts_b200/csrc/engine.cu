@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -30,6 +32,11 @@ struct DevBuf {
 
 }  // namespace
 
+struct LaneGeometry {  // cached launch geometry of a lane kernel variant
+  int W = 0, blocks = 0;
+  size_t smem = 0;
+};
+
 struct bmcts_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -39,6 +46,12 @@ struct bmcts_engine {
   bmcts_scenario scn;
   bool has_scenario = false;
   bmcts::InnerRects rects{};
+  std::map<unsigned long long, LaneGeometry> geometry;
+  // packed staging of small host-memory batches: one pinned block each way
+  void* h_pack_in = nullptr;
+  void* h_pack_out = nullptr;
+  size_t h_pack_in_cap = 0, h_pack_out_cap = 0;
+  DevBuf d_pack_in, d_pack_out;
   bmcts_config* d_cfg = nullptr;
   bmcts_scenario* d_scn = nullptr;
   float* d_dt_table = nullptr;
@@ -127,52 +140,73 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cuda
     return COOP ? bmcts::lane_coop_layout(a.A, a.C, T, W) : bmcts::lane_layout(a.A, a.C, a.H, T, W);
   };
   const int NC = 32 / T;
-  const int groups = a.n;
-  int best_W = 1, best_blocks = 1;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                          cudaSharedmemCarveoutMaxShared));
-  long best_score = -1;
-  for (int W = BMCTS_LANE_MAX_THREADS / 32; W >= 1; --W) {
-    if (force_W > 0 && W != force_W) continue;
-    const bmcts::LaneLayout lay = layout(W);
-    if ((int)lay.total > e->max_smem_optin) continue;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-    int blocks = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, W * 32, lay.total));
-    if (blocks < 1) continue;
-    // a small batch is spread over the SMs first: never more warps than it can fill
-    const long need_warps = (groups + NC - 1) / NC;
-    long resident = (long)blocks * W * e->sm_count;
-    long useful = resident < need_warps ? resident : need_warps;
-    // prefer the geometry that runs most warps at once, then the one that spreads them
-    // over more SMs (smaller W)
-    long score = useful * 64 - (useful == need_warps ? W : 0);
-    if (score > best_score) {
-      best_score = score;
-      best_W = W;
-      best_blocks = blocks;
+  const long need_warps = ((long)a.n + NC - 1) / NC;
+  // the kernel may use all the shared memory the SM offers: set once per process and variant
+  // (engines on several host threads share the function, the attribute only ever grows)
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  const int optin = e->max_smem_optin;
+  std::call_once(attr_once, [&]() {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(e, attr_err, "cudaFuncSetAttribute");
+  // geometry per (variant, scenario size, batch class): occupancy queries are cached
+  const long full = 1L << 40;
+  const unsigned long long key = ((unsigned long long)COOP << 60) | ((unsigned long long)T << 56) |
+                                 ((unsigned long long)a.A << 48) | ((unsigned long long)a.C << 44) |
+                                 ((unsigned long long)a.H << 36) | ((unsigned long long)force_W << 28) |
+                                 (unsigned long long)std::min<long>(need_warps, (1L << 28) - 1);
+  (void)full;
+  LaneGeometry g;
+  auto it = e->geometry.find(key);
+  if (it != e->geometry.end()) {
+    g = it->second;
+  } else {
+    long best_score = -1;
+    for (int W = BMCTS_LANE_MAX_THREADS / 32; W >= 1; --W) {
+      if (force_W > 0 && W != force_W) continue;
+      const bmcts::LaneLayout lay = layout(W);
+      if ((int)lay.total > e->max_smem_optin) continue;
+      int blocks = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, W * 32, lay.total));
+      if (blocks < 1) continue;
+      // a small batch is spread over the SMs first: never more warps than it can fill
+      long resident = (long)blocks * W * e->sm_count;
+      long useful = resident < need_warps ? resident : need_warps;
+      // prefer the geometry that runs most warps at once, then the one that spreads them
+      // over more SMs (smaller W)
+      long score = useful * 64 - (useful == need_warps ? W : 0);
+      if (score > best_score) {
+        best_score = score;
+        g.W = W;
+        g.blocks = blocks;
+        g.smem = lay.total;
+      }
     }
+    if (best_score < 0)
+      return fail(e, BMCTS_ERR_UNSUPPORTED, "scenario needs more shared memory than the SM offers");
+    if (e->geometry.size() > 4096) e->geometry.clear();
+    e->geometry[key] = g;
   }
-  if (best_score < 0)
-    return fail(e, BMCTS_ERR_UNSUPPORTED, "scenario needs more shared memory than the SM offers");
-  const bmcts::LaneLayout lay = layout(best_W);
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-  const long need_blocks = ((long)groups + (long)NC * best_W - 1) / ((long)NC * best_W);
-  long grid = (long)best_blocks * e->sm_count;
+  const long need_blocks = ((long)a.n + (long)NC * g.W - 1) / ((long)NC * g.W);
+  long grid = (long)g.blocks * e->sm_count;
   if (grid > need_blocks) grid = need_blocks;
   if (const char* s = std::getenv("BMCTS_LANE_GRID")) {  // tests: force the refill path
     const long cap = std::atol(s);
     if (cap > 0 && grid > cap) grid = cap;
   }
   CU(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
-  kern<<<(unsigned)grid, best_W * 32, lay.total, stream>>>(a, counter);
+  kern<<<(unsigned)grid, g.W * 32, g.smem, stream>>>(a, counter);
   CU(cudaGetLastError());
   e->launches++;
   e->lane_T = T;
-  e->lane_W = best_W;
+  e->lane_W = g.W;
   if (std::getenv("BMCTS_DEBUG"))
     std::fprintf(stderr, "[bmcts] lane kernel coop=%d T=%d W=%d blocks/SM=%d grid=%ld smem=%zu n=%d\n",
-                 (int)COOP, T, best_W, best_blocks, grid, lay.total, a.n);
+                 (int)COOP, T, g.W, g.blocks, grid, g.smem, a.n);
   return BMCTS_OK;
 }
 
@@ -435,6 +469,68 @@ int rollout_host_pipelined(bmcts_engine* e, const bmcts_leaf_batch* in, const bm
   return BMCTS_OK;
 }
 
+// ---- packed staging of small host-memory batches -------------------------------------
+// A planner wave is a dozen small arrays each way.  Copying them one by one costs a dozen
+// driver calls (and, from pageable memory, a dozen synchronous staging copies); instead they
+// are gathered into ONE pinned block, uploaded with one copy, and the outputs come back the
+// same way: 1 upload + 1 kernel + 1 download + 1 synchronize per wave.
+struct Pack {
+  struct Item {
+    const void* src;
+    void* dst;
+    size_t off, bytes;
+  };
+  std::vector<Item> items;
+  size_t bytes = 0;
+  static constexpr size_t kNone = ~size_t(0);
+  size_t add(const void* src, void* dst, size_t n) {
+    if (!src && !dst) return kNone;
+    const size_t off = bytes;
+    items.push_back({src, dst, off, n});
+    bytes += (n + 255) & ~size_t(255);
+    return off;
+  }
+};
+
+int ensure_pinned(bmcts_engine* e, void** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return BMCTS_OK;
+  if (*p) CU(cudaFreeHost(*p));
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = bytes + bytes / 2 + 4096;
+  CU(cudaHostAlloc(p, want, cudaHostAllocDefault));
+  *cap = want;
+  return BMCTS_OK;
+}
+
+constexpr size_t kPackLimit = 48u << 20;  // larger host batches keep the per-array / streamed paths
+
+// uploads the packed inputs; returns device base pointers of the input and output blocks
+int pack_upload(bmcts_engine* e, const Pack& pin, const Pack& pout, char** d_in, char** d_out) {
+  int st;
+  if ((st = ensure_pinned(e, &e->h_pack_in, &e->h_pack_in_cap, pin.bytes))) return st;
+  if ((st = ensure_pinned(e, &e->h_pack_out, &e->h_pack_out_cap, pout.bytes))) return st;
+  if ((st = ensure(e, e->d_pack_in, pin.bytes))) return st;
+  if ((st = ensure(e, e->d_pack_out, pout.bytes))) return st;
+  for (const Pack::Item& it : pin.items)
+    std::memcpy((char*)e->h_pack_in + it.off, it.src, it.bytes);
+  CU(cudaMemcpyAsync(e->d_pack_in.ptr, e->h_pack_in, pin.bytes, cudaMemcpyHostToDevice, e->stream));
+  *d_in = (char*)e->d_pack_in.ptr;
+  *d_out = (char*)e->d_pack_out.ptr;
+  return BMCTS_OK;
+}
+
+int pack_download(bmcts_engine* e, const Pack& pout) {
+  if (pout.bytes) {
+    CU(cudaMemcpyAsync(e->h_pack_out, e->d_pack_out.ptr, pout.bytes, cudaMemcpyDeviceToHost,
+                       e->stream));
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  for (const Pack::Item& it : pout.items)
+    std::memcpy(it.dst, (char*)e->h_pack_out + it.off, it.bytes);
+  return BMCTS_OK;
+}
+
 int check_ready(bmcts_engine* e) {
   if (!e) return BMCTS_ERR_INVALID_ARG;
   if (!e->has_scenario) return fail(e, BMCTS_ERR_NO_SCENARIO, "bmcts_set_scenario was not called");
@@ -525,6 +621,10 @@ void bmcts_destroy(bmcts_engine* e) {
   }
   if (e->ev_pipe) cudaEventDestroy(e->ev_pipe);
   if (e->d_ready) cudaFree(e->d_ready);
+  if (e->h_pack_in) cudaFreeHost(e->h_pack_in);
+  if (e->h_pack_out) cudaFreeHost(e->h_pack_out);
+  free_buf(e->d_pack_in);
+  free_buf(e->d_pack_out);
   if (e->h_ready) cudaFreeHost(e->h_ready);
   if (e->ev_start) cudaEventDestroy(e->ev_start);
   if (e->ev_stop) cudaEventDestroy(e->ev_stop);
@@ -604,6 +704,32 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
   }
   if (stream_chunk(n) > 0) return rollout_host_streamed(e, in, out, a);
   if (pipeline_chunk(n) > 0) return rollout_host_pipelined(e, in, out, a);
+  {
+    const size_t nA = (size_t)n * A;
+    Pack pin, pout;
+    const size_t i_pose = pin.add(in->pose, nullptr, sizeof(float) * 4 * nA);
+    const size_t i_alive = pin.add(in->alive, nullptr, sizeof(uint32_t) * (size_t)n);
+    const size_t i_hyp = pin.add(in->hyp_id, nullptr, nA);
+    const size_t i_depth = pin.add(in->depth, nullptr, sizeof(uint16_t) * (size_t)n);
+    const size_t o_res = pout.add(nullptr, out->result, sizeof(bmcts_rollout_result) * (size_t)n);
+    const size_t o_ra = pout.add(nullptr, out->ret_agents, sizeof(float) * nA);
+    const size_t o_fp = pout.add(nullptr, out->final_pose, sizeof(float) * 4 * nA);
+    if (pin.bytes + pout.bytes <= kPackLimit) {
+      char *di, *dout;
+      if ((st = pack_upload(e, pin, pout, &di, &dout))) return st;
+      auto ip = [&](size_t off) -> const void* { return off == Pack::kNone ? nullptr : di + off; };
+      auto op = [&](size_t off) -> void* { return off == Pack::kNone ? nullptr : dout + off; };
+      a.pose = (const float4*)ip(i_pose);
+      a.alive = (const uint32_t*)ip(i_alive);
+      a.hyp = (const uint8_t*)ip(i_hyp);
+      a.depth = (const uint16_t*)ip(i_depth);
+      a.result = (bmcts_rollout_result*)op(o_res);
+      a.ret_agents = (float*)op(o_ra);
+      a.final_pose = (float4*)op(o_fp);
+      if ((st = launch(e, a))) return st;
+      return pack_download(e, pout);
+    }
+  }
   const void* d;
   void* o;
   if ((st = h2d(e, e->b_pose, in->pose, sizeof(float) * 4 * (size_t)n * A, &d))) return st;
@@ -672,9 +798,50 @@ static int step_common(bmcts_engine* e, const bmcts_step_in* in, const bmcts_ste
     }
     return launch(e, a);
   }
+  const size_t nA = (size_t)n * A;
+  {
+    Pack pin, pout;
+    const size_t i_pose = pin.add(in->pose, nullptr, sizeof(float) * 4 * nA);
+    const size_t i_alive = pin.add(in->alive, nullptr, sizeof(uint32_t) * (size_t)n);
+    const size_t i_hyp = pin.add(in->hyp_id, nullptr, nA);
+    const size_t i_depth = pin.add(in->depth, nullptr, sizeof(uint16_t) * (size_t)n);
+    const size_t i_action = pin.add(in->action, nullptr, nA);
+    const size_t i_draw = pin.add(in->draw_id, nullptr, sizeof(uint64_t) * nA);
+    const size_t o_np = pout.add(nullptr, so->next_pose, sizeof(float) * 4 * nA);
+    const size_t o_na = pout.add(nullptr, so->next_alive, sizeof(uint32_t) * (size_t)n);
+    const size_t o_rw = pout.add(nullptr, so->reward, sizeof(float) * nA);
+    const size_t o_cost = pout.add(nullptr, so->cost, sizeof(float) * 2 * (size_t)n);
+    const size_t o_fl = pout.add(nullptr, so->flags, sizeof(uint32_t) * (size_t)n);
+    const size_t o_la = pout.add(nullptr, so->last_action, sizeof(float) * nA);
+    const size_t o_res = pout.add(nullptr, ro ? ro->result : nullptr, sizeof(bmcts_rollout_result) * (size_t)n);
+    const size_t o_ra = pout.add(nullptr, ro ? ro->ret_agents : nullptr, sizeof(float) * nA);
+    const size_t o_fp = pout.add(nullptr, ro ? ro->final_pose : nullptr, sizeof(float) * 4 * nA);
+    if (pin.bytes + pout.bytes <= kPackLimit) {
+      char *di, *dout;
+      if ((st = pack_upload(e, pin, pout, &di, &dout))) return st;
+      auto ip = [&](size_t off) -> const void* { return off == Pack::kNone ? nullptr : di + off; };
+      auto op = [&](size_t off) -> void* { return off == Pack::kNone ? nullptr : dout + off; };
+      a.pose = (const float4*)ip(i_pose);
+      a.alive = (const uint32_t*)ip(i_alive);
+      a.hyp = (const uint8_t*)ip(i_hyp);
+      a.depth = (const uint16_t*)ip(i_depth);
+      a.action = (const uint8_t*)ip(i_action);
+      a.draw_id = (const uint64_t*)ip(i_draw);
+      a.next_pose = (float4*)op(o_np);
+      a.next_alive = (uint32_t*)op(o_na);
+      a.reward = (float*)op(o_rw);
+      a.cost = (float*)op(o_cost);
+      a.flags = (uint32_t*)op(o_fl);
+      a.last_action = (float*)op(o_la);
+      a.result = (bmcts_rollout_result*)op(o_res);
+      a.ret_agents = (float*)op(o_ra);
+      a.final_pose = (float4*)op(o_fp);
+      if ((st = launch(e, a))) return st;
+      return pack_download(e, pout);
+    }
+  }
   const void* d;
   void* o;
-  const size_t nA = (size_t)n * A;
   if ((st = h2d(e, e->b_pose, in->pose, sizeof(float) * 4 * nA, &d))) return st;
   a.pose = (const float4*)d;
   if ((st = h2d(e, e->b_alive, in->alive, sizeof(uint32_t) * (size_t)n, &d))) return st;
