@@ -314,6 +314,8 @@ def run_ours(args):
     # statistics merged with an NCCL all-reduce
     plan = None
     if not args.no_plan:
+        if args.plan_trees <= 0:
+            args.plan_trees = max(1, min(16, (os.cpu_count() or 1) // world))
         g = plan_benchmark(args.workload, args.horizon, args.plan_iterations, args.plan_wave, "gpu",
                            device=local_rank, tree_index=rank, trees=args.plan_trees)
         from planner_mcts_b200 import root_parallel
@@ -442,8 +444,9 @@ def main():
     ap.add_argument("--no-plan", action="store_true", help="skip the Plan() iterations/s arm")
     ap.add_argument("--plan-iterations", type=int, default=32768)
     ap.add_argument("--plan-wave", type=int, default=1024)
-    ap.add_argument("--plan-trees", type=int, default=min(16, os.cpu_count() or 1),
-                    help="root-parallel trees per process (Mcts::NumParallelMcts, one thread each)")
+    ap.add_argument("--plan-trees", type=int, default=0,
+                    help="root-parallel trees per process (Mcts::NumParallelMcts, one host thread "
+                         "each); 0 = host threads / ranks, at most 16")
     ap.add_argument("--cpu-plan-iterations", type=int, default=4000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -15,3 +15,12 @@ for trees, wave in ((1, 1024), (1, 4096), (8, 1024), (8, 4096), (16, 1024)):
     r = bench.plan_benchmark(wl, 20, 32768, wave, "gpu", trees=trees)
     r.pop("root_stats")
     print(f"trees {trees} wave {wave}:", r, flush=True)
+
+# latency of a Plan() at the reference's default budget (2000 iterations, one tree)
+import time  # noqa: E402
+for wave in (64, 256, 1024):
+    r = bench.plan_benchmark(wl, 20, 2000, wave, "gpu", trees=1)
+    r.pop("root_stats")
+    print(f"default budget, wave {wave}: plan {r['plan_ms']:.2f} ms, search {r['search_ms']:.2f} ms", flush=True)
+r = bench.plan_benchmark(wl, 20, 2000, 1, "cpu", trees=1)
+print(f"default budget, CPU oracle sequential: plan {r['plan_ms']:.2f} ms", flush=True)
