@@ -62,6 +62,10 @@ int bmcts_planner_set_param(bmcts_planner* p, const char* key, const double* val
 /* appends one BehaviorHypothesisIDM to the planner's hypothesis set */
 int bmcts_planner_add_hypothesis(bmcts_planner* p, const bmcts_hypothesis* region, int num_samples,
                                  int num_buckets, float buckets_lower, float buckets_upper);
+/* the scenario-risk function of BehaviorUCTRiskConstraint, reduced to what the planner calls
+ * (behavior_uct_risk_constraint.cpp:51-72): ScenarioRiskFunction::CalculateIntegralValue of
+ * every hypothesis region, in hypothesis order (computed with include/bmcts_risk_c.h) */
+int bmcts_planner_set_scenario_risk(bmcts_planner* p, const double* integral_per_hypothesis, int n);
 /* lane corridors, road polygon and goal of `map` are read; the rest is ignored */
 int bmcts_planner_set_map(bmcts_planner* p, const bmcts_scenario* map);
 /* root-parallel tree index of this planner (rank): distinct Philox streams per rank */

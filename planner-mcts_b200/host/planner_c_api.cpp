@@ -15,6 +15,23 @@ int Fail(bmcts_planner* p, int st, const std::string& msg) {
   return st;
 }
 
+// ScenarioRiskFunction given by its value on every hypothesis region
+class TableScenarioRiskFunction : public ScenarioRiskFunction {
+ public:
+  TableScenarioRiskFunction(const std::vector<BehaviorHypothesisIDM>& h, std::vector<double> v)
+      : hyps_(h), values_(std::move(v)) {}
+  double CalculateIntegralValue(const BehaviorHypothesisIDM& hypothesis) const override {
+    for (size_t i = 0; i < hyps_.size() && i < values_.size(); ++i)
+      if (std::memcmp(&hyps_[i].region, &hypothesis.region, sizeof(bmcts_hypothesis)) == 0)
+        return values_[i];
+    return 0.0;
+  }
+
+ private:
+  std::vector<BehaviorHypothesisIDM> hyps_;
+  std::vector<double> values_;
+};
+
 void EnsurePlanner(bmcts_planner* p) {
   if (p->planner) return;
   std::shared_ptr<LeafEvaluator> ev =
@@ -25,7 +42,12 @@ void EnsurePlanner(bmcts_planner* p) {
       p->planner = std::make_shared<BehaviorUCTHypothesis>(p->params, p->hypotheses, ev);
       break;
     case BMCTS_PLANNER_RISK_CONSTRAINT:
-      p->planner = std::make_shared<BehaviorUCTRiskConstraint>(p->params, p->hypotheses, nullptr, ev);
+      p->planner = std::make_shared<BehaviorUCTRiskConstraint>(
+          p->params, p->hypotheses,
+          p->risk_integrals.empty()
+              ? nullptr
+              : std::make_shared<TableScenarioRiskFunction>(p->hypotheses, p->risk_integrals),
+          ev);
       break;
     case BMCTS_PLANNER_COOPERATIVE:
       p->planner = std::make_shared<BehaviorUCTCooperative>(p->params, ev);
@@ -130,6 +152,13 @@ int bmcts_planner_add_hypothesis(bmcts_planner* p, const bmcts_hypothesis* regio
   h.buckets_lower_bound = lower;
   h.buckets_upper_bound = upper;
   p->hypotheses.push_back(h);
+  return BMCTS_OK;
+}
+
+int bmcts_planner_set_scenario_risk(bmcts_planner* p, const double* v, int n) {
+  if (!p || !v || n < 0) return BMCTS_ERR_INVALID_ARG;
+  if (p->planner) return Fail(p, BMCTS_ERR_INVALID_ARG, "the risk function is fixed at construction");
+  p->risk_integrals.assign(v, v + n);
   return BMCTS_OK;
 }
 

@@ -42,7 +42,7 @@ class PlanResult(C.Structure):
 
 PLANNER_SYMBOLS = [
     "bmcts_planner_create", "bmcts_planner_destroy", "bmcts_planner_set_param",
-    "bmcts_planner_add_hypothesis", "bmcts_planner_set_map", "bmcts_planner_set_tree_index",
+    "bmcts_planner_add_hypothesis", "bmcts_planner_set_scenario_risk", "bmcts_planner_set_map", "bmcts_planner_set_tree_index",
     "bmcts_planner_plan", "bmcts_planner_get_beliefs", "bmcts_planner_root_stats",
     "bmcts_planner_decide_from_root_stats", "bmcts_planner_parameter_sampling_probability",
     "bmcts_planner_last_error",
@@ -57,6 +57,7 @@ def declare_planner_api(lib):
     lib.bmcts_planner_set_param.argtypes = [C.c_void_p, C.c_char_p, P(C.c_double), C.c_int]
     lib.bmcts_planner_add_hypothesis.argtypes = [C.c_void_p, P(_abi.Hypothesis), C.c_int, C.c_int,
                                                  C.c_float, C.c_float]
+    lib.bmcts_planner_set_scenario_risk.argtypes = [C.c_void_p, P(C.c_double), C.c_int]
     lib.bmcts_planner_set_map.argtypes = [C.c_void_p, P(_abi.Scenario)]
     lib.bmcts_planner_set_tree_index.argtypes = [C.c_void_p, C.c_uint32]
     lib.bmcts_planner_plan.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint32,
@@ -237,7 +238,23 @@ class BehaviorUCTHypothesis(_BehaviorUCT):
 
 
 class BehaviorUCTRiskConstraint(BehaviorUCTHypothesis):
+    """BehaviorUCTRiskConstraint(params, hypotheses, scenario_risk_function)
+    (behavior_uct_risk_constraint.hpp:56-65); scenario_risk_function is a
+    risk_calculation.ScenarioRiskFunction or None"""
     KIND = PLANNER_RISK_CONSTRAINT
+
+    def __init__(self, params=None, hypotheses=(), scenario_risk_function=None, device=0, _lib=None,
+                 _create=None):
+        super().__init__(params, hypotheses, device, _lib, _create)
+        self.scenario_risk_function = scenario_risk_function
+        if scenario_risk_function is not None:
+            from .risk_calculation import HypothesisRegion
+            dims = list(scenario_risk_function.risk_function_definition.GetSupportingRegion()
+                        .GetDefinition())
+            vals = [scenario_risk_function.CalculateIntegralValue(HypothesisRegion(h.region, dims))
+                    for h in self.hypotheses]
+            arr = (C.c_double * len(vals))(*vals)
+            self._check(self._lib.bmcts_planner_set_scenario_risk(self._h, arr, len(vals)))
 
     @property
     def last_cost_values(self):

@@ -36,8 +36,15 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libbmcts.so does not export {name}"
     assert sorted(planner.PLANNER_SYMBOLS) == sorted(declared)
-    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["bmcts_c.h", "bmcts_math.h",
-                                                                 "bmcts_planner_c.h"]
+    # the scenario-risk tooling ABI (include/bmcts_risk_c.h)
+    from planner_mcts_b200 import risk_calculation
+    declared = [f for f in _declared_functions("bmcts_risk_c.h") if f.startswith("bmcts_risk_")
+                and not f.endswith("_fn")]
+    for name in declared:
+        assert hasattr(lib, name), f"libbmcts.so does not export {name}"
+    assert sorted(risk_calculation.RISK_SYMBOLS) == sorted(declared)
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == [
+        "bmcts_c.h", "bmcts_math.h", "bmcts_planner_c.h", "bmcts_risk_c.h"]
 
 
 def test_struct_sizes_match_header():
