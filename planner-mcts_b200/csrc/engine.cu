@@ -308,18 +308,24 @@ int pipeline_chunk(int n) {
 
 // chunk size of the streamed upload (0 = off)
 int stream_chunk(int n) {
-  long chunk = 65536;
-  if (const char* s = std::getenv("BMCTS_STREAM_CHUNK")) chunk = std::atol(s);
-  if (chunk <= 0 || n < 4 * chunk) return 0;
-  return (int)((chunk + 31) & ~31L);
+  if (const char* s = std::getenv("BMCTS_STREAM_CHUNK")) {
+    const long chunk = std::atol(s);
+    if (chunk <= 0 || n < 4 * chunk) return 0;
+    return (int)((chunk + 31) & ~31L);
+  }
+  if (n < 32768) return 0;  // small batches: one packed upload, kernel, one packed download
+  long chunk = ((long)n / 8 + 31) & ~31L;  // about eight chunks, 8 Ki .. 64 Ki rollouts each
+  if (chunk < 8192) chunk = 8192;
+  if (chunk > 65536) chunk = 65536;
+  return (int)chunk;
 }
 
 // Large host-memory rollout batch, streamed: ONE persistent kernel over the whole batch is
 // launched as soon as the first chunk of the leaf arrays is on its way; the remaining chunks
 // are uploaded by the copy engine while the kernel runs, each followed by a 4-byte counter
 // update, and a lane group only starts rollout k once the chunk holding k has arrived
-// (wait_chunk in rollout_device.cuh).  Row-wise 1-D copies keep the upload on the DMA engines:
-// nothing the spinning kernel could starve.  Results are downloaded after the kernel.
+// (wait_chunk in rollout_device.cuh; its spin is bounded, so a stalled upload ends in an error,
+// not a hang).  Results are downloaded after the kernel.
 int rollout_host_streamed(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts_rollout_out* out,
                           const bmcts::KernelArgs& base) {
   const int n = in->n_leaves, A = e->scn.n_agents;
@@ -372,13 +378,12 @@ int rollout_host_streamed(bmcts_engine* e, const bmcts_leaf_batch* in, const bmc
   for (int c = 0; c < n_chunks; ++c) {
     const size_t k0 = (size_t)c * chunk;
     const size_t m = (n - k0 < (size_t)chunk) ? n - k0 : (size_t)chunk;
-    for (int ag = 0; ag < A; ++ag) {
-      const size_t row = (size_t)ag * n + k0;
-      CU(cudaMemcpyAsync((char*)e->b_pose.ptr + row * 16, in->pose + row * 4, m * 16,
-                         cudaMemcpyHostToDevice, cs));
-      if (in->hyp_id)
-        CU(cudaMemcpyAsync((char*)e->b_hyp.ptr + row, in->hyp_id + row, m, cudaMemcpyHostToDevice, cs));
-    }
+    // one strided (2-D) copy per array and chunk: A rows of m elements, row pitch n elements
+    CU(cudaMemcpy2DAsync((char*)e->b_pose.ptr + k0 * 16, (size_t)n * 16, in->pose + k0 * 4,
+                         (size_t)n * 16, m * 16, A, cudaMemcpyHostToDevice, cs));
+    if (in->hyp_id)
+      CU(cudaMemcpy2DAsync((char*)e->b_hyp.ptr + k0, (size_t)n, in->hyp_id + k0, (size_t)n, m, A,
+                           cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync((char*)e->b_alive.ptr + k0 * 4, in->alive + k0, m * 4, cudaMemcpyHostToDevice,
                        cs));
     if (in->depth)
