@@ -443,7 +443,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-plan", action="store_true", help="skip the Plan() iterations/s arm")
     ap.add_argument("--plan-iterations", type=int, default=32768)
-    ap.add_argument("--plan-wave", type=int, default=1024)
+    ap.add_argument("--plan-wave", type=int, default=0,
+                    help="iterations per engine batch; 0 = the planner's default (iterations / 128, "
+                         "at most 256), which keeps root values within Monte-Carlo noise of the "
+                         "sequential search")
     ap.add_argument("--plan-trees", type=int, default=0,
                     help="root-parallel trees per process (Mcts::NumParallelMcts, one host thread "
                          "each); 0 = host threads / ranks, at most 16")

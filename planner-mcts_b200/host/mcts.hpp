@@ -130,7 +130,9 @@ class Mcts {
     t_select_ = t_fill_ = t_engine_ = t_backup_ = 0.0;
     iterations_ = 0;
     max_tree_depth_ = 0;
-    const long wave = std::max<long>(1, p_.WAVE_SIZE);
+    const long wave = p_.WAVE_SIZE > 0
+                          ? p_.WAVE_SIZE
+                          : std::min<long>(256, std::max<long>(1, p_.MAX_NUMBER_OF_ITERATIONS / 128));
     while (iterations_ < p_.MAX_NUMBER_OF_ITERATIONS) {
       const double ms = std::chrono::duration<double, std::milli>(clock::now() - t0).count();
       if (iterations_ > 0 && ms > (double)p_.MAX_SEARCH_TIME) break;

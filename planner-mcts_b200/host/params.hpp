@@ -89,7 +89,7 @@ struct MctsParameters {
   } cost_constrained_statistic;
   // engine-side knob (not a reference key): leaves evaluated per GPU launch.  1 = the
   // reference's strictly sequential search.
-  long WAVE_SIZE = 256;
+  long WAVE_SIZE = 0;  // 0 = automatic: MaxNumIterations / 128, between 1 and 256
 };
 
 // param_config/mcts_parameters_from_param_server.hpp:30-110 (keys relative to `prefix`)
@@ -166,7 +166,11 @@ inline MctsParameters MctsParametersFromParamServer(const Params& p, const std::
   c.COST_THRESHOLDS = p.GetListFloat(k("Mcts::CostConstrainedStatistic::CostThresholds"), {0.1, 0.0});
   c.USE_LAMBDA_POLICY = p.GetBool(k("Mcts::CostConstrainedStatistic::UseLambdaPolicy"), true);
   c.MAX_SOLVER_TIME = p.GetInt(k("Mcts::CostConstrainedStatistic::MaxSolverTime"), -1);
-  m.WAVE_SIZE = p.GetInt(k("Mcts::Engine::WaveSize"), 256);
+  // iterations selected per engine batch.  Root values are means under the tree policy, and a
+  // wave selects without seeing the results of its own earlier selections: waves that are
+  // small against the iteration budget (<= 1 %) reproduce the sequential search's root values
+  // within Monte-Carlo noise (tests/test_planner.py), larger ones trade bias for throughput.
+  m.WAVE_SIZE = p.GetInt(k("Mcts::Engine::WaveSize"), 0);
   return m;
 }
 

@@ -189,3 +189,36 @@ def test_rollouts_are_reproducible_and_schedule_independent():
     b1 = eng.rollout(pose[:, 32:], alive[32:], hyp[:, 32:], first_rollout_id=132)["result"]
     b0 = eng.rollout(pose[:, :32], alive[:32], hyp[:, :32], first_rollout_id=100)["result"]
     assert np.array_equal(a, np.concatenate([b0, b1]))
+
+
+def test_error_codes_instead_of_aborts():
+    """the reference aborts (LOG(FATAL), mcts_state_hypothesis.cpp:65,130); the C ABI returns
+    status codes and keeps the engine usable"""
+    import ctypes as C
+    from planner_mcts_b200 import BmctsError
+    cfg, scn, meta = scenarios.workload("c2_merge_sbg", horizon=5)
+    lib = _abi.load_library()
+    # an engine without a scenario
+    h = C.c_void_p()
+    assert lib.bmcts_create(0, C.byref(cfg), C.byref(h)) == _abi.OK
+    inb = _abi.LeafBatch(1, _abi.MEM_HOST, None, None, None, None, 0, 0, 0, 0)
+    out = _abi.RolloutOut(None, None, None)
+    assert lib.bmcts_rollout_batch(h, C.byref(inb), C.byref(out)) == _abi.ERR_NO_SCENARIO
+    unfinal = _abi.Scenario.from_buffer_copy(scn)
+    unfinal.finalized = 0
+    assert lib.bmcts_set_scenario(h, C.byref(unfinal)) == _abi.ERR_INVALID_ARG
+    assert lib.bmcts_create(99, C.byref(cfg), C.byref(C.c_void_p())) == _abi.ERR_INVALID_ARG
+    lib.bmcts_destroy(h)
+    # null arguments / missing hypothesis ids on a ready engine, which stays usable afterwards
+    eng = RolloutEngine(cfg, scn)
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, 4, seed=1)
+    res = np.zeros(4, dtype=np.dtype([("b", np.uint8, 32)]))
+    with pytest.raises(BmctsError) as ei:
+        eng.rollout_raw(4, _abi.MEM_HOST, pose, alive, None, None, res)   # hyp_id required
+    assert ei.value.status == _abi.ERR_INVALID_ARG
+    with pytest.raises(BmctsError):
+        eng.rollout_raw(4, _abi.MEM_HOST, None, alive, hyp, None, res)
+    g = eng.rollout(pose, alive, hyp)
+    c = oracle.rollout(cfg, scn, pose, alive, hyp)
+    parity.assert_results_match(g, c)
+    assert lib.bmcts_status_string(_abi.ERR_NO_DEVICE).decode().startswith("no CUDA device")
