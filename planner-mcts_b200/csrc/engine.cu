@@ -219,7 +219,7 @@ int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream
   int T = 0, W = 0;
   if (const char* s = std::getenv("BMCTS_LANE_T")) T = std::atoi(s);
   if (const char* s = std::getenv("BMCTS_LANE_W")) W = std::atoi(s);
-  if (T != 1 && T != 2 && T != 4) {
+  if (T != 1 && T != 2 && T != 4 && T != 8 && T != 16) {
     const size_t budget = 11 * 1024 + 512;
     auto warp_bytes = [&](int t) {
       return COOP ? bmcts::lane_coop_layout(a.A, a.C, t, 1).warp_bytes
@@ -228,11 +228,15 @@ int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream
     T = 1;
     if (warp_bytes(1) > budget) T = 2;
     if (warp_bytes(2) > budget) T = 4;
+    // a batch too small to fill the GPU (an MCTS wave) is latency bound: more lanes per
+    // rollout shorten the serial chain of a step (up to one agent per lane)
     const long lanes_resident = (long)e->sm_count * 32 * 16;
-    if (T < 2 && (long)a.n * 2 <= lanes_resident && a.A >= 3) T = 2;
-    if (T < 4 && (long)a.n * 4 <= lanes_resident && a.A >= 5) T = 4;
+    for (int t = 2; t <= 16; t *= 2)
+      if (T < t && (long)a.n * t <= lanes_resident && a.A > t / 2) T = t;
   }
   switch (T) {
+    case 16: return launch_lane_T<16, COOP>(e, a, W, stream, counter);
+    case 8: return launch_lane_T<8, COOP>(e, a, W, stream, counter);
     case 4: return launch_lane_T<4, COOP>(e, a, W, stream, counter);
     case 2: return launch_lane_T<2, COOP>(e, a, W, stream, counter);
     default: return launch_lane_T<1, COOP>(e, a, W, stream, counter);

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 WORKLOADS = ["c1_highway_mdp", "c2_merge_sbg", "c3_merge_risk", "c4_coop", "c5_rsbg"]
 
 
-@pytest.fixture(params=["auto", "1", "2", "4"], autouse=True)
+@pytest.fixture(params=["auto", "1", "2", "4", "8", "16"], autouse=True)
 def lanes_per_rollout(request, monkeypatch):
     """every test runs with the engine's own choice of lanes per rollout and with each
     forced value (BMCTS_LANE_T is read at every launch)"""

@@ -18,7 +18,7 @@ for trees, wave in ((1, 1024), (1, 4096), (8, 1024), (8, 4096), (16, 1024)):
 
 # latency of a Plan() at the reference's default budget (2000 iterations, one tree)
 import time  # noqa: E402
-for wave in (64, 256, 1024):
+for wave in (0, 64, 256, 1024):
     r = bench.plan_benchmark(wl, 20, 2000, wave, "gpu", trees=1)
     r.pop("root_stats")
     print(f"default budget, wave {wave}: plan {r['plan_ms']:.2f} ms, search {r['search_ms']:.2f} ms", flush=True)
