@@ -312,6 +312,12 @@ int pipeline_chunk(int n) {
 
 // chunk size of the streamed upload (0 = off)
 int stream_chunk(int n) {
+  // a kernel that waits for concurrent copies cannot run under a profiler that serialises
+  // GPU work (ncu replays kernels in isolation): fall back to the chunked multi-kernel path
+  static const bool profiled = std::getenv("CUDA_INJECTION64_PATH") != nullptr ||
+                               std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+                               std::getenv("NVTX_INJECTION64_PATH") != nullptr;
+  if (profiled && !std::getenv("BMCTS_STREAM_CHUNK")) return 0;
   if (const char* s = std::getenv("BMCTS_STREAM_CHUNK")) {
     const long chunk = std::atol(s);
     if (chunk <= 0 || n < 4 * chunk) return 0;

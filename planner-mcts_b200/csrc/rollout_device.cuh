@@ -83,16 +83,23 @@ __device__ __forceinline__ uint4 draw(uint32_t k0, uint32_t k1, uint64_t id, uin
 }
 
 // wait until the chunk that holds rollout `rid` has arrived (acquire load at system scope:
-// the data is written by the copy engine, then the counter).  Gives up after a few seconds
-// instead of hanging the GPU if the upload stalled.
+// the data is written by the copy engine, then the counter).  Gives up after two seconds
+// instead of hanging the GPU if the upload stalled (e.g. a tool that serialises GPU work).
 __device__ __forceinline__ bool wait_chunk(const KernelArgs& p, uint32_t rid) {
   if (!p.ready) return true;
   const unsigned int need = rid / p.chunk + 1u;
-  for (unsigned int spins = 0; spins < 30000000u; ++spins) {
+  unsigned long long t0 = 0;
+  for (unsigned int spins = 0;; ++spins) {
     unsigned int have;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(p.ready) : "memory");
     if (have >= need) return true;
     __nanosleep(100);
+    if ((spins & 1023u) == 0u) {  // wall-clock bound: 2 s without the chunk = the upload stalled
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 2000000000ull) break;
+    }
   }
   atomicExch(p.ready + 1, 1u);
   return false;
