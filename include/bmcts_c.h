@@ -250,8 +250,9 @@ typedef struct bmcts_rollout_result {
  * contiguous array per agent slot indexed by the leaf / rollout number:
  *     pose[(a*n + k)*4 + f], hyp_id[a*n + k], action[a*n + k], draw_id[a*n + k],
  *     ret_agents[a*n + k], reward[a*n + k], last_action[a*n + k], cost[c*n + k]
- * so that the 32 lanes of the warp that owns agent slot a (one lane per rollout)
- * read and write 32 consecutive records: 512-byte coalesced float4 accesses.
+ * so that lanes holding consecutive rollouts read the records of one agent slot from
+ * consecutive addresses (16-byte float4 poses), and so that a chunk of rollouts [k0, k1) of a
+ * host batch is one strided 2-D copy per array.
  */
 
 /* A batch of leaf states for the default-policy rollout.
