@@ -169,26 +169,33 @@ BM_HD float bm_atan(float x) {
   return (x < 0.0f) ? -r : r;
 }
 
-/* atan2(y, x) in (-pi, pi] */
+/* atan2(y, x) in (-pi, pi], ~2 ulp.  The octant reduction of bm_atan is applied to the pair
+ * (|y|, |x|) directly, so there is exactly ONE division whatever the range (a reduction on the
+ * rounded quotient needs a second one for steep angles, which diverges badly on the GPU):
+ *   |y| <= tan(pi/8) |x|   : t =  |y| / |x|,              y0 = 0
+ *   |y| <= tan(3pi/8) |x|  : t = (|y| - |x|) / (|y| + |x|), y0 = pi/4
+ *   otherwise              : t = -|x| / |y|,              y0 = pi/2
+ * A zero numerator (an agent exactly on its lane centre line, or |y| == |x|) skips the
+ * division: the device's IEEE division would take its slow path for it. */
 BM_HD float bm_atan2(float y, float x) {
   if (x == 0.0f) {
     if (y > 0.0f) return BM_PIO2_HI;
     if (y < 0.0f) return -BM_PIO2_HI;
     return 0.0f;
   }
-  /* y == 0 (an agent exactly on its lane centre line) would send the device's IEEE division
-   * through its slow path; 0 / x is a zero with the XOR of the signs, spelled out instead */
-  float q;
-  if (y == 0.0f) {
-    union { float f; uint32_t u; } uy, ux, uq;
-    uy.f = y;
-    ux.f = x;
-    uq.u = (uy.u ^ ux.u) & 0x80000000u;
-    q = uq.f;
-  } else {
-    q = bm_div(y, x);
-  }
-  float a = bm_atan(q);
+  const float ay = bm_abs(y), ax = bm_abs(x);
+  const int big = ay > 2.414213562373095f * ax;
+  const int mid = ay > 0.4142135623730950f * ax;
+  const float num = big ? -ax : (mid ? ay - ax : ay);
+  const float den = big ? ay : (mid ? ay + ax : ax);
+  const float y0 = big ? BM_PIO2_HI : (mid ? BM_PIO4 : 0.0f);
+  const float t = (num == 0.0f) ? 0.0f : bm_div(num, den);
+  const float z = t * t;
+  float p = bm_fma(8.05374449538e-2f, z, -1.38776856032e-1f);
+  p = bm_fma(p, z, 1.99777106478e-1f);
+  p = bm_fma(p, z, -3.33329491539e-1f);
+  const float r = y0 + bm_fma(p * z, t, t); /* atan(|y| / |x|) in [0, pi/2] */
+  float a = ((y < 0.0f) != (x < 0.0f)) ? -r : r;
   if (x < 0.0f) a = (y >= 0.0f) ? (a + BM_PI_F) : (a - BM_PI_F);
   return a;
 }
