@@ -669,8 +669,10 @@ int bmcts_set_scenario(bmcts_engine* e, const bmcts_scenario* scn) {
   // inner rectangles: recomputed only when the road polygon changes (a planner sets the same
   // map at every Plan())
   const bool same_road = e->has_scenario && e->scn.n_road_pts == scn->n_road_pts &&
+                         e->scn.n_corridors == scn->n_corridors &&
                          std::memcmp(e->scn.road_x, scn->road_x, sizeof(scn->road_x)) == 0 &&
-                         std::memcmp(e->scn.road_y, scn->road_y, sizeof(scn->road_y)) == 0;
+                         std::memcmp(e->scn.road_y, scn->road_y, sizeof(scn->road_y)) == 0 &&
+                         std::memcmp(e->scn.corridors, scn->corridors, sizeof(scn->corridors)) == 0;
   e->scn = *scn;
   if (!same_road) e->rects = bmcts::find_inner_rects(e->scn);
   bmcts::InnerRects up = e->rects;
@@ -678,7 +680,14 @@ int bmcts_set_scenario(bmcts_engine* e, const bmcts_scenario* scn) {
     for (int r = 0; r < up.n; ++r)
       std::fprintf(stderr, "[bmcts] inner rect %d: x [%g, %g] y [%g, %g]\n", r, up.rect[r][0],
                    up.rect[r][1], up.rect[r][2], up.rect[r][3]);
-  if (std::getenv("BMCTS_NO_RECTS")) up.n = 0;  // tests: the scan-only path
+  if (std::getenv("BMCTS_NO_RECTS")) {  // tests: the scan-only path
+    up.n = 0;
+    for (int c = 0; c < BMCTS_MAX_CORRIDORS; ++c)
+      for (int k = 0; k < BMCTS_MAX_CORRIDOR_PTS; ++k) {
+        up.arc_lo[c][k] = 1.0e30f;
+        up.arc_hi[c][k] = -1.0e30f;
+      }
+  }
   for (int r = up.n; r < 2; ++r) {  // unused rectangles are empty
     up.rect[r][0] = up.rect[r][2] = 1.0e30f;
     up.rect[r][1] = up.rect[r][3] = -1.0e30f;

@@ -59,10 +59,73 @@ double overlap(const Rect& a, const Rect& b) {
   return (w > 0.0 && h > 0.0) ? w * h : 0.0;
 }
 
+// distance from a point to the polygon boundary
+double boundary_distance(const Poly& p, double px, double py) {
+  double best = 1.0e300;
+  const size_t n = p.x.size();
+  for (size_t i = 0, j = n - 1; i < n; j = i++) {
+    const double ex = p.x[i] - p.x[j], ey = p.y[i] - p.y[j];
+    const double l2 = ex * ex + ey * ey;
+    double u = l2 > 0.0 ? ((px - p.x[j]) * ex + (py - p.y[j]) * ey) / l2 : 0.0;
+    u = std::min(1.0, std::max(0.0, u));
+    const double dx = px - (p.x[j] + u * ex), dy = py - (p.y[j] + u * ey);
+    best = std::min(best, std::sqrt(dx * dx + dy * dy));
+  }
+  return best;
+}
+
+// safe arc intervals of the lane centre lines (see InnerRects::arc_lo)
+void find_safe_arcs(const bmcts_scenario& scn, const Poly& p, double margin, InnerRects* out) {
+  for (int c = 0; c < BMCTS_MAX_CORRIDORS; ++c)
+    for (int k = 0; k < BMCTS_MAX_CORRIDOR_PTS; ++k) {
+      out->arc_lo[c][k] = 1.0e30f;
+      out->arc_hi[c][k] = -1.0e30f;
+    }
+  for (int c = 0; c < scn.n_corridors; ++c) {
+    const bmcts_corridor& cor = scn.corridors[c];
+    for (int k = 0; k + 1 < cor.n_pts; ++k) {
+      const double len = cor.seg_len[k];
+      const int steps = (int)std::min(4000.0, std::max(8.0, std::ceil(len / 0.05)));
+      const double h = len / steps;
+      // the distance to the boundary is 1-Lipschitz along the segment: samples that keep
+      // margin + h guarantee the margin in between
+      int best_a = 0, best_b = -1, run_a = 0;
+      bool in_run = false;
+      for (int i = 0; i <= steps + 1; ++i) {
+        bool ok = false;
+        if (i <= steps) {
+          const double u = h * i;
+          const double x = cor.px[k] + u * cor.tx[k], y = cor.py[k] + u * cor.ty[k];
+          ok = inside(p, x, y) && boundary_distance(p, x, y) >= margin + h;
+        }
+        if (ok && !in_run) {
+          in_run = true;
+          run_a = i;
+        } else if (!ok && in_run) {
+          in_run = false;
+          if (i - 1 - run_a > best_b - best_a) {
+            best_a = run_a;
+            best_b = i - 1;
+          }
+        }
+      }
+      if (best_b >= best_a) {
+        out->arc_lo[c][k] = std::nextafter((float)(h * best_a), 3.0e38f);
+        out->arc_hi[c][k] = std::nextafter((float)(h * best_b), -3.0e38f);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 InnerRects find_inner_rects(const bmcts_scenario& scn) {
   InnerRects out{};
+  for (int c = 0; c < BMCTS_MAX_CORRIDORS; ++c)
+    for (int k = 0; k < BMCTS_MAX_CORRIDOR_PTS; ++k) {
+      out.arc_lo[c][k] = 1.0e30f;
+      out.arc_hi[c][k] = -1.0e30f;
+    }
   const int n = scn.n_road_pts;
   if (n < 3) return out;
   Poly p;
@@ -72,6 +135,7 @@ InnerRects find_inner_rects(const bmcts_scenario& scn) {
     p.y.push_back(scn.road_y[i]);
     maxabs = std::max({maxabs, std::fabs(p.x[i]), std::fabs(p.y[i])});
   }
+  find_safe_arcs(scn, p, 0.02 + 1.0e-5 * maxabs, &out);
   std::vector<double> xs = p.x, ys = p.y;
   std::sort(xs.begin(), xs.end());
   xs.erase(std::unique(xs.begin(), xs.end()), xs.end());

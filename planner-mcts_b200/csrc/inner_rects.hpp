@@ -16,6 +16,11 @@ struct InnerRects {
   float rect[2][4];  // x0, x1, y0, y1
   int n;
   int pad_[3];
+  // per lane-corridor segment: the interval [lo, hi] of local arc length on which the centre
+  // line point keeps the margin to the road boundary (lo > hi: none).  An IDM agent, which
+  // sits exactly on its centre line, needs no scan inside it.
+  float arc_lo[BMCTS_MAX_CORRIDORS][BMCTS_MAX_CORRIDOR_PTS];
+  float arc_hi[BMCTS_MAX_CORRIDORS][BMCTS_MAX_CORRIDOR_PTS];
 };
 
 InnerRects find_inner_rects(const bmcts_scenario& scn);

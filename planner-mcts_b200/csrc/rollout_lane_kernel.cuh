@@ -60,7 +60,9 @@ __host__ __device__ inline LaneLayout lane_layout(int A, int C, int H, int T, in
   l.off_hflags = b;
   b += smem_align16(sizeof(uint32_t) * 4 * (size_t)(H > 0 ? H : 1));  // flags, 1/v0, 1/(2 sqrt(ab))
   l.off_rad = b;  // per agent: plain / static-inflated bounding radius; then the goal's AABB
-  b += smem_align16(sizeof(float) * (2 * BMCTS_MAX_AGENTS + 4 + 8));  // + goal AABB + 2 inner rects
+  // + goal AABB + 2 inner rects + safe arc intervals [lo | hi][corridor][segment]
+  b += smem_align16(sizeof(float) * (2 * BMCTS_MAX_AGENTS + 4 + 8 +
+                                     2 * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS));
   l.off_state = b;
   l.warp_bytes = sizeof(float) * (size_t)(L_PROJ + C) * A * (32 / T);
   l.total = b + l.warp_bytes * warps;
@@ -116,6 +118,13 @@ __device__ __forceinline__ void stage_reach(const bmcts_scenario* scn, const bmc
     // inner rectangles of the road polygon (engine.cu stores them behind the scenario)
     const float* rc = reinterpret_cast<const float*>(scn + 1);
     for (int i = 0; i < 8; ++i) bb[4 + i] = rc[i];
+  }
+  // safe arc intervals of the centre lines (behind the rectangles: 8 floats + n + 3 pad words)
+  {
+    const float* arcs = reinterpret_cast<const float*>(scn + 1) + 12;
+    float* dst = rad + 2 * BMCTS_MAX_AGENTS + 12;
+    for (int i = tid; i < 2 * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS; i += nthreads)
+      dst[i] = arcs[i];
   }
 }
 
@@ -233,6 +242,8 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
   const float* reach = reinterpret_cast<const float*>(smem_raw + lay.off_rad);
   const float* goal_bb = reach + 2 * BMCTS_MAX_AGENTS;
   const float* rects = goal_bb + 4;
+  const float* arc_lo = rects + 8;
+  const float* arc_hi = arc_lo + BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = lane % T;  // lane inside the group
@@ -451,6 +462,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         const bool was_alive = (pre >> a) & 1u;
         float x, y, th, v;
         int word = 0;
+        bool on_safe_arc = false;  // centre-line point with a margin to the road boundary
         if (fresh) {
           const float4 q = p.pose[gi];
           x = q.x;
@@ -485,6 +497,8 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
           y = bm_fma(ls, corr.ty[sg], corr.py[sg]);
           th = corr.angle[sg];
           v = ca[L_NV * fstride];
+          on_safe_arc = ls >= arc_lo[cur * BMCTS_MAX_CORRIDOR_PTS + sg] &&
+                        ls <= arc_hi[cur * BMCTS_MAX_CORRIDOR_PTS + sg];
           word = (word & ~0xff) | (cur << 4);  // bits 4-7: the corridor the pose was built on
         }
         if (!was_alive) continue;
@@ -494,9 +508,10 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
             if (p.reward && a > 0) p.reward[gi] = 0.0f;
           }
           if (want_final) p.final_pose[gi] = make_float4(x, y, th, v);
-          // World::RemoveInvalidAgents; a point inside an inner rectangle of the road polygon
-          // needs no scan
-          if (!in_rects(rects, x, y) && !point_in_polygon(scn.road_x, scn.road_y, n_road, x, y)) {
+          // World::RemoveInvalidAgents; a centre-line point on a safe arc or a point inside an
+          // inner rectangle of the road polygon needs no scan
+          if (!on_safe_arc && !in_rects(rects, x, y) &&
+              !point_in_polygon(scn.road_x, scn.road_y, n_road, x, y)) {
             dead |= 1u << a;
             continue;
           }
