@@ -1,0 +1,25 @@
+"""The C++ planner classes (planner-mcts_b200/host/behavior_uct.hpp) used directly, the way
+the reference's C++ tests use theirs: tests/cpp/test_cpp_api.cpp built against the oracle-backed
+planner library."""
+import os
+import subprocess
+
+import oracle
+
+
+def test_cpp_planner_api():
+    oracle.build()
+    exe = os.path.join(oracle.ORACLE_DIR, "_build", "test_cpp_api")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.strip().endswith("ok")
+
+
+def test_example_script_runs_on_the_cpu_backend():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "examples", "plan_merge.py"),
+                          "--backend", "cpu", "--iterations", "200", "--steps", "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("macro action") == 2
