@@ -16,6 +16,7 @@
 #include <memory>
 #include <random>
 #include <stdexcept>
+#include <unordered_map>
 #include <vector>
 
 #include "evaluator.hpp"
@@ -75,10 +76,22 @@ struct JointKey {
   }
   ActionKey& operator[](int i) { return k[i]; }
   const ActionKey& operator[](int i) const { return k[i]; }
-  bool operator<(const JointKey& o) const {
+  bool operator==(const JointKey& o) const {
+    if (n != o.n) return false;
     for (int i = 0; i < n; ++i)
-      if (k[i] != o.k[i]) return k[i] < o.k[i];
-    return false;
+      if (k[i] != o.k[i]) return false;
+    return true;
+  }
+};
+
+struct JointKeyHash {
+  size_t operator()(const JointKey& j) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < j.n; ++i) {
+      h ^= j.k[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+      h *= 0xFF51AFD7ED558CCDull;
+    }
+    return (size_t)(h ^ (h >> 32));
   }
 };
 
@@ -98,7 +111,7 @@ struct Node {
   // cost (hypothesis states: the same for every agent) / the agent's own return (cooperative)
   double latest_cost_other = 0.0;
   std::vector<double> latest_ret_other;
-  std::map<JointKey, Node*> children;
+  std::unordered_map<JointKey, Node*, JointKeyHash> children;
   std::vector<double> edge_reward;  // rewards[] of the execute() that created this node
   double edge_cost[2] = {0.0, 0.0};
 };
