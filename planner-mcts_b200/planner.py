@@ -104,6 +104,18 @@ class HypothesisIDM:
     buckets_lower_bound: float = -10.0
     buckets_upper_bound: float = 10.0
 
+    # pickling (python_wrapper/python_planner_uct.cpp:206-248 pickles hypotheses with their
+    # parameters): the ctypes region travels as its raw bytes
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["region"] = bytes(self.region)
+        return d
+
+    def __setstate__(self, d):
+        d = dict(d)
+        d["region"] = _abi.Hypothesis.from_buffer_copy(d["region"])
+        self.__dict__.update(d)
+
 
 class _BehaviorUCT:
     KIND = PLANNER_HYPOTHESIS
@@ -143,7 +155,26 @@ class _BehaviorUCT:
             pass
 
     def set_tree_index(self, i):
+        self._tree_index = int(i)
         self._check(self._lib.bmcts_planner_set_tree_index(self._h, int(i)))
+
+    # pickling / deepcopy: parameters + hypotheses (+ risk function) are kept, the native
+    # planner is rebuilt; beliefs and debug infos of the last Plan() are not carried over
+    # (the reference does not pickle its belief tracker either, python_planner_uct.cpp:145-166)
+    def __getstate__(self):
+        return {"params": self.params, "hypotheses": self.hypotheses,
+                "tree_index": getattr(self, "_tree_index", 0),
+                "scenario_risk_function": getattr(self, "scenario_risk_function", None)}
+
+    def __setstate__(self, st):
+        if isinstance(self, BehaviorUCTCooperative):
+            self.__init__(st["params"])
+        elif isinstance(self, BehaviorUCTRiskConstraint):
+            self.__init__(st["params"], st["hypotheses"], st["scenario_risk_function"])
+        else:
+            self.__init__(st["params"], st["hypotheses"])
+        if st["tree_index"]:
+            self.set_tree_index(st["tree_index"])
 
     def Plan(self, delta_time, observed_world):
         """Plan(min_planning_time, observed_world) -> trajectory ndarray [n, 5] = [t,x,y,theta,v]"""

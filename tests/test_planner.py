@@ -242,3 +242,22 @@ def test_wave_batched_search_agrees_with_sequential_search_within_monte_carlo_ci
     # acceleration inputs (0, 1, 4, -1, -8): full braking is chosen whatever the wave size
     for wave in best:
         assert set(best[wave]) == {4}, (wave, best[wave])
+
+
+def test_planners_survive_pickle_and_deepcopy():
+    """python_wrapper/tests/pickle_unpickle_test.py:24-110: planners and hypotheses keep their
+    parameters through pickle and deepcopy (the native planner is rebuilt)"""
+    import copy
+    import pickle
+    params = W.base_params(123)
+    hyps = W.hypotheses(num_samples=777)
+    for pl in (P.BehaviorUCTHypothesis(params, hyps), P.BehaviorUCTRiskConstraint(params, hyps),
+               P.BehaviorUCTCooperative(params)):
+        for clone in (pickle.loads(pickle.dumps(pl)), copy.deepcopy(pl)):
+            assert type(clone) is type(pl)
+            assert clone.params == pl.params
+            assert len(clone.hypotheses) == len(pl.hypotheses)
+            for a, b in zip(clone.hypotheses, pl.hypotheses):
+                assert bytes(a.region) == bytes(b.region) and a.num_samples == b.num_samples == 777
+    h = pickle.loads(pickle.dumps(hyps[1]))
+    assert list(h.region.lo)[:1] == [1.5] and list(h.region.hi)[:1] == [3.0]
