@@ -362,6 +362,18 @@ int bmcts_expand_rollout_batch(bmcts_engine* e, const bmcts_step_in* in,
  * prob[(a*H + h)*n_worlds + w] */
 int bmcts_likelihood_batch(bmcts_engine* e, const bmcts_likelihood_in* in, float* prob);
 
+/* ---- self test ---------------------------------------------------------- */
+/* Evaluates one elementary function of include/bmcts_math.h on the device for n host inputs:
+ * out[i] = f(a[i], b[i]).  The flags of the path are threshold tests on FP32 geometry, so the
+ * device and the CPU restatement must agree on these functions bit for bit, special values
+ * included (tests/test_parity_gpu.py compares with the same header compiled by gcc). */
+enum {
+  BMCTS_MATH_SIN = 0, BMCTS_MATH_COS, BMCTS_MATH_ATAN2, BMCTS_MATH_TAN_SMALL, BMCTS_MATH_DIV,
+  BMCTS_MATH_SQRT, BMCTS_MATH_MIN, BMCTS_MATH_MAX, BMCTS_MATH_NORM_ANGLE, BMCTS_MATH_FMA_AAB,
+  BMCTS_MATH_POW4, BMCTS_MATH_NUM_OPS
+};
+int bmcts_math_probe(bmcts_engine* e, int op, const float* a, const float* b, int n, float* out);
+
 /* all batch calls are stream-ordered and asynchronous for BMCTS_MEM_DEVICE; with
  * BMCTS_MEM_HOST they return after the results are in the caller's buffers. */
 int bmcts_sync(bmcts_engine* e);

@@ -63,6 +63,27 @@ static void draw(uint64_t seed, uint32_t stream, uint64_t id, uint32_t agent, ui
   oracle_philox4x32_10(ctr, key, out);
 }
 
+void oracle_math_probe(int op, const float* a, const float* b, int n, float* out) {
+  for (int i = 0; i < n; ++i) {
+    float x = a[i], y = b[i], s, c, r = 0.0f;
+    switch (op) {
+      case BMCTS_MATH_SIN: bm_sincos(x, &s, &c); r = s; break;
+      case BMCTS_MATH_COS: bm_sincos(x, &s, &c); r = c; break;
+      case BMCTS_MATH_ATAN2: r = bm_atan2(x, y); break;
+      case BMCTS_MATH_TAN_SMALL: r = bm_tan_small(x); break;
+      case BMCTS_MATH_DIV: r = bm_div(x, y); break;
+      case BMCTS_MATH_SQRT: r = bm_sqrt(x); break;
+      case BMCTS_MATH_MIN: r = bm_min(x, y); break;
+      case BMCTS_MATH_MAX: r = bm_max(x, y); break;
+      case BMCTS_MATH_NORM_ANGLE: r = bm_norm_angle(x); break;
+      case BMCTS_MATH_FMA_AAB: r = bm_fma(x, x, y); break;
+      case BMCTS_MATH_POW4: r = bm_powi(x, 4); break;
+      default: break;
+    }
+    out[i] = r;
+  }
+}
+
 /* ------------------------------------------- flags -> reward / cost / terminal */
 
 float oracle_prediction_time_span(const bmcts_config* cfg, unsigned depth) {

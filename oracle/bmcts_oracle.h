@@ -42,6 +42,8 @@ uint32_t oracle_terminal_from_flags(const bmcts_config* cfg, uint32_t flags);
 
 /* Frenet projection of (x, y) on corridor c: s, signed lateral d (left > 0),
  * segment index, in_range (0 when beyond either end of the centre line) */
+/* out[i] = f(a[i], b[i]) for the elementary function `op` (BMCTS_MATH_*) */
+void oracle_math_probe(int op, const float* a, const float* b, int n, float* out);
 void oracle_project(const bmcts_corridor* c, float x, float y, float* s, float* d, int* seg,
                     int* in_range);
 

@@ -153,8 +153,10 @@ EXPORTED_SYMBOLS = [
     "bmcts_create", "bmcts_destroy", "bmcts_set_config", "bmcts_set_scenario",
     "bmcts_rollout_batch", "bmcts_step_batch", "bmcts_expand_rollout_batch",
     "bmcts_likelihood_batch", "bmcts_sync", "bmcts_last_kernel_ms", "bmcts_launch_count",
-    "bmcts_stream", "bmcts_last_error", "bmcts_status_string",
+    "bmcts_stream", "bmcts_last_error", "bmcts_status_string", "bmcts_math_probe",
 ]
+MATH_OPS = ["sin", "cos", "atan2", "tan_small", "div", "sqrt", "min", "max", "norm_angle", "fma_aab",
+            "pow4"]
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libbmcts.so")

@@ -984,6 +984,28 @@ int bmcts_likelihood_batch(bmcts_engine* e, const bmcts_likelihood_in* in, float
   return BMCTS_OK;
 }
 
+int bmcts_math_probe(bmcts_engine* e, int op, const float* a, const float* b, int n, float* out) {
+  if (!e || !a || !b || !out || n < 0 || op < 0 || op >= BMCTS_MATH_NUM_OPS)
+    return e ? fail(e, BMCTS_ERR_INVALID_ARG, "math_probe: bad argument") : BMCTS_ERR_INVALID_ARG;
+  if (n == 0) return BMCTS_OK;
+  CU(cudaSetDevice(e->device));
+  const size_t bytes = sizeof(float) * (size_t)n;
+  int st;
+  if ((st = ensure(e, e->d_pack_in, 2 * bytes))) return st;
+  if ((st = ensure(e, e->d_pack_out, bytes))) return st;
+  float* da = (float*)e->d_pack_in.ptr;
+  float* db = da + n;
+  CU(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, e->stream));
+  bmcts::math_probe_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(op, da, db, n,
+                                                                    (float*)e->d_pack_out.ptr);
+  CU(cudaGetLastError());
+  e->launches++;
+  CU(cudaMemcpyAsync(out, e->d_pack_out.ptr, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return BMCTS_OK;
+}
+
 int bmcts_alloc_host(size_t bytes, void** out) {
   if (!out) return BMCTS_ERR_INVALID_ARG;
   *out = nullptr;

@@ -455,4 +455,27 @@ __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p)
   if (t == 0) p.prob[out_idx] = bm_div((float)s_count, (float)p.n_samples);
 }
 
+// elementary-function probe (bmcts_math_probe): out[i] = f(a[i], b[i])
+__global__ void math_probe_kernel(int op, const float* a, const float* b, int n, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = a[i], y = b[i];
+  float s, c, r = 0.0f;
+  switch (op) {
+    case BMCTS_MATH_SIN: bm_sincos(x, &s, &c); r = s; break;
+    case BMCTS_MATH_COS: bm_sincos(x, &s, &c); r = c; break;
+    case BMCTS_MATH_ATAN2: r = bm_atan2(x, y); break;
+    case BMCTS_MATH_TAN_SMALL: r = bm_tan_small(x); break;
+    case BMCTS_MATH_DIV: r = bm_div(x, y); break;
+    case BMCTS_MATH_SQRT: r = bm_sqrt(x); break;
+    case BMCTS_MATH_MIN: r = bm_min(x, y); break;
+    case BMCTS_MATH_MAX: r = bm_max(x, y); break;
+    case BMCTS_MATH_NORM_ANGLE: r = bm_norm_angle(x); break;
+    case BMCTS_MATH_FMA_AAB: r = bm_fma(x, x, y); break;
+    case BMCTS_MATH_POW4: r = bm_powi(x, 4); break;
+    default: break;
+  }
+  out[i] = r;
+}
+
 }  // namespace bmcts

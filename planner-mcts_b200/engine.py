@@ -74,6 +74,17 @@ class RolloutEngine:
         except Exception:
             pass
 
+    def math_probe(self, op, a, b):
+        """out[i] = f(a[i], b[i]) of include/bmcts_math.h evaluated on the device (self test)"""
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        out = np.zeros_like(a)
+        fp = C.POINTER(C.c_float)
+        self._lib.bmcts_math_probe.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_int, fp]
+        self._check(self._lib.bmcts_math_probe(self._h, _abi.MATH_OPS.index(op), a.ctypes.data_as(fp),
+                                               b.ctypes.data_as(fp), a.size, out.ctypes.data_as(fp)))
+        return out
+
     def set_config(self, config):
         self._check(self._lib.bmcts_set_config(self._h, C.byref(config)))
         self.config = config

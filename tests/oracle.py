@@ -57,6 +57,19 @@ def load():
     return lib
 
 
+def math_probe(op, a, b):
+    lib = load()
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    out = np.zeros_like(a)
+    fp = C.POINTER(C.c_float)
+    lib.oracle_math_probe.argtypes = [C.c_int, fp, fp, C.c_int, fp]
+    lib.oracle_math_probe.restype = None
+    lib.oracle_math_probe(_abi.MATH_OPS.index(op), a.ctypes.data_as(fp), b.ctypes.data_as(fp), a.size,
+                          out.ctypes.data_as(fp))
+    return out
+
+
 def _h(a, dtype, shape, name):
     a = np.ascontiguousarray(a, dtype=dtype)
     assert tuple(a.shape) == tuple(shape), f"{name}: {a.shape} != {shape}"
