@@ -129,9 +129,12 @@ class _BehaviorUCT:
             st = self._lib.bmcts_planner_create(self.KIND, int(device), C.byref(self._h))
         if st != _abi.OK:
             raise _abi.BmctsError(st, "bmcts_planner_create")
-        self.params = dict(params or {})
+        # a flat {"A::B::key": value} dict or a parameters.ParameterServer tree
+        self.params = params if hasattr(params, "flatten") else dict(params or {})
         for key, val in self.params.items():
-            vals = np.atleast_1d(np.asarray(val, dtype=np.float64))
+            if val is None or isinstance(val, str):
+                continue  # names of model / function types: not planner parameters
+            vals = np.atleast_1d(np.asarray(val, dtype=np.float64)).ravel()
             arr = (C.c_double * len(vals))(*vals)
             self._check(self._lib.bmcts_planner_set_param(self._h, key.encode(), arr, len(vals)))
         self.hypotheses = list(hypotheses)

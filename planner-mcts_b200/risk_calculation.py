@@ -38,6 +38,21 @@ def _arr(values):
     return (C.c_double * len(values))(*values)
 
 
+def _param(params, path, default):
+    """a parameter from a flat {"A::B": v} dict or from a ParameterServer tree (where reading
+    registers the default, like the C++ Params getters)"""
+    if hasattr(params, "AddChild"):
+        return params[path, "", default]
+    return params.get(path, default)
+
+
+def CalculateRegionBoundariesArea(region_boundaries):
+    """knowledge_region.hpp: product of the widths of a {name: (lo, hi)} box"""
+    lo = [float(b[0]) for b in region_boundaries.values()]
+    hi = [float(b[1]) for b in region_boundaries.values()]
+    return _lib().bmcts_risk_region_area(_arr(lo), _arr(hi), len(lo))
+
+
 class KnowledgeRegion:
     @property
     def definition(self):
@@ -80,7 +95,7 @@ class KnowledgeFunctionDefinition:
 
     def __init__(self, supporting_region, params=None):
         self.supporting_region = supporting_region
-        self.params = params or {}
+        self.params = params if params is not None else {}
 
     def GetSupportingRegion(self):
         return self.supporting_region
@@ -103,8 +118,8 @@ class LinearKnowledgeFunctionDefinition(KnowledgeFunctionDefinition):
         self.function_params = {}
         for name in supporting_region.GetDefinition():
             self.function_params[name] = (
-                float(self.params.get(f"LinearKnowledgeFunction::{name}::a", 1.0)),
-                float(self.params.get(f"LinearKnowledgeFunction::{name}::b", 1.0)))
+                float(_param(self.params, f"LinearKnowledgeFunction::{name}::a", 1.0)),
+                float(_param(self.params, f"LinearKnowledgeFunction::{name}::b", 1.0)))
 
     def CalculateIntegral(self, region_boundaries):
         names = list(region_boundaries)
@@ -136,9 +151,9 @@ class PriorKnowledgeFunction:
     def __init__(self, prior_knowledge_region, knowledge_function, params=None):
         self.prior_knowledge_region = prior_knowledge_region
         self.knowledge_function = knowledge_function
-        self.params = params or {}
+        self.params = params if params is not None else {}
         self.num_partitions_integration = int(
-            self.params.get("PriorKnowledgeFunction::NumPartitionsIntegration", 100))
+            _param(self.params, "PriorKnowledgeFunction::NumPartitionsIntegration", 100))
 
     def GetIntegralKnowledeValue(self, knowledge_region):
         return self.knowledge_function.CalculateIntegral(knowledge_region)
