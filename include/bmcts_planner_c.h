@@ -19,8 +19,26 @@ extern "C" {
 enum {
   BMCTS_PLANNER_HYPOTHESIS = 0,      /* BehaviorUCTHypothesis */
   BMCTS_PLANNER_RISK_CONSTRAINT = 1, /* BehaviorUCTRiskConstraint */
-  BMCTS_PLANNER_COOPERATIVE = 2      /* BehaviorUCTCooperative */
+  BMCTS_PLANNER_COOPERATIVE = 2,     /* BehaviorUCTCooperative */
+  /* BehaviorUCTNHeuristicRiskConstraint (behavior_uct_nheuristic_risk_constraint.hpp:23-60):
+   * the risk-constrained planner whose ego nodes are warm-started by a learned model; needs
+   * bmcts_planner_set_node_prior before the first plan */
+  BMCTS_PLANNER_NHEURISTIC_RISK_CONSTRAINT = 3
 };
+
+/* what a node-prior callback filled */
+enum { BMCTS_PRIOR_POLICY = 1, BMCTS_PRIOR_VALUES = 2 };
+
+/* The learned model behind NeuralCostConstrainedStatistic::initialize_from_neural_model
+ * (mcts_statistics/mcts_neural_cost_constrained_statistic.hpp:175-198), batched: called once
+ * per wave of the search with the observations [n_nodes][obs_dim] of every node the wave
+ * created (bmcts_planner_observe layout).  Fill, per node and ego action ([n_nodes][n_actions]):
+ * the exploration policy and / or the value triple {return, envelope risk, collision risk};
+ * return BMCTS_PRIOR_POLICY | BMCTS_PRIOR_VALUES for what was filled, < 0 on failure.  Called
+ * from the search threads, one call at a time. */
+typedef int (*bmcts_node_prior_fn)(void* user, int n_nodes, int obs_dim, const float* observations,
+                                   int n_actions, float* policy, float* returns,
+                                   float* envelope_risk, float* collision_risk);
 
 #define BMCTS_PLAN_MAX_TRAJ 64
 
@@ -82,6 +100,18 @@ int bmcts_planner_root_stats(bmcts_planner* p, double* stats, int max_n);
 /* re-decide the action from merged statistics (after the NCCL all-reduce) */
 int bmcts_planner_decide_from_root_stats(bmcts_planner* p, const double* stats, int n,
                                          bmcts_plan_result* out);
+/* model of the neural warm start (kind BMCTS_PLANNER_NHEURISTIC_RISK_CONSTRAINT); must be set
+ * before the first bmcts_planner_plan.  `user` is passed back to every call. */
+int bmcts_planner_set_node_prior(bmcts_planner* p, bmcts_node_prior_fn fn, void* user);
+/* length of one observation: (ML::NearestObserver::NNearestAgents + 1) * 4 */
+int bmcts_planner_observation_size(bmcts_planner* p);
+/* the observer the search applies to its nodes, on an observed world (to build training data
+ * and to test models): [x, y, theta, v] of the ego and of its nearest agents, normalised to
+ * [0, 1]; needs bmcts_planner_set_map.  Returns the number of floats written or < 0. */
+int bmcts_planner_observe(bmcts_planner* p, uint32_t ego_id, const bmcts_agent_state* agents,
+                          int n_agents, float* observation, int max_n);
+/* calls of the node-prior callback / nodes evaluated so far */
+int bmcts_planner_node_prior_stats(bmcts_planner* p, uint64_t* calls, uint64_t* nodes);
 /* BehaviorHypothesis::ParameterSamplingProbability of hypothesis h */
 double bmcts_planner_parameter_sampling_probability(bmcts_planner* p, int h);
 const char* bmcts_planner_last_error(const bmcts_planner* p);

@@ -450,6 +450,9 @@ Trajectory BehaviorUCTRiskConstraint::Plan(double min_planning_time, const Obser
     Mcts mcts(current, EgoMode::kCostConstrained, OtherMode::kHypothesis, sw.scenario.n_agents,
               sw.scenario.n_ego_actions, sw.scenario.n_hypotheses, n_costs, ev, tree);
     mcts.set_cost_constraints(current_scenario_risk_);
+    if (node_prior_)
+      mcts.set_node_prior(node_prior_.get(), GetObserver(&sw.scenario),
+                          (double)params_->GetInt("BehaviorUctBase::Mcts::NeuralStatistic::PriorVisits", 1));
     mcts.Search(sw.pose, sw.alive, 1, MakeSampler(sw, tree));
     TreeResult r;
     r.stats = mcts.GetRootStats();

@@ -14,6 +14,7 @@
 
 #include "evaluator.hpp"
 #include "mcts.hpp"
+#include "node_prior.hpp"
 #include "params.hpp"
 #include "statistics.hpp"
 #include "world.hpp"
@@ -189,6 +190,14 @@ class BehaviorUCTRiskConstraint : public BehaviorUCTHypothesisBase,
   }
   ScenarioRiskFunctionPtr GetScenarioRiskFunction() const { return scenario_risk_function_; }
   double CalculateAvailableScenarioRisk() const;  // behavior_uct_risk_constraint.cpp:51-72
+  // neural warm start of the ego statistic (node_prior.hpp); null = plain CostConstrainedStatistic
+  void set_node_prior(std::shared_ptr<NodePriorProvider> provider) { node_prior_ = std::move(provider); }
+  std::shared_ptr<NodePriorProvider> GetNodePrior() const { return node_prior_; }
+  NearestObserver GetObserver(const MapGeometry* map) const {
+    NearestObserver o = NearestObserver::FromParams(*params_);
+    if (map) o.SetWorldBounds(*map);
+    return o;
+  }
 
  protected:
   void InitRisk();
@@ -196,6 +205,36 @@ class BehaviorUCTRiskConstraint : public BehaviorUCTHypothesisBase,
   bool estimate_scenario_risk_, initialized_available_risk_, update_scenario_risk_;
   ScenarioRiskFunctionPtr scenario_risk_function_;
   std::vector<double> last_lambdas_;
+  std::shared_ptr<NodePriorProvider> node_prior_;
+};
+
+// behavior_uct_nheuristic_risk_constraint.hpp:23-60: PlanWithMcts with
+// mcts::NeuralCostConstrainedStatistic as the ego statistic.  The reference's (model file,
+// bark-ml observer, value converter) triple is one NodePriorProvider here.
+class BehaviorUCTNHeuristicRiskConstraint : public BehaviorUCTRiskConstraint {
+ public:
+  BehaviorUCTNHeuristicRiskConstraint(const ParamsPtr& params,
+                                      const std::vector<BehaviorHypothesisIDM>& h,
+                                      const ScenarioRiskFunctionPtr& scenario_risk_function,
+                                      std::shared_ptr<NodePriorProvider> node_prior, int device = 0)
+      : BehaviorUCTRiskConstraint(params, h, scenario_risk_function, device) {
+    set_node_prior(std::move(node_prior));
+  }
+  BehaviorUCTNHeuristicRiskConstraint(const ParamsPtr& params,
+                                      const std::vector<BehaviorHypothesisIDM>& h,
+                                      const ScenarioRiskFunctionPtr& scenario_risk_function,
+                                      std::shared_ptr<NodePriorProvider> node_prior,
+                                      std::shared_ptr<LeafEvaluator> evaluator)
+      : BehaviorUCTRiskConstraint(params, h, scenario_risk_function, evaluator) {
+    set_node_prior(std::move(node_prior));
+  }
+  Trajectory Plan(double min_planning_time, const ObservedWorld& observed_world) override {
+    if (!node_prior_) throw std::runtime_error("BehaviorUCTNHeuristicRiskConstraint: no node prior set");
+    return BehaviorUCTRiskConstraint::Plan(min_planning_time, observed_world);
+  }
+  std::shared_ptr<BehaviorUCTBase> Clone() const {
+    return std::make_shared<BehaviorUCTNHeuristicRiskConstraint>(*this);
+  }
 };
 
 class BehaviorUCTCooperative : public BehaviorUCTBase {

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "evaluator.hpp"
+#include "node_prior.hpp"
 #include "statistics.hpp"
 
 namespace bark_mcts_b200 {
@@ -114,6 +115,7 @@ struct Node {
   std::unordered_map<JointKey, Node*, JointKeyHash> children;
   std::vector<double> edge_reward;  // rewards[] of the execute() that created this node
   double edge_cost[2] = {0.0, 0.0};
+  std::unique_ptr<NodePrior> prior;  // neural warm start of the ego statistic (node_prior.hpp)
 };
 
 class Mcts {
@@ -136,9 +138,11 @@ class Mcts {
     using clock = std::chrono::steady_clock;
     const auto t0 = clock::now();
     nodes_.clear();
+    awaiting_prior_.clear();
     cc_params_ = p_;
     cc_params_.cost_constrained_statistic.COST_CONSTRAINTS = constraints_;
     root_ = NewNode(nullptr, root_pose, root_alive, root_depth, false);
+    EvaluatePriors();
     EnsureStats(root_);
     t_select_ = t_fill_ = t_engine_ = t_backup_ = 0.0;
     iterations_ = 0;
@@ -183,6 +187,14 @@ class Mcts {
   const Node& get_root() const { return *root_; }
   const std::vector<double>& lambdas() const { return lambdas_; }
   void set_cost_constraints(const std::vector<double>& c) { constraints_ = c; }
+  // neural warm start (cost-constrained ego statistic only): every node a wave creates is
+  // observed and the provider is asked once per wave for the whole batch
+  void set_node_prior(NodePriorProvider* provider, const NearestObserver& observer,
+                      double prior_visits) {
+    prior_ = provider;
+    observer_ = observer;
+    prior_visits_ = prior_visits;
+  }
   // number of distinct actions expanded at the root per agent slot (tree-shape tests)
   std::vector<int> RootExpandedActions() const {
     std::vector<int> n(A_, 0);
@@ -230,6 +242,7 @@ class Mcts {
     // objects exist (they hold the latest return / cost), their action tables do not yet.
     if (ego_mode_ == EgoMode::kCostConstrained) n->ego_cc.InitLight(n_costs_);
     if (other_mode_ == OtherMode::kUct) n->latest_ret_other.assign(A_, 0.0);
+    if (prior_ && !terminal && ego_mode_ == EgoMode::kCostConstrained) awaiting_prior_.push_back(n);
     return n;
   }
 
@@ -242,6 +255,13 @@ class Mcts {
                       p_.USE_BOUND_ESTIMATION);
     } else {
       n->ego_cc.Init(n_actions_, n_costs_, cc_params_);
+      if (n->prior) {
+        const NodePrior& pr = *n->prior;
+        const bool vals = (pr.mask & kPriorHasValues) != 0;
+        n->ego_cc.SetPrior((pr.mask & kPriorHasPolicy) ? pr.policy.data() : nullptr,
+                           vals ? pr.ret.data() : nullptr, vals ? pr.envelope_risk.data() : nullptr,
+                           vals ? pr.collision_risk.data() : nullptr, prior_visits_);
+      }
     }
     if (other_mode_ == OtherMode::kHypothesis) {
       n->other_hyp.assign(A_, HypothesisStatistic());
@@ -364,6 +384,33 @@ class Mcts {
       if (ego_mode_ == EgoMode::kCostConstrained) UpdateLambdas();
     }
     t_backup_ += ms(t3, clock::now());
+    EvaluatePriors();
+  }
+
+  // one provider call for all nodes created since the last call
+  void EvaluatePriors() {
+    if (!prior_ || awaiting_prior_.empty()) return;
+    const int n = (int)awaiting_prior_.size(), d = observer_.observation_size();
+    obs_.assign((size_t)n * d, 0.0f);
+    for (int i = 0; i < n; ++i)
+      observer_.Observe(awaiting_prior_[i]->pose.data(), awaiting_prior_[i]->alive, A_,
+                        obs_.data() + (size_t)i * d);
+    for (auto* v : {&pr_policy_, &pr_ret_, &pr_env_, &pr_col_}) v->assign((size_t)n * n_actions_, 0.0f);
+    const int mask = prior_->Evaluate(n, d, obs_.data(), n_actions_, pr_policy_.data(),
+                                      pr_ret_.data(), pr_env_.data(), pr_col_.data());
+    for (int i = 0; i < n; ++i) {
+      auto pr = std::make_unique<NodePrior>();
+      pr->mask = mask;
+      const size_t o = (size_t)i * n_actions_;
+      if (mask & kPriorHasPolicy) pr->policy.assign(pr_policy_.begin() + o, pr_policy_.begin() + o + n_actions_);
+      if (mask & kPriorHasValues) {
+        pr->ret.assign(pr_ret_.begin() + o, pr_ret_.begin() + o + n_actions_);
+        pr->envelope_risk.assign(pr_env_.begin() + o, pr_env_.begin() + o + n_actions_);
+        pr->collision_risk.assign(pr_col_.begin() + o, pr_col_.begin() + o + n_actions_);
+      }
+      awaiting_prior_[i]->prior = std::move(pr);
+    }
+    awaiting_prior_.clear();
   }
 
   void SetHeuristic(Node* n, double ret, const double* cost, const float* ret_agents, int k) {
@@ -500,6 +547,11 @@ class Mcts {
   double search_time_ms_ = 0.0;
   double t_select_ = 0.0, t_fill_ = 0.0, t_engine_ = 0.0, t_backup_ = 0.0;
   uint64_t next_draw_id_ = 1, rollout_counter_ = 0;
+  NodePriorProvider* prior_ = nullptr;
+  NearestObserver observer_;
+  double prior_visits_ = 1.0;
+  std::vector<Node*> awaiting_prior_;
+  std::vector<float> obs_, pr_policy_, pr_ret_, pr_env_, pr_col_;
 };
 
 }  // namespace bark_mcts_b200

@@ -52,6 +52,16 @@ void EnsurePlanner(bmcts_planner* p) {
     case BMCTS_PLANNER_COOPERATIVE:
       p->planner = std::make_shared<BehaviorUCTCooperative>(p->params, ev);
       break;
+    case BMCTS_PLANNER_NHEURISTIC_RISK_CONSTRAINT:
+      if (!p->node_prior)
+        throw std::runtime_error("bmcts_planner_set_node_prior was not called");
+      p->planner = std::make_shared<BehaviorUCTNHeuristicRiskConstraint>(
+          p->params, p->hypotheses,
+          p->risk_integrals.empty()
+              ? nullptr
+              : std::make_shared<TableScenarioRiskFunction>(p->hypotheses, p->risk_integrals),
+          p->node_prior, ev);
+      break;
     default:
       throw std::runtime_error("unknown planner kind");
   }
@@ -123,7 +133,7 @@ void FillResult(bmcts_planner* p, bmcts_plan_result* out) {
 extern "C" {
 
 int bmcts_planner_create(int kind, int device, bmcts_planner** out) {
-  if (!out || kind < BMCTS_PLANNER_HYPOTHESIS || kind > BMCTS_PLANNER_COOPERATIVE)
+  if (!out || kind < BMCTS_PLANNER_HYPOTHESIS || kind > BMCTS_PLANNER_NHEURISTIC_RISK_CONSTRAINT)
     return BMCTS_ERR_INVALID_ARG;
   bmcts_planner* p = new bmcts_planner();
   p->kind = kind;
@@ -235,6 +245,52 @@ int bmcts_planner_decide_from_root_stats(bmcts_planner* p, const double* stats, 
   } catch (const std::exception& e) {
     return Fail(p, BMCTS_ERR_CUDA, e.what());
   }
+  return BMCTS_OK;
+}
+
+int bmcts_planner_set_node_prior(bmcts_planner* p, bmcts_node_prior_fn fn, void* user) {
+  if (!p || !fn) return BMCTS_ERR_INVALID_ARG;
+  if (p->kind != BMCTS_PLANNER_NHEURISTIC_RISK_CONSTRAINT)
+    return Fail(p, BMCTS_ERR_INVALID_ARG, "only the NHeuristic risk-constraint planner takes a node prior");
+  if (p->planner) return Fail(p, BMCTS_ERR_INVALID_ARG, "the node prior is fixed at construction");
+  p->node_prior = std::make_shared<CallbackPriorProvider>(fn, user);
+  return BMCTS_OK;
+}
+
+int bmcts_planner_observation_size(bmcts_planner* p) {
+  if (!p) return BMCTS_ERR_INVALID_ARG;
+  return NearestObserver::FromParams(*p->params).observation_size();
+}
+
+int bmcts_planner_observe(bmcts_planner* p, uint32_t ego_id, const bmcts_agent_state* agents,
+                          int n_agents, float* observation, int max_n) {
+  if (!p || !agents || n_agents < 1 || n_agents > BMCTS_MAX_AGENTS || !observation)
+    return BMCTS_ERR_INVALID_ARG;
+  if (!p->map) return Fail(p, BMCTS_ERR_NO_SCENARIO, "bmcts_planner_set_map was not called");
+  NearestObserver o = NearestObserver::FromParams(*p->params);
+  o.SetWorldBounds(*p->map);
+  if (o.observation_size() > max_n) return Fail(p, BMCTS_ERR_INVALID_ARG, "observation buffer too small");
+  // slot 0 = ego, the others in the order given
+  std::vector<float> pose((size_t)n_agents * 4, 0.0f);
+  int slot = 1, found = 0;
+  for (int i = 0; i < n_agents; ++i) {
+    const int s = agents[i].id == ego_id && !found ? 0 : slot++;
+    if (s == 0) found = 1;
+    if (s >= n_agents) return Fail(p, BMCTS_ERR_INVALID_ARG, "ego agent not in the world");
+    pose[s * 4 + 0] = agents[i].x;
+    pose[s * 4 + 1] = agents[i].y;
+    pose[s * 4 + 2] = agents[i].theta;
+    pose[s * 4 + 3] = agents[i].v;
+  }
+  if (!found) return Fail(p, BMCTS_ERR_INVALID_ARG, "ego agent not in the world");
+  o.Observe(pose.data(), n_agents >= 32 ? 0xffffffffu : ((1u << n_agents) - 1u), n_agents, observation);
+  return o.observation_size();
+}
+
+int bmcts_planner_node_prior_stats(bmcts_planner* p, uint64_t* calls, uint64_t* nodes) {
+  if (!p || !p->node_prior) return BMCTS_ERR_INVALID_ARG;
+  if (calls) *calls = p->node_prior->calls();
+  if (nodes) *nodes = p->node_prior->nodes();
   return BMCTS_OK;
 }
 

@@ -19,6 +19,7 @@ struct bmcts_planner {
   std::shared_ptr<bark_mcts_b200::MapGeometry> map;
   // how the leaf evaluator is made; the product default is the CUDA engine
   std::function<std::shared_ptr<bark_mcts_b200::LeafEvaluator>()> evaluator_factory;
+  std::shared_ptr<bark_mcts_b200::CallbackPriorProvider> node_prior;  // neural warm start
   std::shared_ptr<bark_mcts_b200::BehaviorUCTBase> planner;  // built lazily at the first plan
   std::string err;
 };

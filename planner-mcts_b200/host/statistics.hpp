@@ -384,8 +384,26 @@ class CostConstrainedStatistic {
   int ChooseNextAction(const std::vector<double>& lambdas, std::mt19937& gen) {
     int a;
     if (!policy_is_ready() && !unexpanded_.empty()) {
-      std::uniform_int_distribution<size_t> d(0, unexpanded_.size() - 1);
-      size_t i = d(gen);
+      size_t i;
+      if (explore_policy_.empty()) {
+        std::uniform_int_distribution<size_t> d(0, unexpanded_.size() - 1);
+        i = d(gen);
+      } else {
+        // NeuralCostConstrainedStatistic::choose_next_action: sample_policy(exploration policy),
+        // restricted to the actions not tried yet
+        double tot = 0.0;
+        for (int u : unexpanded_) tot += explore_policy_[u];
+        double r = std::generate_canonical<double, 53>(gen) * tot;
+        i = unexpanded_.size() - 1;
+        for (size_t k = 0; k < unexpanded_.size(); ++k) {
+          r -= explore_policy_[unexpanded_[k]];
+          if (r < 0.0) {
+            i = k;
+            break;
+          }
+        }
+        if (!(tot > 0.0)) i = std::uniform_int_distribution<size_t>(0, unexpanded_.size() - 1)(gen);
+      }
       a = unexpanded_[i];
       unexpanded_.erase(unexpanded_.begin() + i);
     } else {
@@ -508,6 +526,31 @@ class CostConstrainedStatistic {
     constraints_.resize(num_costs(), 0.0);
   }
 
+  // NeuralCostConstrainedStatistic::initialize_from_neural_model
+  // (mcts_neural_cost_constrained_statistic.hpp:175-198), after Init: the policy becomes the
+  // exploration policy; the value triple {return, envelope risk, collision risk} initialises
+  // every action's means as `prior_visits` virtual visits (mamcts' set_heuristic_estimate over
+  // action maps is not in the container; the weight of the prior is this engine's parameter
+  // Mcts::NeuralStatistic::PriorVisits)
+  void SetPrior(const float* policy, const float* ret, const float* envelope_risk,
+                const float* collision_risk, double prior_visits) {
+    const int n = num_actions();
+    if (policy) {
+      explore_policy_.assign(n, 0.0);
+      for (int a = 0; a < n; ++a) explore_policy_[a] = std::max(0.0, (double)policy[a]);
+    }
+    if (ret && envelope_risk && collision_risk && prior_visits > 0.0) {
+      for (int a = 0; a < n; ++a) {
+        reward_.MergeRaw(a, prior_visits, prior_visits * (double)ret[a]);
+        if (num_costs() > 0)
+          costs_[0].MergeRaw(a, prior_visits, prior_visits * (double)envelope_risk[a]);
+        if (num_costs() > 1)
+          costs_[1].MergeRaw(a, prior_visits, prior_visits * (double)collision_risk[a]);
+      }
+    }
+  }
+  const std::vector<double>& exploration_policy() const { return explore_policy_; }
+
  private:
   UctStatistic reward_;
   std::vector<UctStatistic> costs_;
@@ -515,6 +558,7 @@ class CostConstrainedStatistic {
   std::vector<std::vector<double>> step_cost_sum_;
   std::vector<unsigned> step_cost_n_;
   std::vector<int> unexpanded_;
+  std::vector<double> explore_policy_;  // empty = uniform over the unexpanded actions
   std::vector<unsigned> pending_;
   unsigned total_pending_ = 0;
   double kappa_ = 10.0, filter_ = 0.5;

@@ -15,6 +15,7 @@ import numpy as np
 from . import _abi
 
 PLANNER_HYPOTHESIS, PLANNER_RISK_CONSTRAINT, PLANNER_COOPERATIVE = 0, 1, 2
+PLANNER_NHEURISTIC_RISK_CONSTRAINT = 3
 PLAN_MAX_TRAJ = 64
 
 
@@ -45,7 +46,8 @@ PLANNER_SYMBOLS = [
     "bmcts_planner_add_hypothesis", "bmcts_planner_set_scenario_risk", "bmcts_planner_set_map", "bmcts_planner_set_tree_index",
     "bmcts_planner_plan", "bmcts_planner_get_beliefs", "bmcts_planner_root_stats",
     "bmcts_planner_decide_from_root_stats", "bmcts_planner_parameter_sampling_probability",
-    "bmcts_planner_last_error",
+    "bmcts_planner_last_error", "bmcts_planner_set_node_prior", "bmcts_planner_observation_size",
+    "bmcts_planner_observe", "bmcts_planner_node_prior_stats",
 ]
 
 
