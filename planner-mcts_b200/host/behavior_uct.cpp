@@ -345,12 +345,9 @@ void BehaviorUCTHypothesisBase::UpdateBeliefs(const ObservedWorld& observed_worl
 
 Mcts::HypothesisSampler BehaviorUCTHypothesisBase::MakeSampler(const SearchWorld& sw,
                                                                unsigned tree_index) {
-  std::vector<AgentId> ids = sw.slot_ids;
-  const unsigned H = (unsigned)sw.scenario.n_hypotheses;
-  auto tracker = std::make_shared<HypothesisBeliefTracker>(belief_tracker_.SamplerForTree(tree_index));
-  return [tracker, ids, H](std::vector<uint8_t>* hyp) {
-    for (size_t s = 1; s < ids.size(); ++s) (*hyp)[s] = (uint8_t)tracker->sample_for(ids[s], H);
-  };
+  auto sampler = std::make_shared<HypothesisBeliefTracker::SlotSampler>(
+      belief_tracker_.SamplerForSlots(sw.slot_ids, (unsigned)sw.scenario.n_hypotheses, tree_index));
+  return [sampler](std::vector<uint8_t>* hyp) { (*sampler)(hyp); };
 }
 
 // ----------------------------------------------------------- BehaviorUCTHypothesis

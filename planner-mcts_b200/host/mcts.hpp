@@ -141,7 +141,7 @@ class Mcts {
     awaiting_prior_.clear();
     cc_params_ = p_;
     cc_params_.cost_constrained_statistic.COST_CONSTRAINTS = constraints_;
-    root_ = NewNode(nullptr, root_pose, root_alive, root_depth, false);
+    root_ = NewNode(nullptr, &root_pose, root_alive, root_depth, false);
     EvaluatePriors();
     EnsureStats(root_);
     t_select_ = t_fill_ = t_engine_ = t_backup_ = 0.0;
@@ -226,7 +226,7 @@ class Mcts {
     Node* reached = nullptr;     // existing terminal / max-depth node reached instead
   };
 
-  Node* NewNode(Node* parent, const std::vector<float>& pose, uint32_t alive, unsigned state_depth,
+  Node* NewNode(Node* parent, const std::vector<float>* pose, uint32_t alive, unsigned state_depth,
                 bool terminal) {
     nodes_.emplace_back(new Node());
     Node* n = nodes_.back().get();
@@ -234,10 +234,14 @@ class Mcts {
     n->tree_depth = parent ? parent->tree_depth + 1 : 0;
     max_tree_depth_ = std::max(max_tree_depth_, n->tree_depth);
     n->state_depth = state_depth;
-    n->pose = pose;
+    if (pose)
+      n->pose = *pose;
+    else
+      n->pose.resize((size_t)A_ * 4);  // filled by the caller
     n->alive = alive;
     n->terminal = terminal;
-    n->edge_reward.assign(A_, 0.0);
+    // rewards of the other agents are only read by the cooperative (joint UCT) statistics
+    n->edge_reward.assign(other_mode_ == OtherMode::kUct ? A_ : 1, 0.0);
     // Most nodes are leaves that only ever receive one heuristic estimate: the statistics
     // objects exist (they hold the latest return / cost), their action tables do not yet.
     if (ego_mode_ == EgoMode::kCostConstrained) n->ego_cc.InitLight(n_costs_);
@@ -276,15 +280,18 @@ class Mcts {
   }
 
   // StageNode::select_or_expand down the tree for one iteration
-  Selection Select(const HypothesisSampler& sample_hypotheses) {
-    Selection sel;
+  // (fills a Selection that is reused from wave to wave: no allocation per iteration)
+  void Select(const HypothesisSampler& sample_hypotheses, Selection& sel) {
+    sel.path.clear();
+    sel.needs_engine = false;
+    sel.reached = nullptr;
     sel.hyp.assign(A_, 0);
     if (sample_hypotheses) sample_hypotheses(&sel.hyp);
     Node* node = root_;
     for (;;) {
       if (node->terminal || node->tree_depth >= p_.MAX_SEARCH_DEPTH) {
         sel.reached = node;
-        return sel;
+        return;
       }
       EnsureStats(node);
       PathStep st;
@@ -326,7 +333,7 @@ class Mcts {
         }
       }
       sel.needs_engine = true;
-      return sel;
+      return;
     }
   }
 
@@ -336,12 +343,13 @@ class Mcts {
       return std::chrono::duration<double, std::milli>(b - a).count();
     };
     const auto t0 = clock::now();
-    std::vector<Selection> sels;
-    sels.reserve(w);
-    for (int i = 0; i < w; ++i) sels.push_back(Select(sample_hypotheses));
+    std::vector<Selection>& sels = sels_;
+    if ((int)sels.size() < w) sels.resize(w);
+    for (int i = 0; i < w; ++i) Select(sample_hypotheses, sels[i]);
     const auto t1 = clock::now();
     t_select_ += ms(t0, t1);
-    std::vector<int> slot(w, -1);
+    std::vector<int>& slot = slot_;
+    slot.assign(w, -1);
     int n_engine = 0;
     for (int i = 0; i < w; ++i)
       if (sels[i].needs_engine) slot[i] = n_engine++;
@@ -451,21 +459,21 @@ class Mcts {
           joint[s] = (ActionKey)st.other_idx[s];
         }
       }
-      auto it = parent->children.find(joint);
-      if (it != parent->children.end()) {
+      // one hash of the joint action: look up, and claim the slot if it is new
+      const bool link = (long)nodes_.size() < p_.MAX_NUMBER_OF_NODES;
+      auto it = link ? parent->children.try_emplace(joint, nullptr).first : parent->children.find(joint);
+      if (it != parent->children.end() && it->second) {
         leaf = it->second;  // same joint action expanded earlier (in this wave or by value merge)
       } else {
-        std::vector<float> pose((size_t)A_ * 4);
-        for (int a = 0; a < A_; ++a)
-          for (int f = 0; f < 4; ++f) pose[(size_t)a * 4 + f] = wave_.next_pose[wave_.at(a, k) * 4 + f];
         const bool terminal = (wave_.flags[k] & BMCTS_F_TERMINAL) != 0;
-        leaf = NewNode(parent, pose, wave_.next_alive[k], parent->state_depth + 1, terminal);
-        for (int a = 0; a < A_; ++a) leaf->edge_reward[a] = wave_.reward[wave_.at(a, k)];
+        leaf = NewNode(parent, nullptr, wave_.next_alive[k], parent->state_depth + 1, terminal);
+        for (int a = 0; a < A_; ++a)
+          for (int f = 0; f < 4; ++f) leaf->pose[(size_t)a * 4 + f] = wave_.next_pose[wave_.at(a, k) * 4 + f];
+        for (size_t a = 0; a < leaf->edge_reward.size(); ++a) leaf->edge_reward[a] = wave_.reward[wave_.at((int)a, k)];
         leaf->edge_cost[0] = wave_.cost[k];
         leaf->edge_cost[1] = wave_.cost[(size_t)wave_.n + k];
-        if ((long)nodes_.size() <= p_.MAX_NUMBER_OF_NODES) {
-          parent->children[joint] = leaf;
-        }  // beyond the node cap the child is evaluated but not linked (bounded memory)
+        if (link) it->second = leaf;
+        // beyond the node cap the child is evaluated but not linked (bounded memory)
       }
       const bmcts_rollout_result& r = wave_.result[k];
       const double cost[2] = {r.cost0, r.cost1};
@@ -491,9 +499,8 @@ class Mcts {
         if (st.other_idx[s] < 0) continue;
         if (other_mode_ == OtherMode::kHypothesis) {
           const int h = sel.hyp[s];
-          n->other_hyp[s].ReleasePending(h, st.other_idx[s]);
-          n->other_hyp[s].UpdateStatistic(h, st.other_idx[s], child->edge_cost[0],
-                                          child->latest_cost_other);
+          n->other_hyp[s].BackupEntry(h, st.other_idx[s], child->edge_cost[0],
+                                      child->latest_cost_other);
         } else {
           n->other_uct[s].ReleasePending(st.other_idx[s]);
           n->other_uct[s].UpdateStatistic(st.other_idx[s], child->edge_reward[s],
@@ -520,12 +527,12 @@ class Mcts {
   void UpdateLambdas() {
     const auto& c = p_.cost_constrained_statistic;
     if (root_->ego_cc.total_visits() == 0) return;
-    auto pol = root_->ego_cc.GreedyPolicy(0.0, c.ACTION_FILTER_FACTOR, lambdas_, gen_);
+    const int greedy = root_->ego_cc.GreedyAction(0.0, c.ACTION_FILTER_FACTOR, lambdas_, gen_);
     const double range = std::max(1e-9, c.COST_UPPER_BOUND - c.COST_LOWER_BOUND);
     const double lam_max = 1.0 / (std::max(1e-6, c.TAU_GRADIENT_CLIP) * std::max(1e-6, 1.0 - p_.DISCOUNT_FACTOR));
     const double step = c.GRADIENT_UPDATE_STEP / (1.0 + 0.01 * (double)iterations_);
     for (int i = 0; i < n_costs_ && i < (int)lambdas_.size(); ++i) {
-      const double q = root_->ego_cc.cost_statistic(i).pairs()[pol.first].value;
+      const double q = root_->ego_cc.cost_statistic(i).pairs()[greedy].value;
       const double limit = i < (int)constraints_.size() ? constraints_[i] : 0.0;
       lambdas_[i] = std::min(lam_max, std::max(0.0, lambdas_[i] + step * (q - limit) / range));
     }
@@ -542,6 +549,8 @@ class Mcts {
   std::vector<std::unique_ptr<Node>> nodes_;
   Node* root_ = nullptr;
   WaveBuffers wave_;
+  std::vector<Selection> sels_;
+  std::vector<int> slot_;
   long iterations_ = 0;
   int max_tree_depth_ = 0;
   double search_time_ms_ = 0.0;

@@ -23,7 +23,27 @@
 
 namespace bark_mcts_b200 {
 
-using ActionKey = uint64_t;
+using ActionKey = uint32_t;
+constexpr ActionKey kNoKey = 0xFFFFFFFFu;  // a NaN pattern: never the key of an acceleration
+
+// uniform double in [0, 1) from two draws; std::generate_canonical evaluates two long-double
+// logarithms per call, which made it the most expensive part of hypothesis sampling
+inline double Uniform01(std::mt19937& gen) {
+  const uint64_t hi = gen() >> 5, lo = gen() >> 6;  // 27 + 26 bits
+  return ((double)hi * 67108864.0 + (double)lo) * (1.0 / 9007199254740992.0);
+}
+
+// sqrt(2 ln N) of the UCB exploration term for small N (one table for the process)
+inline double SqrtTwoLog(double n) {
+  constexpr int kN = 4096;
+  static const std::vector<double> table = [] {
+    std::vector<double> t(kN);
+    for (int i = 0; i < kN; ++i) t[i] = std::sqrt(2.0 * std::log(std::max(1.0, (double)i)));
+    return t;
+  }();
+  const long k = (long)n;
+  return (n >= 0.0 && k < kN && (double)k == n) ? table[k] : std::sqrt(2.0 * std::log(std::max(1.0, n)));
+}
 
 inline ActionKey KeyOfAcceleration(float acc) {
   // the reference addresses a continuous action by boost::hash of its value
@@ -187,19 +207,32 @@ class UctStatistic {
 // (each = one IDM parameter draw) with visit counts and the ego cost they led to.
 class HypothesisStatistic {
  public:
+  // One expanded action of one hypothesis.  What the selection scan reads at every visit lives
+  // in Hot (16 bytes, contiguous per table); the rest is only touched for the chosen entry.
   struct Entry {
     ActionKey key = 0;      // bit pattern of the applied acceleration, once resolved
     uint64_t draw_id = 0;   // Philox id that reproduces the action (replaces the stored trajectory)
     unsigned count = 0, pending = 0;
-    double ego_cost = 0.0;  // mean accumulated ego cost after this action
     bool resolved = false;
     bool dead = false;      // merged into another entry with the same action: never selected
   };
+  struct Hot {
+    double ego_cost = 0.0;     // mean accumulated ego cost after this action
+    float inv_sqrt_n = 1.0f;   // 1 / sqrt(n); -inf for a dead entry (never the UCB maximum)
+    uint32_t n = 0;            // count + pending; 0 for a dead entry
+  };
+
+  // everything of one hypothesis behind one header.  (Software prefetch of the tables of all
+  // agents ahead of a selection step was measured: 8 % slower than leaving it to the core.)
+  struct Table {
+    std::vector<Hot> hot;
+    std::vector<Entry> cold;
+    std::vector<ActionKey> keys;  // key of a resolved live entry, else kNoKey
+    unsigned visits = 0, pending = 0;
+  };
 
   void Init(int num_hypotheses, const MctsParameters& m) {
-    per_hyp_.assign(std::max(1, num_hypotheses), {});
-    visits_.assign(per_hyp_.size(), 0);
-    pending_.assign(per_hyp_.size(), 0);
+    tables_.assign(std::max(1, num_hypotheses), Table());
     k_ = m.hypothesis_statistic.PROGRESSIVE_WIDENING_K;
     alpha_ = m.hypothesis_statistic.PROGRESSIVE_WIDENING_ALPHA;
     hyp_based_ = m.hypothesis_statistic.PROGRESSIVE_WIDENING_HYPOTHESIS_BASED;
@@ -213,17 +246,19 @@ class HypothesisStatistic {
   // returns the index of the chosen entry in the table of hypothesis h; *is_new tells the
   // caller to plan the action (S::plan_action_current_hypothesis) with entry.draw_id
   int ChooseNextAction(int h, std::mt19937& gen, uint64_t fresh_draw_id, bool* is_new) {
-    std::vector<Entry>& tab = per_hyp_[h];
+    Table& t = tables_[h];
+    std::vector<Entry>& tab = t.cold;
+    std::vector<Hot>& hot = t.hot;
     double n_vis, n_act;
     if (hyp_based_) {
-      n_vis = visits_[h] + pending_[h];
+      n_vis = t.visits + t.pending;
       n_act = (double)tab.size();
     } else {
       n_vis = 0;
       n_act = 0;
-      for (size_t i = 0; i < per_hyp_.size(); ++i) {
-        n_vis += visits_[i] + pending_[i];
-        n_act += (double)per_hyp_[i].size();
+      for (const Table& o : tables_) {
+        n_vis += o.visits + o.pending;
+        n_act += (double)o.cold.size();
       }
     }
     // progressive widening: |actions| <= K * N^alpha.  Inside a wave an entry may be chosen
@@ -240,31 +275,31 @@ class HypothesisStatistic {
     bool widen = n_vis >= widen_cache_v_;
     int idx = -1;
     if (!widen) {
+      const int n_tab = (int)hot.size();
       if (cost_based_) {
-        // worst case for the ego: UCB on the normalised ego cost (RMDP / RSBG)
+        // worst case for the ego: UCB on the normalised ego cost (RMDP / RSBG),
+        // v = normalised cost + 2 c sqrt(2 ln N / n)
         double best = -std::numeric_limits<double>::infinity();
-        const double two_log_n = 2.0 * std::log(std::max(1.0, n_vis));
-        for (int i = 0; i < (int)tab.size(); ++i) {
-          if (tab[i].dead) continue;
-          const double n = tab[i].count + tab[i].pending;
-          double v = (n <= 0) ? std::numeric_limits<double>::max()
-                              : (hi_ > lo_ ? (tab[i].ego_cost - lo_) / (hi_ - lo_) : 0.0) +
-                                    2.0 * c_ * std::sqrt(two_log_n / n);
+        const double explore = 2.0 * c_ * SqrtTwoLog(n_vis);
+        const double inv_range = hi_ > lo_ ? 1.0 / (hi_ - lo_) : 0.0;
+        for (int i = 0; i < n_tab; ++i) {
+          const double v = (hot[i].ego_cost - lo_) * inv_range + explore * (double)hot[i].inv_sqrt_n;
           if (v > best) {
             best = v;
             idx = i;
           }
         }
       } else {
-        // stochastic behaviour model: re-sample among the expanded actions by visit count
-        double tot = 0.0;
-        for (const Entry& e : tab) tot += e.dead ? 0.0 : (double)(e.count + e.pending) + 1e-9;
+        // stochastic behaviour model: re-sample among the expanded actions by visit count.
+        // Every live entry has been chosen at least once and merged entries carry nothing, so
+        // the weights sum to visits + pending of this hypothesis.
+        const double tot = (double)t.visits + (double)t.pending;
         if (tot > 0.0) {
-          double u = std::generate_canonical<double, 53>(gen) * tot;
-          for (int i = 0; i < (int)tab.size(); ++i) {
-            if (tab[i].dead) continue;
+          double u = Uniform01(gen) * tot;
+          for (int i = 0; i < n_tab; ++i) {
+            if (hot[i].n == 0) continue;
             idx = i;
-            u -= (double)(tab[i].count + tab[i].pending) + 1e-9;
+            u -= (double)hot[i].n;
             if (u < 0.0) break;
           }
         }
@@ -274,68 +309,110 @@ class HypothesisStatistic {
       Entry e;
       e.draw_id = fresh_draw_id;
       tab.push_back(e);
+      hot.push_back(Hot());
+      t.keys.push_back(kNoKey);
       idx = (int)tab.size() - 1;
     }
     *is_new = !tab[idx].resolved;
     tab[idx].pending++;
-    pending_[h]++;
+    SetN(hot[idx], hot[idx].n + 1);
+    t.pending++;
     return idx;
   }
 
   // the planned action of a new entry is known: resolve its key; merge with an existing
   // entry that carries the same action (the reference keys the action store by value)
   int Resolve(int h, int idx, ActionKey key) {
-    std::vector<Entry>& tab = per_hyp_[h];
+    Table& t = tables_[h];
+    std::vector<Entry>& tab = t.cold;
+    std::vector<Hot>& hot = t.hot;
     if (tab[idx].resolved) return idx;  // resolved by an earlier backup of the same wave
-    for (int i = 0; i < (int)tab.size(); ++i)
-      if (i != idx && tab[i].resolved && tab[i].key == key) {
+    const std::vector<ActionKey>& keys = t.keys;  // keys of the resolved live entries
+    for (int i = 0; i < (int)keys.size(); ++i)
+      if (keys[i] == key && i != idx) {
         tab[i].pending += tab[idx].pending;
+        SetN(hot[i], hot[i].n + tab[idx].pending);
         tab[idx].pending = 0;
-        if (!tab[idx].dead) dead_++;
         tab[idx].dead = true;  // never selected again
         tab[idx].key = key;
+        hot[idx].n = 0;
+        hot[idx].inv_sqrt_n = -std::numeric_limits<float>::infinity();
+        hot[idx].ego_cost = 0.0;
         return i;
       }
     tab[idx].key = key;
     tab[idx].resolved = true;
+    t.keys[idx] = key;
     return idx;
   }
 
   void ReleasePending(int h, int idx) {
-    if (per_hyp_[h][idx].pending) per_hyp_[h][idx].pending--;
-    if (pending_[h]) pending_[h]--;
+    Table& t = tables_[h];
+    Entry& e = t.cold[idx];
+    if (e.pending) {
+      e.pending--;
+      if (!e.dead) SetN(t.hot[idx], t.hot[idx].n - 1);
+    }
+    if (t.pending) t.pending--;
   }
 
   void UpdateFromHeuristic(double ego_cost) { latest_ego_cost_ = ego_cost; }
 
   void UpdateStatistic(int h, int idx, double collected_ego_cost, double child_latest_ego_cost) {
-    Entry& e = per_hyp_[h][idx];
+    Table& tb = tables_[h];
+    Entry& e = tb.cold[idx];
+    Hot& t = tb.hot[idx];
     latest_ego_cost_ = collected_ego_cost + gamma_ * child_latest_ego_cost;
     e.count += 1;
-    e.ego_cost += (latest_ego_cost_ - e.ego_cost) / e.count;
-    visits_[h] += 1;
+    t.ego_cost += (latest_ego_cost_ - t.ego_cost) / e.count;
+    SetN(t, t.n + 1);
+    tb.visits += 1;
+  }
+
+  // back-propagation through a selected entry: ReleasePending + UpdateStatistic in one step
+  // (count + pending is unchanged, so the cached square root stays)
+  void BackupEntry(int h, int idx, double collected_ego_cost, double child_latest_ego_cost) {
+    Table& tb = tables_[h];
+    Entry& e = tb.cold[idx];
+    if (!e.pending || e.dead) {  // not the common case: fall back to the two plain steps
+      ReleasePending(h, idx);
+      UpdateStatistic(h, idx, collected_ego_cost, child_latest_ego_cost);
+      return;
+    }
+    e.pending--;
+    if (tb.pending) tb.pending--;
+    latest_ego_cost_ = collected_ego_cost + gamma_ * child_latest_ego_cost;
+    e.count += 1;
+    Hot& t = tb.hot[idx];
+    t.ego_cost += (latest_ego_cost_ - t.ego_cost) / e.count;
+    tb.visits += 1;
   }
 
   double latest_ego_cost() const { return latest_ego_cost_; }
-  const std::vector<Entry>& table(int h) const { return per_hyp_[h]; }
-  int num_hypotheses() const { return (int)per_hyp_.size(); }
+  const std::vector<Entry>& table(int h) const { return tables_[h].cold; }
+  double ego_cost(int h, int idx) const { return tables_[h].hot[idx].ego_cost; }
+  int num_hypotheses() const { return (int)tables_.size(); }
   int NumExpandedActions() const {  // distinct resolved actions over all hypotheses
     std::vector<ActionKey> keys;
-    for (const auto& tab : per_hyp_)
-      for (const Entry& e : tab)
+    for (const Table& t : tables_)
+      for (const Entry& e : t.cold)
         if (e.resolved) keys.push_back(e.key);
     std::sort(keys.begin(), keys.end());
     return (int)(std::unique(keys.begin(), keys.end()) - keys.begin());
   }
 
  private:
-  std::vector<std::vector<Entry>> per_hyp_;
-  std::vector<unsigned> visits_, pending_;
+  static void SetN(Hot& t, uint32_t n) {
+    t.n = n;
+    // a live entry nobody has tried or is trying comes first, as in UCB1
+    t.inv_sqrt_n = n ? 1.0f / std::sqrt((float)n) : 1.0e30f;
+  }
+
+  std::vector<Table> tables_;
   double k_ = 4, alpha_ = 0.25, lo_ = 0, hi_ = 1, c_ = 0.7, gamma_ = 0.9;
   bool hyp_based_ = true, cost_based_ = false;
   double latest_ego_cost_ = 0.0;
   double widen_cache_n_ = -1.0, widen_cache_v_ = 0.0;
-  unsigned dead_ = 0;
 };
 
 // --------------------------------------------------------- CostConstrainedStatistic
@@ -393,7 +470,7 @@ class CostConstrainedStatistic {
         // restricted to the actions not tried yet
         double tot = 0.0;
         for (int u : unexpanded_) tot += explore_policy_[u];
-        double r = std::generate_canonical<double, 53>(gen) * tot;
+        double r = Uniform01(gen) * tot;
         i = unexpanded_.size() - 1;
         for (size_t k = 0; k < unexpanded_.size(); ++k) {
           r -= explore_policy_[unexpanded_[k]];
@@ -407,7 +484,7 @@ class CostConstrainedStatistic {
       a = unexpanded_[i];
       unexpanded_.erase(unexpanded_.begin() + i);
     } else {
-      a = GreedyPolicy(kappa_, filter_, lambdas, gen).first;
+      a = GreedyAction(kappa_, filter_, lambdas, gen);
       auto it = std::find(unexpanded_.begin(), unexpanded_.end(), a);
       if (it != unexpanded_.end()) unexpanded_.erase(it);
     }
@@ -423,15 +500,23 @@ class CostConstrainedStatistic {
 
   // greedy_policy(kappa, action_filter_factor): near-optimal action set under the
   // Lagrangian value, then the stochastic mix that meets the first cost constraint
-  // (closed form of the two-action LP the reference solves with OR-tools)
-  std::pair<int, Policy> GreedyPolicy(double kappa, double filter,
-                                      const std::vector<double>& lambdas, std::mt19937& gen) const {
+  // (closed form of the two-action LP the reference solves with OR-tools).
+  // The result as numbers: the sampled action and the (at most two-point) policy behind it.
+  struct Greedy {
+    int action = 0;
+    int a_star = -1, a_min = -1;  // policy: p_min on a_min, the rest on a_star; a_star < 0: uniform
+    double p_min = 0.0;
+  };
+  Greedy GreedyCore(double kappa, double filter, const std::vector<double>& lambdas,
+                    std::mt19937& gen) const {
     const int n = num_actions();
     const double n_total = std::max(2.0, (double)(reward_.total_visits() + total_pending_));
-    std::vector<double> lag(n, -std::numeric_limits<double>::infinity()), ucb(n, lag[0]);
-    std::vector<double> cnt(n, 0.0);
+    const double ninf = -std::numeric_limits<double>::infinity();
+    double ucb[BMCTS_MAX_EGO_ACTIONS], cnt[BMCTS_MAX_EGO_ACTIONS];
+    const double log_total = std::log(n_total);
     int a_star = -1;
     for (int a = 0; a < n; ++a) {
+      ucb[a] = ninf;
       cnt[a] = reward_.pairs()[a].count + pending_[a];
       if (reward_.pairs()[a].count == 0) {
         if (kappa > 0 && cnt[a] == 0) {  // never tried: explore first
@@ -443,44 +528,57 @@ class CostConstrainedStatistic {
       double v = reward_.Normalized(a);
       for (int i = 0; i < num_costs(); ++i)
         v -= (i < (int)lambdas.size() ? lambdas[i] : 0.0) * costs_[i].Normalized(a);
-      lag[a] = v;
-      ucb[a] = v + kappa * std::sqrt(std::log(n_total) / std::max(1.0, cnt[a]));
+      ucb[a] = v + kappa * std::sqrt(log_total / std::max(1.0, cnt[a]));
       if (a_star < 0 || ucb[a] > ucb[a_star]) a_star = a;
     }
-    Policy pol;
+    Greedy g;
     if (a_star < 0) {  // nothing visited yet: uniform
-      for (int a = 0; a < n; ++a) pol[(unsigned)a] = 1.0 / n;
-      std::uniform_int_distribution<int> d(0, n - 1);
-      return {d(gen), pol};
+      g.action = std::uniform_int_distribution<int>(0, n - 1)(gen);
+      return g;
     }
-    if (reward_.pairs()[a_star].count == 0) {
-      pol[(unsigned)a_star] = 1.0;
-      return {a_star, pol};
-    }
+    g.a_star = g.action = a_star;
+    if (reward_.pairs()[a_star].count == 0) return g;
     auto conf = [&](int a) { return std::sqrt(std::log(std::max(2.0, cnt[a])) / std::max(1.0, cnt[a])); };
-    std::vector<int> near;
-    for (int a = 0; a < n; ++a) {
-      if (reward_.pairs()[a].count == 0) continue;
-      if (std::fabs(ucb[a] - ucb[a_star]) <= filter * (conf(a) + conf(a_star))) near.push_back(a);
-    }
     const double c0 = constraints_.empty() ? 0.0 : constraints_[0];
     auto qc = [&](int a) { return costs_.empty() ? 0.0 : costs_[0].pairs()[a].value; };
-    if (costs_.empty() || qc(a_star) <= c0 || near.size() < 2) {
-      pol[(unsigned)a_star] = 1.0;
-      return {a_star, pol};
+    if (costs_.empty() || qc(a_star) <= c0) return g;
+    // cheapest action (first cost channel) among the near-optimal ones
+    const double conf_star = conf(a_star);
+    int n_near = 0, a_min = -1;
+    for (int a = 0; a < n; ++a) {
+      if (reward_.pairs()[a].count == 0) continue;
+      if (std::fabs(ucb[a] - ucb[a_star]) <= filter * (conf(a) + conf_star)) {
+        n_near++;
+        if (a_min < 0 || qc(a) < qc(a_min)) a_min = a;
+      }
     }
-    int a_min = near[0];
-    for (int a : near)
-      if (qc(a) < qc(a_min)) a_min = a;
+    if (n_near < 2) return g;
     if (a_min == a_star || qc(a_min) >= c0) {
-      pol[(unsigned)a_min] = 1.0;
-      return {a_min, pol};
+      g.a_star = g.action = a_min;
+      return g;
     }
-    const double p_min = (qc(a_star) - c0) / (qc(a_star) - qc(a_min));
-    pol[(unsigned)a_min] = p_min;
-    pol[(unsigned)a_star] = 1.0 - p_min;
-    std::uniform_real_distribution<double> u(0.0, 1.0);
-    return {u(gen) < p_min ? a_min : a_star, pol};
+    g.a_min = a_min;
+    g.p_min = (qc(a_star) - c0) / (qc(a_star) - qc(a_min));
+    g.action = Uniform01(gen) < g.p_min ? a_min : a_star;
+    return g;
+  }
+  int GreedyAction(double kappa, double filter, const std::vector<double>& lambdas,
+                   std::mt19937& gen) const {
+    return GreedyCore(kappa, filter, lambdas, gen).action;
+  }
+  std::pair<int, Policy> GreedyPolicy(double kappa, double filter,
+                                      const std::vector<double>& lambdas, std::mt19937& gen) const {
+    const Greedy g = GreedyCore(kappa, filter, lambdas, gen);
+    Policy pol;
+    if (g.a_star < 0) {
+      for (int a = 0; a < num_actions(); ++a) pol[(unsigned)a] = 1.0 / num_actions();
+    } else if (g.a_min < 0) {
+      pol[(unsigned)g.a_star] = 1.0;
+    } else {
+      pol[(unsigned)g.a_min] = g.p_min;
+      pol[(unsigned)g.a_star] = 1.0 - g.p_min;
+    }
+    return {g.action, pol};
   }
 
   std::vector<double> ExpectedPolicyCost(const Policy& pol) const {
@@ -625,36 +723,81 @@ class HypothesisBeliefTracker {
     return current_;
   }
 
-  // Independent sampler of one root-parallel tree: a snapshot of the beliefs with its own
-  // generator (seed + tree index), so trees can run on different threads / ranks
-  HypothesisBeliefTracker SamplerForTree(unsigned tree_index) const {
-    HypothesisBeliefTracker t(*this);
-    t.history_.clear();
-    t.gen_.seed((unsigned)p_.RANDOM_SEED_HYPOTHESIS_SAMPLING + 7919u * tree_index);
-    return t;
-  }
+  // Root-belief sampling of one tree, laid out for the selection loop: per agent slot a
+  // cumulative belief table (or the fixed hypothesis), its own generator, no look-ups by id.
+  class SlotSampler {
+   public:
+    SlotSampler(const HypothesisBeliefTracker& t, const std::vector<AgentId>& slot_ids,
+                unsigned num_hypotheses, unsigned seed)
+        : gen_(seed), H_(std::max(1u, num_hypotheses)) {
+      slots_.resize(slot_ids.size());
+      for (size_t s = 1; s < slot_ids.size(); ++s) {
+        Slot& sl = slots_[s];
+        auto f = t.fixed_.find(slot_ids[s]);
+        if (f != t.fixed_.end()) {
+          sl.fixed = (int)f->second;
+          continue;
+        }
+        auto it = t.beliefs_.find(slot_ids[s]);
+        if (it == t.beliefs_.end() || it->second.empty())
+          BuildAlias(std::vector<double>(H_, 1.0), &sl);  // no belief yet: uniform over H
+        else
+          BuildAlias(it->second, &sl);
+      }
+    }
+    void operator()(std::vector<uint8_t>* hyp) {
+      for (size_t s = 1; s < slots_.size(); ++s) {
+        const Slot& sl = slots_[s];
+        if (sl.fixed >= 0) {
+          (*hyp)[s] = (uint8_t)sl.fixed;
+          continue;
+        }
+        // alias method: one uniform draw picks a column and a side of it
+        const double u = Uniform01(gen_) * (double)sl.prob.size();
+        const size_t col = std::min((size_t)u, sl.prob.size() - 1);
+        (*hyp)[s] = (u - (double)col) < sl.prob[col] ? (uint8_t)col : sl.alias[col];
+      }
+    }
 
-  unsigned sample_for(AgentId id, unsigned num_hypotheses) {
-    auto f = fixed_.find(id);
-    if (f != fixed_.end()) return f->second;
-    auto it = beliefs_.find(id);
-    if (it == beliefs_.end() || it->second.empty()) {
-      std::uniform_int_distribution<unsigned> d(0, std::max(1u, num_hypotheses) - 1);
-      return d(gen_);
+   private:
+    struct Slot {
+      int fixed = -1;
+      std::vector<double> prob;    // alias table over the hypotheses (Vose)
+      std::vector<uint8_t> alias;
+    };
+    static void BuildAlias(const std::vector<double>& weights, Slot* sl) {
+      const size_t n = weights.size();
+      double tot = 0.0;
+      for (double w : weights) tot += w > 0.0 ? w : 0.0;
+      sl->prob.assign(n, 1.0);
+      sl->alias.resize(n);
+      std::vector<double> scaled(n);
+      std::vector<size_t> small, large;
+      for (size_t i = 0; i < n; ++i) {
+        sl->alias[i] = (uint8_t)i;
+        scaled[i] = tot > 0.0 ? std::max(0.0, weights[i]) * (double)n / tot : 1.0;
+        (scaled[i] < 1.0 ? small : large).push_back(i);
+      }
+      while (!small.empty() && !large.empty()) {
+        const size_t lo = small.back(), hi = large.back();
+        small.pop_back();
+        sl->prob[lo] = scaled[lo];
+        sl->alias[lo] = (uint8_t)hi;
+        scaled[hi] -= 1.0 - scaled[lo];
+        if (scaled[hi] < 1.0) {
+          large.pop_back();
+          small.push_back(hi);
+        }
+      }
     }
-    // one hypothesis drawn from the agent's belief (allocation free)
-    const std::vector<double>& b = it->second;
-    double tot = 0.0;
-    for (double v : b) tot += v;
-    double u = std::generate_canonical<double, 53>(gen_) * tot;
-    unsigned h = 0;
-    for (unsigned i = 0; i < b.size(); ++i) {
-      if (b[i] <= 0.0) continue;
-      h = i;
-      u -= b[i];
-      if (u < 0.0) break;
-    }
-    return h;
+    std::mt19937 gen_;
+    unsigned H_;
+    std::vector<Slot> slots_;
+  };
+  SlotSampler SamplerForSlots(const std::vector<AgentId>& slot_ids, unsigned num_hypotheses,
+                              unsigned tree_index) const {
+    return SlotSampler(*this, slot_ids, num_hypotheses,
+                       (unsigned)p_.RANDOM_SEED_HYPOTHESIS_SAMPLING + 7919u * tree_index);
   }
 
  private:
