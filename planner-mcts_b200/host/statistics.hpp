@@ -283,11 +283,11 @@ class HypothesisStatistic {
         const double explore = 2.0 * c_ * SqrtTwoLog(n_vis);
         const double inv_range = hi_ > lo_ ? 1.0 / (hi_ - lo_) : 0.0;
         for (int i = 0; i < n_tab; ++i) {
+          // (selects, not branches: where the running maximum moves is not predictable)
           const double v = (hot[i].ego_cost - lo_) * inv_range + explore * (double)hot[i].inv_sqrt_n;
-          if (v > best) {
-            best = v;
-            idx = i;
-          }
+          const bool better = v > best;
+          best = better ? v : best;
+          idx = better ? i : idx;
         }
       } else {
         // stochastic behaviour model: re-sample among the expanded actions by visit count.
