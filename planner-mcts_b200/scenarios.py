@@ -147,6 +147,29 @@ def merge_geometry(length=400.0, n_main_lanes=1, ramp_start=100.0, taper=150.0, 
     return cors, road, ramp_idx
 
 
+def curved_geometry(radius=200.0, sweep_deg=90.0, n_lanes=4, lane_w=3.5):
+    """A quarter circle at the structure limits: BMCTS_MAX_CORRIDORS lanes of
+    BMCTS_MAX_CORRIDOR_PTS points each (15 chords) and a road polygon of
+    BMCTS_MAX_ROAD_PTS points.  Lane 0 is the innermost; the road bends to the left.  No
+    axis-aligned rectangle fits this polygon, so every drivable-area test takes the scan or the
+    safe arcs of the centre lines."""
+    n = _abi.MAX_CORRIDOR_PTS
+    ang = np.radians(-90.0 + np.linspace(0.0, sweep_deg, n))
+    cors = []
+    for i in range(n_lanes):
+        r = radius + i * lane_w
+        # left of the driving direction on a left bend = towards the centre = the lower index
+        cors.append(make_corridor(list(zip(r * np.cos(ang), r * np.sin(ang))), lane_w / 2,
+                                  left=(i - 1 if i > 0 else -1),
+                                  right=(i + 1 if i + 1 < n_lanes else -1)))
+    r_in, r_out = radius - lane_w / 2, radius + (n_lanes - 0.5) * lane_w
+    m = _abi.MAX_ROAD_PTS // 2
+    edge = np.radians(-90.0 + np.linspace(0.0, sweep_deg, m))
+    road = list(zip(r_out * np.cos(edge), r_out * np.sin(edge))) + \
+        list(zip(r_in * np.cos(edge[::-1]), r_in * np.sin(edge[::-1])))
+    return cors, road
+
+
 # ------------------------------------------------------------------- pose helpers
 
 def pose_on_corridor(c, s):
@@ -214,7 +237,8 @@ def _base_config(state_kind, horizon):
 
 def workload(name, horizon=20, seed=1000):
     """Returns (config, scenario, meta) for one of the BASELINE.json configs:
-    'c1_highway_mdp', 'c2_merge_sbg', 'c3_merge_risk', 'c4_coop', 'c5_rsbg'."""
+    'c1_highway_mdp', 'c2_merge_sbg', 'c3_merge_risk', 'c4_coop', 'c5_rsbg' (+ the test
+    geometry 'x_curved_max')."""
     rng = np.random.default_rng(seed)
     if name == "c1_highway_mdp":
         cors, road = highway_geometry(300.0)
@@ -246,6 +270,14 @@ def workload(name, horizon=20, seed=1000):
         cfg = _base_config(_abi.STATE_COOPERATIVE, horizon)
         goal = polygon_goal([(440.0, 0.0), (500.0, 0.0), (500.0, -3.5), (440.0, -3.5)])
         lanes, ego_lane, length = [0, 1], 1, 500.0
+    elif name == "x_curved_max":
+        # not a BASELINE.json config: geometry at the structure limits for the parity tests
+        cors, road = curved_geometry()
+        A, hyps = 12, hypothesis_set(2, 2)
+        cfg = _base_config(_abi.STATE_RISK_CONSTRAINT, horizon)
+        cfg.add_safe_dist, cfg.split_safe_dist_collision = 1, 1
+        goal = frenet_goal(2, max_lat=(0.6, 0.6), max_angle=(0.15, 0.15), vel=(3.0, 30.0))
+        lanes, ego_lane, length = [0, 1, 2, 3], 1, 300.0
     else:
         raise ValueError(f"unknown workload {name}")
     scn = build_scenario(cors, road, A, hyps, ego_actions(), goal)

@@ -25,7 +25,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import oracle  # noqa: E402
 from planner_mcts_b200 import scenarios  # noqa: E402
 
-WORKLOADS = ["c1_highway_mdp", "c2_merge_sbg", "c3_merge_risk", "c4_coop", "c5_rsbg"]
+WORKLOADS = ["c1_highway_mdp", "c2_merge_sbg", "c3_merge_risk", "c4_coop", "c5_rsbg",
+             "x_curved_max"]
 SEED, STREAM, FIRST_ID = 1000, 2, 4242
 
 
@@ -60,7 +61,7 @@ def path(name):
 
 
 if __name__ == "__main__":
-    for name in WORKLOADS:
+    for name in (sys.argv[1:] or WORKLOADS):   # optionally only the named fixtures
         out = compute(name, oracle.rollout, oracle.expand_rollout)
         np.savez_compressed(path(name), **out)
         print(name, {k: v.shape for k, v in out.items()})

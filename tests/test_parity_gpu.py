@@ -13,6 +13,9 @@ from planner_mcts_b200 import RolloutEngine, _abi, scenarios
 pytestmark = pytest.mark.gpu
 
 WORKLOADS = ["c1_highway_mdp", "c2_merge_sbg", "c3_merge_risk", "c4_coop", "c5_rsbg"]
+# + a quarter circle at the structure limits (4 lanes x 16 points, 32-point road polygon, Frenet
+# goal, lane changes): projections over 15 chords, vertices, no inner rectangle
+GEOMETRIES = WORKLOADS + ["x_curved_max"]
 
 
 @pytest.fixture(params=["auto", "1", "2", "4", "8", "16"], autouse=True)
@@ -26,7 +29,7 @@ def lanes_per_rollout(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("name", ["c2_merge_sbg", "c3_merge_risk"])
+@pytest.mark.parametrize("name", ["c2_merge_sbg", "c3_merge_risk", "x_curved_max"])
 def test_rollout_parity_with_refill(name, monkeypatch):
     """a 2-block grid: every lane group pulls several rollouts from the work counter"""
     monkeypatch.setenv("BMCTS_LANE_GRID", "2")
@@ -72,7 +75,7 @@ def test_host_batch_pipeline_parity(name, monkeypatch):
     assert eng.launch_count() == 7
 
 
-@pytest.mark.parametrize("name", WORKLOADS)
+@pytest.mark.parametrize("name", GEOMETRIES)
 def test_rollout_parity(name):
     cfg, scn, meta = scenarios.workload(name, horizon=20)
     n = 96 if name != "c5_rsbg" else 64
@@ -87,7 +90,7 @@ def test_rollout_parity(name):
     assert eng.launch_count() == 1
 
 
-@pytest.mark.parametrize("name", ["c2_merge_sbg", "c3_merge_risk", "c4_coop"])
+@pytest.mark.parametrize("name", ["c2_merge_sbg", "c3_merge_risk", "c4_coop", "x_curved_max"])
 def test_step_and_expand_parity(name):
     cfg, scn, meta = scenarios.workload(name, horizon=12)
     n = 70   # ragged: not a multiple of the 32-rollout block

@@ -18,7 +18,7 @@ def _run(eng, pose, alive, hyp, **kw):
 
 @pytest.mark.parametrize("name,n", [("c2_merge_sbg", 1 << 20), ("c5_rsbg", 1 << 17),
                                     ("c4_coop", 1 << 17), ("c3_merge_risk", 1 << 17),
-                                    ("c1_highway_mdp", 1 << 17)])
+                                    ("c1_highway_mdp", 1 << 17), ("x_curved_max", 1 << 16)])
 def test_full_size_batch_properties(name, n, monkeypatch):
     cfg, scn, meta = scenarios.workload(name, horizon=20)
     pose, alive, hyp = scenarios.leaves_for(scn, meta, n, seed=21)
