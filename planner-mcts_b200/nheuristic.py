@@ -197,6 +197,10 @@ class BehaviorUCTNHeuristicRiskConstraint(BehaviorUCTRiskConstraint):
                 self._prior = self._make_prior()
             x = np.ctypeslib.as_array(obs, shape=(n, obs_dim)).copy()
             values = self._prior(x)
+            for key, v in values.items():
+                if np.shape(v) != (n, n_actions):
+                    raise ValueError(f"node prior {key!r} has shape {np.shape(v)}, the search "
+                                     f"expects ({n}, {n_actions}) = (nodes, ego actions of this world)")
             mask = 0
             if "Policy" in values:
                 np.ctypeslib.as_array(policy, shape=(n, n_actions))[:] = values["Policy"]
