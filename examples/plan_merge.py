@@ -2,8 +2,7 @@
 """Minimal use of the drop-in planner: an SBG planner (8 IDM hypotheses over the headway range)
 on the synthetic merge scenario, one Plan() per simulation step.
 
-    python examples/plan_merge.py                 # needs a B200 (no CPU fallback)
-    python examples/plan_merge.py --backend cpu   # same host search on the CPU oracle (tests)
+    python examples/plan_merge.py                 # needs a B200 (there is no CPU fallback)
 """
 import argparse
 import os
@@ -18,7 +17,6 @@ from planner_mcts_b200 import scenarios  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--backend", default="gpu", choices=["gpu", "cpu"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--iterations", type=int, default=2000)
     args = ap.parse_args()
@@ -34,12 +32,7 @@ def main():
               b + "MaxNearestAgents": meta["A"] - 1,
               b + "EgoBehavior::AccelerationInputs": [0.0, 1.0, 4.0, -1.0, -8.0]}
     hypotheses = [P.HypothesisIDM(scn.hypotheses[h], num_samples=2000) for h in range(meta["H"])]
-    if args.backend == "cpu":
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle
-        planner = oracle.make_planner(P.BehaviorUCTHypothesis, params, hypotheses)
-    else:
-        planner = P.BehaviorUCTHypothesis(params, hypotheses)
+    planner = P.BehaviorUCTHypothesis(params, hypotheses)
 
     dt = 0.2
     for step in range(args.steps):

@@ -3,8 +3,7 @@
 parameters -> hypothesis set and scenario-risk function -> BehaviorUCTRiskConstraint, optionally
 warm-started by a (here: untrained) value network evaluated on the GPU once per search wave.
 
-    python examples/risk_constrained_rsbg.py                  # needs a B200 (no CPU fallback)
-    python examples/risk_constrained_rsbg.py --backend cpu    # host search on the CPU oracle (tests)
+    python examples/risk_constrained_rsbg.py                  # needs a B200 (there is no CPU fallback)
     python examples/risk_constrained_rsbg.py --nheuristic     # + BehaviorUCTNHeuristicRiskConstraint
 """
 import argparse
@@ -24,7 +23,6 @@ from planner_mcts_b200.parameters import ParameterServer  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--backend", default="gpu", choices=["gpu", "cpu"])
     ap.add_argument("--nheuristic", action="store_true")
     ap.add_argument("--iterations", type=int, default=4000)
     ap.add_argument("--split", type=int, default=4, help="hypotheses per ranged parameter")
@@ -68,12 +66,6 @@ def main():
     world = P.ObservedWorld(ego_id=1, agents=agents, map=scn)
     base["MaxNearestAgents"] = meta["A"] - 1
 
-    kw = {}
-    if args.backend == "cpu":
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle
-        lib = oracle.planner_lib()
-        kw = dict(_lib=lib, _create=lambda kind, out: lib.oracle_planner_create(kind, out))
     if args.nheuristic:
         import torch
         n_actions = 5
@@ -81,9 +73,9 @@ def main():
                                     torch.nn.Linear(64, 3 * n_actions))
         planner = BehaviorUCTNHeuristicRiskConstraint(
             params, hypotheses, risk_function, model, None,
-            NNToValueConverterSequential(n_actions), **kw)
+            NNToValueConverterSequential(n_actions))
     else:
-        planner = P.BehaviorUCTRiskConstraint(params, hypotheses, risk_function, **kw)
+        planner = P.BehaviorUCTRiskConstraint(params, hypotheses, risk_function)
 
     for step in range(2):
         planner.Plan(0.2, world)
