@@ -19,7 +19,11 @@ import sys
 import threading
 import time
 
-import numpy as np
+# one CUDA stream per root-parallel tree: use all hardware work queues (must be set before the
+# CUDA context exists, i.e. before torch touches the device)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "tests")):
@@ -124,7 +128,8 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_index=0, trees=1):
+def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_index=0, trees=1,
+                   threads=0):
     """MCTS iterations/s of one BehaviorUCT*::Plan() on the workload's scenario (second half of
     BASELINE.json's metric).  backend 'gpu' = the product (host tree search, waves of leaves on
     the GPU); 'cpu' = the same tree search on the CPU oracle, sequential (wave 1) like the
@@ -141,7 +146,8 @@ def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_
               b + "Mcts::MaxNumNodes": max(2000, iterations), b + "Mcts::Engine::WaveSize": wave,
               b + "MaxNearestAgents": A - 1, b + "Mcts::RandomHeuristic::MaxNumIterations": horizon,
               b + "EgoBehavior::AccelerationInputs": [0.0, 1.0, 4.0, -1.0, -8.0],
-              b + "Mcts::NumParallelMcts": trees, b + "Mcts::UseMultiThreading": 1 if trees > 1 else 0}
+              b + "Mcts::NumParallelMcts": trees, b + "Mcts::UseMultiThreading": 1 if trees > 1 else 0,
+              b + "Mcts::Engine::MaxThreads": threads}
     if cfg.add_safe_dist:
         params[b + "Mcts::State::EvaluationParameters::AddSafeDist"] = 1
         params[b + "Mcts::State::SplitSafeDistCollision"] = 1
@@ -165,7 +171,8 @@ def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_
     wall = time.perf_counter() - t0
     return {"iterations_per_s": pl.last_num_iterations / wall, "iterations": pl.last_num_iterations,
             "plan_ms": wall * 1e3, "search_ms": pl.last_solution_time, "wave": wave,
-            "trees_per_process": trees, "iterations_per_tree": iterations,
+            "trees_per_process": trees, "threads_per_process": threads or (os.cpu_count() or 1),
+            "iterations_per_tree": iterations,
             "nodes": pl.last_num_nodes, "best_action": pl.last_macro_action,
             "root_stats": pl.root_stats().tolist()}
 
@@ -314,10 +321,14 @@ def run_ours(args):
     # statistics merged with an NCCL all-reduce
     plan = None
     if not args.no_plan:
+        threads = max(1, min(16, (os.cpu_count() or 1) // world))
         if args.plan_trees <= 0:
-            args.plan_trees = max(1, min(16, (os.cpu_count() or 1) // world))
+            # two trees per host thread: a thread interleaves their waves, so the GPU works on
+            # one tree while the thread selects / backs up the other
+            args.plan_trees = 2 * threads
         g = plan_benchmark(args.workload, args.horizon, args.plan_iterations, args.plan_wave, "gpu",
-                           device=local_rank, tree_index=rank, trees=args.plan_trees)
+                           device=local_rank, tree_index=rank, trees=args.plan_trees,
+                           threads=threads)
         from planner_mcts_b200 import root_parallel
         ms = torch.tensor([g["plan_ms"]], dtype=torch.float64, device=dev)
         torch.cuda.synchronize()
@@ -448,8 +459,8 @@ def main():
                          "at most 256), which keeps root values within Monte-Carlo noise of the "
                          "sequential search")
     ap.add_argument("--plan-trees", type=int, default=0,
-                    help="root-parallel trees per process (Mcts::NumParallelMcts, one host thread "
-                         "each); 0 = host threads / ranks, at most 16")
+                    help="root-parallel trees per process (Mcts::NumParallelMcts); 0 = two per host "
+                         "thread, with host threads = cores / ranks, at most 16")
     ap.add_argument("--cpu-plan-iterations", type=int, default=4000)
     args = ap.parse_args()
     if args.impl == "ours":

@@ -358,6 +358,15 @@ int bmcts_step_batch(bmcts_engine* e, const bmcts_step_in* in, const bmcts_step_
 int bmcts_expand_rollout_batch(bmcts_engine* e, const bmcts_step_in* in,
                                const bmcts_step_out* step_out, uint64_t first_rollout_id,
                                const bmcts_rollout_out* rollout_out);
+/* The same call in two halves, for a caller that drives several engines from one thread (the
+ * planners' root-parallel trees): _begin packs the host buffers, enqueues upload, kernel and
+ * download on the engine's stream and returns; _end waits for them and fills the output arrays
+ * given to _begin (which must stay valid and untouched in between).  Between the two only
+ * bmcts_last_error / bmcts_launch_count may be called on this engine.  Host buffers only. */
+int bmcts_expand_rollout_batch_begin(bmcts_engine* e, const bmcts_step_in* in,
+                                     const bmcts_step_out* step_out, uint64_t first_rollout_id,
+                                     const bmcts_rollout_out* rollout_out);
+int bmcts_expand_rollout_batch_end(bmcts_engine* e);
 /* replaces BehaviorHypothesisIDM::GetProbability for all (world, agent, hypothesis):
  * prob[(a*H + h)*n_worlds + w] */
 int bmcts_likelihood_batch(bmcts_engine* e, const bmcts_likelihood_in* in, float* prob);

@@ -152,6 +152,7 @@ EXPORTED_SYMBOLS = [
     "bmcts_config_validate", "bmcts_struct_size", "bmcts_alloc_host", "bmcts_free_host",
     "bmcts_create", "bmcts_destroy", "bmcts_set_config", "bmcts_set_scenario",
     "bmcts_rollout_batch", "bmcts_step_batch", "bmcts_expand_rollout_batch",
+    "bmcts_expand_rollout_batch_begin", "bmcts_expand_rollout_batch_end",
     "bmcts_likelihood_batch", "bmcts_sync", "bmcts_last_kernel_ms", "bmcts_launch_count",
     "bmcts_stream", "bmcts_last_error", "bmcts_status_string", "bmcts_math_probe",
 ]

@@ -234,33 +234,103 @@ void BehaviorUCTBase::DecideFromRootStats(const RootStats& merged) {
   last_num_nodes_ = (unsigned)merged.nodes;
 }
 
-RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees,
-                                    const std::function<TreeResult(long, LeafEvaluator*)>& run_tree,
+BehaviorUCTBase::TreeResult BehaviorUCTBase::CollectTree(Mcts& mcts) {
+  TreeResult r;
+  r.stats = mcts.GetRootStats();
+  r.time_ms = mcts.searchTime();
+  r.max_depth = mcts.maxTreeDepth();
+  r.root_expanded = mcts.RootExpandedActions();
+  return r;
+}
+
+RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees, const StartTree& start_tree,
+                                    const std::function<TreeResult(Mcts&)>& collect,
                                     std::vector<double>* mean_lambdas) {
   std::vector<TreeResult> results((size_t)trees);
   long n_threads = 1;
   if (mcts_parameters_.USE_MULTI_THREADING && trees > 1 && evaluator_factory_) {
     n_threads = std::min<long>(trees, std::max(1u, std::thread::hardware_concurrency()));
+    if (mcts_parameters_.MAX_THREADS > 0) n_threads = std::min(n_threads, mcts_parameters_.MAX_THREADS);
     n_threads = std::min<long>(n_threads, 64);
   }
-  if (n_threads <= 1) {
-    for (long t = 0; t < trees; ++t) results[t] = run_tree(t, evaluator_.get());
-  } else {
-    // one engine (CUDA stream + buffers) per tree thread; engines are kept between Plan() calls
-    while ((long)tree_evaluators_.size() < n_threads) tree_evaluators_.push_back(evaluator_factory_());
-    for (long i = 0; i < n_threads; ++i) {
+  // A thread keeps the waves of up to `lanes` trees in flight (one engine = one CUDA stream per
+  // tree): while the GPU rolls out the wave of one tree the thread selects / backs up another.
+  // Trees are still independent searches: what a tree computes does not depend on the schedule.
+  long lanes = 1;
+  if (evaluator_factory_ && trees > n_threads)
+    lanes = std::min<long>(kMaxTreesInFlight, (trees + n_threads - 1) / n_threads);
+  const bool own_engines = evaluator_factory_ && (n_threads > 1 || lanes > 1);
+  if (own_engines) {
+    // engines are kept between Plan() calls
+    while ((long)tree_evaluators_.size() < n_threads * lanes) tree_evaluators_.push_back(evaluator_factory_());
+    for (long i = 0; i < n_threads * lanes; ++i) {
       int st = tree_evaluators_[i]->Configure(engine_config_, sw.scenario);
       if (st != BMCTS_OK)
         throw std::runtime_error("engine configure failed: " + tree_evaluators_[i]->LastError());
     }
-    std::atomic<long> next(0);
+  }
+  std::atomic<long> next(0);
+  struct Slot {
+    long tree = -1;
+    std::unique_ptr<Mcts> mcts;
+    LeafEvaluator* evaluator = nullptr;
+  };
+  // runs trees from the shared counter on this thread's engines until none is left
+  auto worker = [&](long thread_index) {
+    std::vector<Slot> slots((size_t)lanes);
+    for (long k = 0; k < lanes; ++k)
+      slots[k].evaluator = own_engines ? tree_evaluators_[thread_index * lanes + k].get() : evaluator_.get();
+    // next tree into the slot, first wave on its way; false when no tree is left
+    auto refill = [&](Slot& s) {
+      for (;;) {
+        const long t = next.fetch_add(1);
+        if (t >= trees) {
+          s.tree = -1;
+          s.mcts.reset();
+          return false;
+        }
+        s.tree = t;
+        s.mcts = start_tree(t, s.evaluator);
+        if (!s.mcts->Done()) {
+          s.mcts->BeginWave();
+          return true;
+        }
+        s.mcts->FinishSearch();  // nothing to do (zero budget)
+        results[t] = collect(*s.mcts);
+      }
+    };
+    long active = 0;
+    try {
+      for (Slot& s : slots) active += refill(s);
+      while (active > 0) {
+        for (Slot& s : slots) {
+          if (s.tree < 0) continue;
+          s.mcts->EndWave();
+          if (!s.mcts->Done()) {
+            s.mcts->BeginWave();
+            continue;
+          }
+          s.mcts->FinishSearch();
+          results[s.tree] = collect(*s.mcts);
+          if (!refill(s)) active--;
+        }
+      }
+    } catch (...) {
+      // leave no wave in flight behind: the engines are reused by the next Plan()
+      for (Slot& s : slots)
+        if (s.evaluator) s.evaluator->EndExpandRollout();
+      throw;
+    }
+  };
+  if (n_threads <= 1) {
+    worker(0);
+  } else {
     std::vector<std::string> errors((size_t)n_threads);
     std::vector<std::thread> pool;
     for (long i = 0; i < n_threads; ++i)
       pool.emplace_back([&, i]() {
         try {
-          for (long t = next.fetch_add(1); t < trees; t = next.fetch_add(1))
-            results[t] = run_tree(t, tree_evaluators_[i].get());
+          worker(i);
         } catch (const std::exception& ex) {
           errors[i] = ex.what();
         }
@@ -365,16 +435,12 @@ Trajectory BehaviorUCTHypothesis::Plan(double min_planning_time, const ObservedW
   const long trees = std::max<long>(1, mcts_parameters_.NUM_PARALLEL_MCTS);
   RootStats merged = RunTrees(sw, trees, [&](long t, LeafEvaluator* ev) {
     const unsigned tree = tree_index_ * (unsigned)trees + (unsigned)t;
-    Mcts mcts(mcts_parameters_, EgoMode::kUct, OtherMode::kHypothesis, sw.scenario.n_agents,
-              sw.scenario.n_ego_actions, sw.scenario.n_hypotheses, 1, ev, tree);
-    mcts.Search(sw.pose, sw.alive, 1, MakeSampler(sw, tree));
-    TreeResult r;
-    r.stats = mcts.GetRootStats();
-    r.time_ms = mcts.searchTime();
-    r.max_depth = mcts.maxTreeDepth();
-    r.root_expanded = mcts.RootExpandedActions();
-    return r;
-  });
+    auto mcts = std::make_unique<Mcts>(mcts_parameters_, EgoMode::kUct, OtherMode::kHypothesis,
+                                       sw.scenario.n_agents, sw.scenario.n_ego_actions,
+                                       sw.scenario.n_hypotheses, 1, ev, tree);
+    mcts->StartSearch(sw.pose, sw.alive, 1, MakeSampler(sw, tree));
+    return mcts;
+  }, CollectTree);
   DecideFromRootStats(merged);
   FinishPlan(sw, observed_world, last_motion_idx_, min_planning_time);
   return last_trajectory_;
@@ -444,18 +510,17 @@ Trajectory BehaviorUCTRiskConstraint::Plan(double min_planning_time, const Obser
   const long trees = std::max<long>(1, mcts_parameters_.NUM_PARALLEL_MCTS);
   RootStats merged = RunTrees(sw, trees, [&](long t, LeafEvaluator* ev) {
     const unsigned tree = tree_index_ * (unsigned)trees + (unsigned)t;
-    Mcts mcts(current, EgoMode::kCostConstrained, OtherMode::kHypothesis, sw.scenario.n_agents,
-              sw.scenario.n_ego_actions, sw.scenario.n_hypotheses, n_costs, ev, tree);
-    mcts.set_cost_constraints(current_scenario_risk_);
+    auto mcts = std::make_unique<Mcts>(current, EgoMode::kCostConstrained, OtherMode::kHypothesis,
+                                       sw.scenario.n_agents, sw.scenario.n_ego_actions,
+                                       sw.scenario.n_hypotheses, n_costs, ev, tree);
+    mcts->set_cost_constraints(current_scenario_risk_);
     if (node_prior_)
-      mcts.set_node_prior(node_prior_.get(), GetObserver(&sw.scenario),
-                          (double)params_->GetInt("BehaviorUctBase::Mcts::NeuralStatistic::PriorVisits", 1));
-    mcts.Search(sw.pose, sw.alive, 1, MakeSampler(sw, tree));
-    TreeResult r;
-    r.stats = mcts.GetRootStats();
-    r.time_ms = mcts.searchTime();
-    r.max_depth = mcts.maxTreeDepth();
-    r.root_expanded = mcts.RootExpandedActions();
+      mcts->set_node_prior(node_prior_.get(), GetObserver(&sw.scenario),
+                           (double)params_->GetInt("BehaviorUctBase::Mcts::NeuralStatistic::PriorVisits", 1));
+    mcts->StartSearch(sw.pose, sw.alive, 1, MakeSampler(sw, tree));
+    return mcts;
+  }, [n_costs](Mcts& mcts) {
+    TreeResult r = CollectTree(mcts);
     r.lambdas = mcts.lambdas();
     r.lambdas.resize(n_costs, 0.0);
     return r;
@@ -522,16 +587,11 @@ Trajectory BehaviorUCTCooperative::Plan(double min_planning_time, const Observed
   const long trees = std::max<long>(1, mcts_parameters_.NUM_PARALLEL_MCTS);
   RootStats merged = RunTrees(sw, trees, [&](long t, LeafEvaluator* ev) {
     const unsigned tree = tree_index_ * (unsigned)trees + (unsigned)t;
-    Mcts mcts(mcts_parameters_, EgoMode::kUct, OtherMode::kUct, sw.scenario.n_agents,
-              sw.scenario.n_ego_actions, 0, 1, ev, tree);
-    mcts.Search(sw.pose, sw.alive, 1, nullptr);
-    TreeResult r;
-    r.stats = mcts.GetRootStats();
-    r.time_ms = mcts.searchTime();
-    r.max_depth = mcts.maxTreeDepth();
-    r.root_expanded = mcts.RootExpandedActions();
-    return r;
-  });
+    auto mcts = std::make_unique<Mcts>(mcts_parameters_, EgoMode::kUct, OtherMode::kUct,
+                                       sw.scenario.n_agents, sw.scenario.n_ego_actions, 0, 1, ev, tree);
+    mcts->StartSearch(sw.pose, sw.alive, 1, nullptr);
+    return mcts;
+  }, CollectTree);
   DecideFromRootStats(merged);
   FinishPlan(sw, observed_world, last_motion_idx_, min_planning_time);
   return last_trajectory_;

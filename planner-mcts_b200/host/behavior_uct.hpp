@@ -119,9 +119,14 @@ class BehaviorUCTBase : public UctBaseDebugInfos {
     std::vector<double> lambdas;
   };
   // runs `trees` independent searches (Mcts::NumParallelMcts) -- on threads with one engine
-  // each when Mcts::UseMultiThreading is set -- and merges their root statistics in tree order
-  RootStats RunTrees(const SearchWorld& sw, long trees,
-                     const std::function<TreeResult(long, LeafEvaluator*)>& run_tree,
+  // each when Mcts::UseMultiThreading is set, and with the waves of several trees in flight per
+  // thread when there are more trees than threads -- and merges their root statistics in tree
+  // order.  start_tree builds the search of tree t on the given engine and calls StartSearch.
+  using StartTree = std::function<std::unique_ptr<Mcts>(long, LeafEvaluator*)>;
+  static constexpr long kMaxTreesInFlight = 8;
+  static TreeResult CollectTree(Mcts& mcts);
+  RootStats RunTrees(const SearchWorld& sw, long trees, const StartTree& start_tree,
+                     const std::function<TreeResult(Mcts&)>& collect,
                      std::vector<double>* mean_lambdas = nullptr);
 
   ParamsPtr params_;

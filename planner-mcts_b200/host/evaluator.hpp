@@ -61,12 +61,28 @@ class LeafEvaluator {
   // expansion step with explicit joint actions, then a rollout from every non-terminal child
   virtual int ExpandRollout(WaveBuffers& w, uint64_t seed, uint32_t stream,
                             uint64_t first_rollout_id) = 0;
+  // The same in two halves, so that one thread can keep the waves of several trees in flight:
+  // Begin enqueues the work and returns, End waits for it and fills the wave's outputs.  The
+  // default runs the batch inside Begin.
+  virtual int BeginExpandRollout(WaveBuffers& w, uint64_t seed, uint32_t stream,
+                                 uint64_t first_rollout_id) {
+    deferred_status_ = ExpandRollout(w, seed, stream, first_rollout_id);
+    return BMCTS_OK;
+  }
+  virtual int EndExpandRollout() {
+    const int st = deferred_status_;
+    deferred_status_ = BMCTS_OK;
+    return st;
+  }
   // P(action | hypothesis) for every (agent, hypothesis) of one world: prob[a*H + h]
   virtual int Likelihood(const std::vector<float>& pose, uint32_t alive,
                          const std::vector<float>& action, int n_samples, int n_buckets,
                          float lower, float upper, uint64_t seed, std::vector<float>* prob) = 0;
   virtual uint64_t LaunchCount() const = 0;
   virtual std::string LastError() const = 0;
+
+ private:
+  int deferred_status_ = BMCTS_OK;
 };
 
 // Product factory: the CUDA engine on `device`.  Throws std::runtime_error when the

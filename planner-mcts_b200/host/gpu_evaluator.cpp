@@ -32,6 +32,16 @@ class GpuLeafEvaluator : public LeafEvaluator {
 
   int ExpandRollout(WaveBuffers& w, uint64_t seed, uint32_t stream,
                     uint64_t first_rollout_id) override {
+    return Submit(w, seed, stream, first_rollout_id, false);
+  }
+  int BeginExpandRollout(WaveBuffers& w, uint64_t seed, uint32_t stream,
+                         uint64_t first_rollout_id) override {
+    return Submit(w, seed, stream, first_rollout_id, true);
+  }
+  int EndExpandRollout() override { return bmcts_expand_rollout_batch_end(engine_); }
+
+  int Submit(WaveBuffers& w, uint64_t seed, uint32_t stream, uint64_t first_rollout_id,
+             bool async) {
     bmcts_step_in in{};
     in.n = w.n;
     in.memory = BMCTS_MEM_HOST;
@@ -53,7 +63,8 @@ class GpuLeafEvaluator : public LeafEvaluator {
     bmcts_rollout_out ro{};
     ro.result = w.result.data();
     ro.ret_agents = w.ret_agents.data();
-    return bmcts_expand_rollout_batch(engine_, &in, &so, first_rollout_id, &ro);
+    return async ? bmcts_expand_rollout_batch_begin(engine_, &in, &so, first_rollout_id, &ro)
+                 : bmcts_expand_rollout_batch(engine_, &in, &so, first_rollout_id, &ro);
   }
 
   int Likelihood(const std::vector<float>& pose, uint32_t alive, const std::vector<float>& action,

@@ -135,8 +135,22 @@ class Mcts {
 
   void Search(const std::vector<float>& root_pose, uint32_t root_alive, unsigned root_depth,
               const HypothesisSampler& sample_hypotheses) {
-    using clock = std::chrono::steady_clock;
-    const auto t0 = clock::now();
+    StartSearch(root_pose, root_alive, root_depth, sample_hypotheses);
+    while (!Done()) {
+      BeginWave();
+      EndWave();
+    }
+    FinishSearch();
+  }
+
+  // The search in steps, for a driver that keeps the waves of several trees in flight from one
+  // thread (BehaviorUCTBase::RunTrees): StartSearch, then BeginWave / EndWave until Done(),
+  // then FinishSearch.  BeginWave selects a wave and hands it to the engine without waiting;
+  // EndWave waits for the engine and backs the results up.
+  void StartSearch(const std::vector<float>& root_pose, uint32_t root_alive, unsigned root_depth,
+                   const HypothesisSampler& sample_hypotheses) {
+    t_start_ = std::chrono::steady_clock::now();
+    sampler_ = sample_hypotheses;
     nodes_.clear();
     awaiting_prior_.clear();
     cc_params_ = p_;
@@ -147,16 +161,22 @@ class Mcts {
     t_select_ = t_fill_ = t_engine_ = t_backup_ = 0.0;
     iterations_ = 0;
     max_tree_depth_ = 0;
-    const long wave = p_.WAVE_SIZE > 0
-                          ? p_.WAVE_SIZE
-                          : std::min<long>(256, std::max<long>(1, p_.MAX_NUMBER_OF_ITERATIONS / 128));
-    while (iterations_ < p_.MAX_NUMBER_OF_ITERATIONS) {
-      const double ms = std::chrono::duration<double, std::milli>(clock::now() - t0).count();
-      if (iterations_ > 0 && ms > (double)p_.MAX_SEARCH_TIME) break;
-      const int w = (int)std::min<long>(wave, p_.MAX_NUMBER_OF_ITERATIONS - iterations_);
-      RunWave(w, sample_hypotheses);
-    }
-    search_time_ms_ = std::chrono::duration<double, std::milli>(clock::now() - t0).count();
+    wave_in_flight_ = 0;
+    wave_size_ = p_.WAVE_SIZE > 0
+                     ? p_.WAVE_SIZE
+                     : std::min<long>(256, std::max<long>(1, p_.MAX_NUMBER_OF_ITERATIONS / 128));
+  }
+
+  bool Done() const {
+    if (iterations_ >= p_.MAX_NUMBER_OF_ITERATIONS) return true;
+    const double ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start_).count();
+    return iterations_ > 0 && ms > (double)p_.MAX_SEARCH_TIME;
+  }
+
+  void FinishSearch() {
+    search_time_ms_ =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start_).count();
     if (std::getenv("BMCTS_DEBUG"))
       std::fprintf(stderr, "[bmcts] search %.2f ms: select %.2f, fill %.2f, engine %.2f, backup %.2f (%ld iterations, %zu nodes)\n",
                    search_time_ms_, t_select_, t_fill_, t_engine_, t_backup_, iterations_, nodes_.size());
@@ -337,11 +357,16 @@ class Mcts {
     }
   }
 
-  void RunWave(int w, const HypothesisSampler& sample_hypotheses) {
-    using clock = std::chrono::steady_clock;
-    auto ms = [](clock::time_point a, clock::time_point b) {
-      return std::chrono::duration<double, std::milli>(b - a).count();
-    };
+  using clock = std::chrono::steady_clock;
+  static double Ms(clock::time_point a, clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  }
+
+ public:
+  void BeginWave() {
+    const HypothesisSampler& sample_hypotheses = sampler_;
+    const int w = (int)std::min<long>(wave_size_, p_.MAX_NUMBER_OF_ITERATIONS - iterations_);
+    auto ms = Ms;
     const auto t0 = clock::now();
     std::vector<Selection>& sels = sels_;
     if ((int)sels.size() < w) sels.resize(w);
@@ -380,7 +405,24 @@ class Mcts {
       t_fill_ += ms(t1, t2);
       const uint64_t first_id = rollout_counter_;
       rollout_counter_ += (uint64_t)n_engine;
-      int stc = eval_->ExpandRollout(wave_, p_.RANDOM_SEED, tree_index_, first_id);
+      int stc = eval_->BeginExpandRollout(wave_, p_.RANDOM_SEED, tree_index_, first_id);
+      if (stc != BMCTS_OK)
+        throw std::runtime_error("rollout engine failed: " + eval_->LastError());
+      t_engine_ += ms(t2, clock::now());
+    }
+    wave_in_flight_ = w;
+    wave_engine_ = n_engine > 0;
+  }
+
+  void EndWave() {
+    const int w = wave_in_flight_;
+    wave_in_flight_ = 0;
+    std::vector<Selection>& sels = sels_;
+    std::vector<int>& slot = slot_;
+    auto ms = Ms;
+    if (wave_engine_) {
+      const auto t2 = clock::now();
+      int stc = eval_->EndExpandRollout();
       if (stc != BMCTS_OK)
         throw std::runtime_error("rollout engine failed: " + eval_->LastError());
       t_engine_ += ms(t2, clock::now());
@@ -394,6 +436,8 @@ class Mcts {
     t_backup_ += ms(t3, clock::now());
     EvaluatePriors();
   }
+
+ private:
 
   // one provider call for all nodes created since the last call
   void EvaluatePriors() {
@@ -551,6 +595,11 @@ class Mcts {
   WaveBuffers wave_;
   std::vector<Selection> sels_;
   std::vector<int> slot_;
+  HypothesisSampler sampler_;
+  std::chrono::steady_clock::time_point t_start_;
+  long wave_size_ = 1;
+  int wave_in_flight_ = 0;
+  bool wave_engine_ = false;
   long iterations_ = 0;
   int max_tree_depth_ = 0;
   double search_time_ms_ = 0.0;

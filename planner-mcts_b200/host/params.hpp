@@ -90,6 +90,9 @@ struct MctsParameters {
   // engine-side knob (not a reference key): leaves evaluated per GPU launch.  1 = the
   // reference's strictly sequential search.
   long WAVE_SIZE = 0;  // 0 = automatic: MaxNumIterations / 128, between 1 and 256
+  // engine-side knob: host threads of a multi-threaded root-parallel search (0 = all cores);
+  // with more trees than threads each thread interleaves several trees
+  long MAX_THREADS = 0;
 };
 
 // param_config/mcts_parameters_from_param_server.hpp:30-110 (keys relative to `prefix`)
@@ -171,6 +174,7 @@ inline MctsParameters MctsParametersFromParamServer(const Params& p, const std::
   // small against the iteration budget (<= 1 %) reproduce the sequential search's root values
   // within Monte-Carlo noise (tests/test_planner.py), larger ones trade bias for throughput.
   m.WAVE_SIZE = p.GetInt(k("Mcts::Engine::WaveSize"), 0);
+  m.MAX_THREADS = p.GetInt(k("Mcts::Engine::MaxThreads"), 0);
   return m;
 }
 

@@ -4,7 +4,10 @@ planner library."""
 import os
 import subprocess
 
+import pytest
+
 import oracle
+from conftest import has_gpu
 
 
 def test_cpp_planner_api():
@@ -15,11 +18,19 @@ def test_cpp_planner_api():
     assert res.stdout.strip().endswith("ok")
 
 
-def test_example_script_runs_on_the_cpu_backend():
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_gpu(), reason="needs a CUDA device")
+def test_example_scripts_run():
+    """the examples use the product path only (no CPU backend): they need the GPU"""
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, os.path.join(root, "examples", "plan_merge.py"),
-                          "--backend", "cpu", "--iterations", "200", "--steps", "2"],
+                          "--iterations", "200", "--steps", "2"],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("macro action") == 2
+    res = subprocess.run([sys.executable, os.path.join(root, "examples", "risk_constrained_rsbg.py"),
+                          "--iterations", "256", "--nheuristic"],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("expected risk") == 2 and "model evaluated" in res.stdout

@@ -6,6 +6,8 @@ belief_calculator_test.cc:91-114) re-expressed on the POD world.
 CPU tests run the host tree search on top of the CPU oracle (liboracle_planner.so); the GPU
 tests run the product (libbmcts.so) and require it to take the SAME decisions with the SAME
 statistics: leaf evaluation is bit-identical, so the two searches build the same tree."""
+import os
+
 import numpy as np
 import pytest
 
@@ -183,6 +185,32 @@ def test_multi_threaded_trees_equal_sequential_trees(make):
     assert np.array_equal(out[0][0], out[1][0])
     assert out[0][1:] == out[1][1:]
     assert out[0][2] == 4 * 300
+
+
+@pytest.mark.parametrize("make", BACKENDS)
+def test_more_trees_than_threads_are_interleaved_without_changing_them(make):
+    """with more trees than host threads every thread keeps the waves of several trees in flight
+    (one engine per tree); each tree is still the search it would be on its own: the merged
+    statistics equal the sum over single-tree planners with the same tree indices"""
+    world = W.observed_world(2, 4.0, 6.0, 3.0, goal_center=(150.0, -1.75))
+    trees = 3 * (os.cpu_count() or 1) + 1
+    params = W.base_params(96)
+    params[P0 + "Mcts::Engine::WaveSize"] = 16
+    many = dict(params)
+    many[P0 + "Mcts::NumParallelMcts"] = trees
+    many[P0 + "Mcts::UseMultiThreading"] = 1
+    pl = make(P.BehaviorUCTRiskConstraint, many, W.hypotheses())
+    pl.Plan(0.2, world)
+    assert pl.last_num_iterations == trees * 96
+    total = None
+    for t in range(trees):
+        one = make(P.BehaviorUCTRiskConstraint, params, W.hypotheses())
+        one.set_tree_index(t)
+        one.Plan(0.2, world)
+        total = one.root_stats() if total is None else total + one.root_stats()
+    np.testing.assert_allclose(pl.root_stats(), total, rtol=1e-12, atol=1e-9)
+    n_act = pl.last.num_actions
+    assert np.array_equal(pl.root_stats()[:n_act], total[:n_act])   # visit counts exactly
 
 
 @pytest.mark.gpu
