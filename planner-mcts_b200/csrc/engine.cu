@@ -161,12 +161,10 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cuda
   });
   if (attr_err != cudaSuccess) return cuda_fail(e, attr_err, "cudaFuncSetAttribute");
   // geometry per (variant, scenario size, batch class): occupancy queries are cached
-  const long full = 1L << 40;
   const unsigned long long key = ((unsigned long long)COOP << 60) | ((unsigned long long)T << 56) |
                                  ((unsigned long long)a.A << 48) | ((unsigned long long)a.C << 44) |
                                  ((unsigned long long)a.H << 36) | ((unsigned long long)force_W << 28) |
                                  (unsigned long long)std::min<long>(need_warps, (1L << 28) - 1);
-  (void)full;
   LaneGeometry g;
   auto it = e->geometry.find(key);
   if (it != e->geometry.end()) {

@@ -6,6 +6,7 @@
 #include <thread>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -247,6 +248,7 @@ RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees, const Sta
                                     const std::function<TreeResult(Mcts&)>& collect,
                                     std::vector<double>* mean_lambdas) {
   std::vector<TreeResult> results((size_t)trees);
+  const auto t_begin = std::chrono::steady_clock::now();
   long n_threads = 1;
   if (mcts_parameters_.USE_MULTI_THREADING && trees > 1 && evaluator_factory_) {
     n_threads = std::min<long>(trees, std::max(1u, std::thread::hardware_concurrency()));
@@ -341,11 +343,12 @@ RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees, const Sta
   }
   RootStats merged;
   merged.Resize(sw.scenario.n_ego_actions);
-  double time_ms = 0.0;
+  // trees overlap in time (threads, interleaved waves): the solution time is the wall clock
+  const double time_ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   if (mean_lambdas) mean_lambdas->clear();
   for (long t = 0; t < trees; ++t) {  // merge_node_statistics, in tree order (deterministic)
     merged.Add(results[t].stats);
-    time_ms = n_threads > 1 ? std::max(time_ms, results[t].time_ms) : time_ms + results[t].time_ms;
     if (mean_lambdas) {  // merge_mcts_parameters: mean lambda
       if (mean_lambdas->size() < results[t].lambdas.size()) mean_lambdas->resize(results[t].lambdas.size(), 0.0);
       for (size_t i = 0; i < results[t].lambdas.size(); ++i)
