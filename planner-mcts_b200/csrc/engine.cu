@@ -502,6 +502,7 @@ struct Pack {
   };
   std::vector<Item> items;
   size_t bytes = 0;
+  bool rewritten = false;  // an output the kernel writes more than once is part of the block
   static constexpr size_t kNone = ~size_t(0);
   size_t add(const void* src, void* dst, size_t n) {
     if (!src && !dst) return kNone;
@@ -531,8 +532,11 @@ constexpr size_t kPackLimit = 48u << 20;  // larger host batches keep the per-ar
 // 2000-iteration Plan() in waves of 15 leaves; no gain from 256-leaf waves on, hence the limit.
 constexpr size_t kZeroCopyLimit = 64u << 10;
 
+// (not when final poses are asked for: the kernel rewrites them at every step, which is cheap in
+// device memory and would be a stream of small PCIe writes in host memory)
 bool pack_zero_copy(const Pack& pin, const Pack& pout) {
-  return pin.bytes + pout.bytes <= kZeroCopyLimit && !std::getenv("BMCTS_NO_ZERO_COPY");
+  return pin.bytes + pout.bytes <= kZeroCopyLimit && !pout.rewritten &&
+         !std::getenv("BMCTS_NO_ZERO_COPY");
 }
 
 // stages the packed inputs (and uploads them unless the wave is small enough for zero copy);
@@ -781,6 +785,7 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
     const size_t o_res = pout.add(nullptr, out->result, sizeof(bmcts_rollout_result) * (size_t)n);
     const size_t o_ra = pout.add(nullptr, out->ret_agents, sizeof(float) * nA);
     const size_t o_fp = pout.add(nullptr, out->final_pose, sizeof(float) * 4 * nA);
+    pout.rewritten = out->final_pose != nullptr;
     if (pin.bytes + pout.bytes <= kPackLimit) {
       char *di, *dout;
       if ((st = pack_upload(e, pin, pout, &di, &dout))) return st;
@@ -883,6 +888,7 @@ static int step_common(bmcts_engine* e, const bmcts_step_in* in, const bmcts_ste
     const size_t o_res = pout.add(nullptr, ro ? ro->result : nullptr, sizeof(bmcts_rollout_result) * (size_t)n);
     const size_t o_ra = pout.add(nullptr, ro ? ro->ret_agents : nullptr, sizeof(float) * nA);
     const size_t o_fp = pout.add(nullptr, ro ? ro->final_pose : nullptr, sizeof(float) * 4 * nA);
+    pout.rewritten = ro && ro->final_pose != nullptr;
     if (pin.bytes + pout.bytes <= kPackLimit) {
       char *di, *dout;
       if ((st = pack_upload(e, pin, pout, &di, &dout))) return st;
