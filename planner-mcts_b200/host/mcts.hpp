@@ -100,7 +100,7 @@ struct Node {
   Node* parent = nullptr;
   unsigned state_depth = 1;  // MctsStateBase::depth_
   int tree_depth = 0;
-  std::vector<float> pose;   // [A][4]
+  float* pose = nullptr;     // [A][4], in the search's pose arena
   uint32_t alive = 0;
   bool terminal = false;
   bool stats_ready = false;  // action tables built (first time the node is selected through)
@@ -113,7 +113,10 @@ struct Node {
   double latest_cost_other = 0.0;
   std::vector<double> latest_ret_other;
   std::unordered_map<JointKey, Node*, JointKeyHash> children;
-  std::vector<double> edge_reward;  // rewards[] of the execute() that created this node
+  // rewards[] of the execute() that created this node: the ego's, and (cooperative states
+  // only: nobody else reads them) every agent's
+  double edge_reward_ego = 0.0;
+  std::vector<double> edge_reward;
   double edge_cost[2] = {0.0, 0.0};
   std::unique_ptr<NodePrior> prior;  // neural warm start of the ego statistic (node_prior.hpp)
 };
@@ -151,7 +154,9 @@ class Mcts {
                    const HypothesisSampler& sample_hypotheses) {
     t_start_ = std::chrono::steady_clock::now();
     sampler_ = sample_hypotheses;
-    nodes_.clear();
+    node_chunks_.clear();
+    pose_chunks_.clear();
+    n_nodes_ = 0;
     awaiting_prior_.clear();
     cc_params_ = p_;
     cc_params_.cost_constrained_statistic.COST_CONSTRAINTS = constraints_;
@@ -179,7 +184,7 @@ class Mcts {
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start_).count();
     if (std::getenv("BMCTS_DEBUG"))
       std::fprintf(stderr, "[bmcts] search %.2f ms: select %.2f, fill %.2f, engine %.2f, backup %.2f (%ld iterations, %zu nodes)\n",
-                   search_time_ms_, t_select_, t_fill_, t_engine_, t_backup_, iterations_, nodes_.size());
+                   search_time_ms_, t_select_, t_fill_, t_engine_, t_backup_, iterations_, n_nodes_);
   }
 
   RootStats GetRootStats() const {
@@ -196,12 +201,12 @@ class Mcts {
       }
     }
     s.iterations = (double)iterations_;
-    s.nodes = (double)nodes_.size();
+    s.nodes = (double)n_nodes_;
     return s;
   }
 
   long numIterations() const { return iterations_; }
-  size_t numNodes() const { return nodes_.size(); }
+  size_t numNodes() const { return n_nodes_; }
   double searchTime() const { return search_time_ms_; }
   int maxTreeDepth() const { return max_tree_depth_; }
   const Node& get_root() const { return *root_; }
@@ -248,20 +253,23 @@ class Mcts {
 
   Node* NewNode(Node* parent, const std::vector<float>* pose, uint32_t alive, unsigned state_depth,
                 bool terminal) {
-    nodes_.emplace_back(new Node());
-    Node* n = nodes_.back().get();
+    // nodes and their poses come from chunked arenas: one allocation per 256 nodes
+    const size_t slot = n_nodes_ % kChunk;
+    if (slot == 0) {
+      node_chunks_.emplace_back(new Node[kChunk]);
+      pose_chunks_.emplace_back(new float[kChunk * (size_t)A_ * 4]);
+    }
+    Node* n = &node_chunks_.back()[slot];
+    n->pose = &pose_chunks_.back()[slot * (size_t)A_ * 4];
+    n_nodes_++;
     n->parent = parent;
     n->tree_depth = parent ? parent->tree_depth + 1 : 0;
     max_tree_depth_ = std::max(max_tree_depth_, n->tree_depth);
     n->state_depth = state_depth;
-    if (pose)
-      n->pose = *pose;
-    else
-      n->pose.resize((size_t)A_ * 4);  // filled by the caller
+    if (pose) std::copy(pose->begin(), pose->begin() + (size_t)A_ * 4, n->pose);  // else: the caller fills it
     n->alive = alive;
     n->terminal = terminal;
-    // rewards of the other agents are only read by the cooperative (joint UCT) statistics
-    n->edge_reward.assign(other_mode_ == OtherMode::kUct ? A_ : 1, 0.0);
+    if (other_mode_ == OtherMode::kUct) n->edge_reward.assign(A_, 0.0);
     // Most nodes are leaves that only ever receive one heuristic estimate: the statistics
     // objects exist (they hold the latest return / cost), their action tables do not yet.
     if (ego_mode_ == EgoMode::kCostConstrained) n->ego_cc.InitLight(n_costs_);
@@ -445,7 +453,7 @@ class Mcts {
     const int n = (int)awaiting_prior_.size(), d = observer_.observation_size();
     obs_.assign((size_t)n * d, 0.0f);
     for (int i = 0; i < n; ++i)
-      observer_.Observe(awaiting_prior_[i]->pose.data(), awaiting_prior_[i]->alive, A_,
+      observer_.Observe(awaiting_prior_[i]->pose, awaiting_prior_[i]->alive, A_,
                         obs_.data() + (size_t)i * d);
     for (auto* v : {&pr_policy_, &pr_ret_, &pr_env_, &pr_col_}) v->assign((size_t)n * n_actions_, 0.0f);
     const int mask = prior_->Evaluate(n, d, obs_.data(), n_actions_, pr_policy_.data(),
@@ -504,7 +512,7 @@ class Mcts {
         }
       }
       // one hash of the joint action: look up, and claim the slot if it is new
-      const bool link = (long)nodes_.size() < p_.MAX_NUMBER_OF_NODES;
+      const bool link = (long)n_nodes_ < p_.MAX_NUMBER_OF_NODES;
       auto it = link ? parent->children.try_emplace(joint, nullptr).first : parent->children.find(joint);
       if (it != parent->children.end() && it->second) {
         leaf = it->second;  // same joint action expanded earlier (in this wave or by value merge)
@@ -513,6 +521,7 @@ class Mcts {
         leaf = NewNode(parent, nullptr, wave_.next_alive[k], parent->state_depth + 1, terminal);
         for (int a = 0; a < A_; ++a)
           for (int f = 0; f < 4; ++f) leaf->pose[(size_t)a * 4 + f] = wave_.next_pose[wave_.at(a, k) * 4 + f];
+        leaf->edge_reward_ego = wave_.reward[wave_.at(0, k)];
         for (size_t a = 0; a < leaf->edge_reward.size(); ++a) leaf->edge_reward[a] = wave_.reward[wave_.at((int)a, k)];
         leaf->edge_cost[0] = wave_.cost[k];
         leaf->edge_cost[1] = wave_.cost[(size_t)wave_.n + k];
@@ -534,10 +543,10 @@ class Mcts {
       Node* n = st.node;
       if (ego_mode_ == EgoMode::kUct) {
         n->ego_uct.ReleasePending(st.ego_action);
-        n->ego_uct.UpdateStatistic(st.ego_action, child->edge_reward[0], child->ego_uct.latest_return());
+        n->ego_uct.UpdateStatistic(st.ego_action, child->edge_reward_ego, child->ego_uct.latest_return());
       } else {
         n->ego_cc.ReleasePending(st.ego_action);
-        n->ego_cc.UpdateStatistic(st.ego_action, child->edge_reward[0], child->edge_cost, child->ego_cc);
+        n->ego_cc.UpdateStatistic(st.ego_action, child->edge_reward_ego, child->edge_cost, child->ego_cc);
       }
       for (int s = 1; s < A_; ++s) {
         if (st.other_idx[s] < 0) continue;
@@ -590,7 +599,10 @@ class Mcts {
   unsigned tree_index_;
   std::mt19937 gen_;
   std::vector<double> lambdas_, constraints_;
-  std::vector<std::unique_ptr<Node>> nodes_;
+  static constexpr size_t kChunk = 256;
+  std::vector<std::unique_ptr<Node[]>> node_chunks_;
+  std::vector<std::unique_ptr<float[]>> pose_chunks_;
+  size_t n_nodes_ = 0;
   Node* root_ = nullptr;
   WaveBuffers wave_;
   std::vector<Selection> sels_;

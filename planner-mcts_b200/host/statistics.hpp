@@ -425,8 +425,8 @@ class CostConstrainedStatistic {
     reward_.Init(num_actions, c.REWARD_LOWER_BOUND, c.REWARD_UPPER_BOUND, 0.0, m.DISCOUNT_FACTOR,
                  false);
     InitLight(num_costs);  // keeps heuristic values set before the tables were needed
-    for (auto& s : costs_)
-      s.Init(num_actions, c.COST_LOWER_BOUND, c.COST_UPPER_BOUND, 0.0, m.DISCOUNT_FACTOR, false);
+    for (int i = 0; i < n_costs_; ++i)
+      costs_[i].Init(num_actions, c.COST_LOWER_BOUND, c.COST_UPPER_BOUND, 0.0, m.DISCOUNT_FACTOR, false);
     kappa_ = c.KAPPA;
     filter_ = c.ACTION_FILTER_FACTOR;
     constraints_ = c.COST_CONSTRAINTS;
@@ -442,11 +442,11 @@ class CostConstrainedStatistic {
   // what a freshly expanded node needs to receive its heuristic estimate; the action tables
   // (Init) are built when the node is first selected through
   void InitLight(int num_costs) {
-    if ((int)costs_.size() != num_costs) costs_.assign(num_costs, UctStatistic());
+    n_costs_ = std::min(num_costs, 2);
   }
 
   int num_actions() const { return reward_.num_actions(); }
-  int num_costs() const { return (int)costs_.size(); }
+  int num_costs() const { return n_costs_; }
   const UctStatistic& reward_statistic() const { return reward_; }
   const UctStatistic& cost_statistic(int i) const { return costs_[i]; }
   UctStatistic& reward_statistic() { return reward_; }
@@ -540,8 +540,8 @@ class CostConstrainedStatistic {
     if (reward_.pairs()[a_star].count == 0) return g;
     auto conf = [&](int a) { return std::sqrt(std::log(std::max(2.0, cnt[a])) / std::max(1.0, cnt[a])); };
     const double c0 = constraints_.empty() ? 0.0 : constraints_[0];
-    auto qc = [&](int a) { return costs_.empty() ? 0.0 : costs_[0].pairs()[a].value; };
-    if (costs_.empty() || qc(a_star) <= c0) return g;
+    auto qc = [&](int a) { return n_costs_ == 0 ? 0.0 : costs_[0].pairs()[a].value; };
+    if (n_costs_ == 0 || qc(a_star) <= c0) return g;
     // cheapest action (first cost channel) among the near-optimal ones
     const double conf_star = conf(a_star);
     int n_near = 0, a_min = -1;
@@ -651,7 +651,9 @@ class CostConstrainedStatistic {
 
  private:
   UctStatistic reward_;
-  std::vector<UctStatistic> costs_;
+  UctStatistic costs_[2];  // envelope / collision channel (get_num_costs() is 1 or 2): inline, a
+                           // node is created per iteration
+  int n_costs_ = 0;
   std::vector<double> constraints_;
   std::vector<std::vector<double>> step_cost_sum_;
   std::vector<unsigned> step_cost_n_;
