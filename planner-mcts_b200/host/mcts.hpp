@@ -165,7 +165,9 @@ struct Node {
   bool terminal = false;
   bool stats_ready = false;  // action tables built (first time the node is selected through)
   UctStatistic ego_uct;
-  CostConstrainedStatistic ego_cc;
+  // the ego statistic of the search's mode: ego_uct, or *ego_cc (cost-constrained searches
+  // only; lives in an arena next to the nodes -- it is 520 bytes a plain UCT search never reads)
+  CostConstrainedStatistic* ego_cc = nullptr;
   std::vector<HypothesisStatistic> other_hyp;  // per agent slot (slot 0 unused); built lazily
   std::vector<UctStatistic> other_uct;
   // latest back-propagated value seen by the other agents' statistics of this node: the ego
@@ -216,6 +218,7 @@ class Mcts {
     sampler_ = sample_hypotheses;
     node_chunks_.clear();
     pose_chunks_.clear();
+    cc_chunks_.clear();
     n_nodes_ = 0;
     awaiting_prior_.clear();
     cc_params_ = p_;
@@ -250,14 +253,14 @@ class Mcts {
   RootStats GetRootStats() const {
     RootStats s;
     s.Resize(n_actions_);
-    const UctStatistic& r = ego_mode_ == EgoMode::kUct ? root_->ego_uct : root_->ego_cc.reward_statistic();
+    const UctStatistic& r = ego_mode_ == EgoMode::kUct ? root_->ego_uct : root_->ego_cc->reward_statistic();
     for (int a = 0; a < n_actions_; ++a) {
       s.count[a] = r.pairs()[a].count;
       s.ret_sum[a] = r.pairs()[a].value * r.pairs()[a].count;
       if (ego_mode_ == EgoMode::kCostConstrained) {
-        s.cost0_sum[a] = root_->ego_cc.cost_statistic(0).pairs()[a].value * r.pairs()[a].count;
+        s.cost0_sum[a] = root_->ego_cc->cost_statistic(0).pairs()[a].value * r.pairs()[a].count;
         if (n_costs_ > 1)
-          s.cost1_sum[a] = root_->ego_cc.cost_statistic(1).pairs()[a].value * r.pairs()[a].count;
+          s.cost1_sum[a] = root_->ego_cc->cost_statistic(1).pairs()[a].value * r.pairs()[a].count;
       }
     }
     s.iterations = (double)iterations_;
@@ -284,7 +287,7 @@ class Mcts {
   std::vector<int> RootExpandedActions() const {
     std::vector<int> n(A_, 0);
     for (int a = 0; a < n_actions_; ++a) {
-      const UctStatistic& r = ego_mode_ == EgoMode::kUct ? root_->ego_uct : root_->ego_cc.reward_statistic();
+      const UctStatistic& r = ego_mode_ == EgoMode::kUct ? root_->ego_uct : root_->ego_cc->reward_statistic();
       n[0] += r.pairs()[a].count > 0;
     }
     for (int s = 1; s < A_; ++s) {
@@ -318,9 +321,12 @@ class Mcts {
     if (slot == 0) {
       node_chunks_.emplace_back(new Node[kChunk]);
       pose_chunks_.emplace_back(new float[kChunk * (size_t)A_ * 4]);
+      if (ego_mode_ == EgoMode::kCostConstrained)
+        cc_chunks_.emplace_back(new CostConstrainedStatistic[kChunk]);
     }
     Node* n = &node_chunks_.back()[slot];
     n->pose = &pose_chunks_.back()[slot * (size_t)A_ * 4];
+    if (ego_mode_ == EgoMode::kCostConstrained) n->ego_cc = &cc_chunks_.back()[slot];
     n_nodes_++;
     n->parent = parent;
     n->tree_depth = parent ? parent->tree_depth + 1 : 0;
@@ -332,7 +338,7 @@ class Mcts {
     if (other_mode_ == OtherMode::kUct) n->edge_reward.assign(A_, 0.0);
     // Most nodes are leaves that only ever receive one heuristic estimate: the statistics
     // objects exist (they hold the latest return / cost), their action tables do not yet.
-    if (ego_mode_ == EgoMode::kCostConstrained) n->ego_cc.InitLight(n_costs_);
+    if (ego_mode_ == EgoMode::kCostConstrained) n->ego_cc->InitLight(n_costs_);
     if (other_mode_ == OtherMode::kUct) n->latest_ret_other.assign(A_, 0.0);
     if (prior_ && !terminal && ego_mode_ == EgoMode::kCostConstrained) awaiting_prior_.push_back(n);
     return n;
@@ -346,11 +352,11 @@ class Mcts {
                       p_.uct_statistic.EXPLORATION_CONSTANT, p_.DISCOUNT_FACTOR,
                       p_.USE_BOUND_ESTIMATION);
     } else {
-      n->ego_cc.Init(n_actions_, n_costs_, cc_params_);
+      n->ego_cc->Init(n_actions_, n_costs_, cc_params_);
       if (n->prior) {
         const NodePrior& pr = *n->prior;
         const bool vals = (pr.mask & kPriorHasValues) != 0;
-        n->ego_cc.SetPrior((pr.mask & kPriorHasPolicy) ? pr.policy.data() : nullptr,
+        n->ego_cc->SetPrior((pr.mask & kPriorHasPolicy) ? pr.policy.data() : nullptr,
                            vals ? pr.ret.data() : nullptr, vals ? pr.envelope_risk.data() : nullptr,
                            vals ? pr.collision_risk.data() : nullptr, prior_visits_);
       }
@@ -389,7 +395,7 @@ class Mcts {
         st.other_new[s] = 0;
       }
       st.ego_action = ego_mode_ == EgoMode::kUct ? node->ego_uct.ChooseNextAction(gen_)
-                                                 : node->ego_cc.ChooseNextAction(lambdas_, gen_);
+                                                 : node->ego_cc->ChooseNextAction(lambdas_, gen_);
       JointKey joint(A_);
       joint[0] = (ActionKey)st.ego_action;
       bool all_resolved = true;
@@ -536,7 +542,7 @@ class Mcts {
     if (ego_mode_ == EgoMode::kUct)
       n->ego_uct.UpdateFromHeuristic(ret);
     else
-      n->ego_cc.UpdateFromHeuristic(ret, cost);
+      n->ego_cc->UpdateFromHeuristic(ret, cost);
     if (other_mode_ == OtherMode::kHypothesis) {
       n->latest_cost_other = cost[0];
     } else {
@@ -612,8 +618,8 @@ class Mcts {
         n->ego_uct.ReleasePending(st.ego_action);
         n->ego_uct.UpdateStatistic(st.ego_action, child->edge_reward_ego, child->ego_uct.latest_return());
       } else {
-        n->ego_cc.ReleasePending(st.ego_action);
-        n->ego_cc.UpdateStatistic(st.ego_action, child->edge_reward_ego, child->edge_cost, child->ego_cc);
+        n->ego_cc->ReleasePending(st.ego_action);
+        n->ego_cc->UpdateStatistic(st.ego_action, child->edge_reward_ego, child->edge_cost, *child->ego_cc);
       }
       for (int s = 1; s < A_; ++s) {
         if (st.other_idx[s] < 0) continue;
@@ -638,7 +644,7 @@ class Mcts {
     if (ego_mode_ == EgoMode::kUct)
       n->ego_uct.UpdateFromHeuristic(0.0);
     else
-      n->ego_cc.UpdateFromHeuristic(0.0, zero);
+      n->ego_cc->UpdateFromHeuristic(0.0, zero);
     n->latest_cost_other = 0.0;
     for (double& v : n->latest_ret_other) v = 0.0;
   }
@@ -646,13 +652,13 @@ class Mcts {
   // CostConstrainedStatistic::update_statistic_parameters: sub-gradient step on lambda
   void UpdateLambdas() {
     const auto& c = p_.cost_constrained_statistic;
-    if (root_->ego_cc.total_visits() == 0) return;
-    const int greedy = root_->ego_cc.GreedyAction(0.0, c.ACTION_FILTER_FACTOR, lambdas_, gen_);
+    if (root_->ego_cc->total_visits() == 0) return;
+    const int greedy = root_->ego_cc->GreedyAction(0.0, c.ACTION_FILTER_FACTOR, lambdas_, gen_);
     const double range = std::max(1e-9, c.COST_UPPER_BOUND - c.COST_LOWER_BOUND);
     const double lam_max = 1.0 / (std::max(1e-6, c.TAU_GRADIENT_CLIP) * std::max(1e-6, 1.0 - p_.DISCOUNT_FACTOR));
     const double step = c.GRADIENT_UPDATE_STEP / (1.0 + 0.01 * (double)iterations_);
     for (int i = 0; i < n_costs_ && i < (int)lambdas_.size(); ++i) {
-      const double q = root_->ego_cc.cost_statistic(i).pairs()[greedy].value;
+      const double q = root_->ego_cc->cost_statistic(i).pairs()[greedy].value;
       const double limit = i < (int)constraints_.size() ? constraints_[i] : 0.0;
       lambdas_[i] = std::min(lam_max, std::max(0.0, lambdas_[i] + step * (q - limit) / range));
     }
@@ -669,6 +675,7 @@ class Mcts {
   static constexpr size_t kChunk = 256;
   std::vector<std::unique_ptr<Node[]>> node_chunks_;
   std::vector<std::unique_ptr<float[]>> pose_chunks_;
+  std::vector<std::unique_ptr<CostConstrainedStatistic[]>> cc_chunks_;
   size_t n_nodes_ = 0;
   Node* root_ = nullptr;
   WaveBuffers wave_;

@@ -229,6 +229,7 @@ class HypothesisStatistic {
     std::vector<Entry> cold;
     std::vector<ActionKey> keys;  // key of a resolved live entry, else kNoKey
     unsigned visits = 0, pending = 0;
+    double widen_n = -1.0, widen_v = 0.0;  // progressive-widening threshold for widen_n actions
   };
 
   void Init(int num_hypotheses, const MctsParameters& m) {
@@ -267,12 +268,14 @@ class HypothesisStatistic {
     // n_act <= K * N^alpha  <=>  N >= (n_act / K)^(1 / alpha); the right-hand side only
     // changes when an action is added, so it is cached (pow is the most expensive call of a
     // selection step)
-    if (n_act != widen_cache_n_) {
-      widen_cache_n_ = n_act;
-      widen_cache_v_ = (k_ > 0.0 && alpha_ > 0.0) ? std::pow(n_act / k_, 1.0 / alpha_)
-                                                   : std::numeric_limits<double>::infinity();
+    // (kept per table: with hypothesis-based widening the tables of one agent differ in size,
+    // and a cache per statistic would be recomputed whenever the sampled hypothesis changes)
+    if (n_act != t.widen_n) {
+      t.widen_n = n_act;
+      t.widen_v = (k_ > 0.0 && alpha_ > 0.0) ? std::pow(n_act / k_, 1.0 / alpha_)
+                                             : std::numeric_limits<double>::infinity();
     }
-    bool widen = n_vis >= widen_cache_v_;
+    bool widen = n_vis >= t.widen_v;
     int idx = -1;
     if (!widen) {
       const int n_tab = (int)hot.size();
@@ -412,7 +415,6 @@ class HypothesisStatistic {
   double k_ = 4, alpha_ = 0.25, lo_ = 0, hi_ = 1, c_ = 0.7, gamma_ = 0.9;
   bool hyp_based_ = true, cost_based_ = false;
   double latest_ego_cost_ = 0.0;
-  double widen_cache_n_ = -1.0, widen_cache_v_ = 0.0;
 };
 
 // --------------------------------------------------------- CostConstrainedStatistic
