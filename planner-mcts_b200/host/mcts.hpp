@@ -164,10 +164,17 @@ struct Node {
   uint32_t alive = 0;
   bool terminal = false;
   bool stats_ready = false;  // action tables built (first time the node is selected through)
-  UctStatistic ego_uct;
-  // the ego statistic of the search's mode: ego_uct, or *ego_cc (cost-constrained searches
-  // only; lives in an arena next to the nodes -- it is 520 bytes a plain UCT search never reads)
-  CostConstrainedStatistic* ego_cc = nullptr;
+  // The ego statistic of the search's mode (UctStatistic or CostConstrainedStatistic) exists
+  // from the first time the node is selected through.  Until then -- for most nodes: for ever --
+  // the node only carries its heuristic estimate: the last value and how often it was set.
+  std::unique_ptr<UctStatistic> ego_uct;
+  std::unique_ptr<CostConstrainedStatistic> ego_cc;
+  double h_return = 0.0, h_cost[2] = {0.0, 0.0};
+  unsigned h_visits = 0;
+  double LatestReturn() const {
+    return ego_uct ? ego_uct->latest_return() : ego_cc ? ego_cc->latest_return() : h_return;
+  }
+  double LatestCost(int i) const { return ego_cc ? ego_cc->latest_cost(i) : h_cost[i]; }
   std::vector<HypothesisStatistic> other_hyp;  // per agent slot (slot 0 unused); built lazily
   std::vector<UctStatistic> other_uct;
   // latest back-propagated value seen by the other agents' statistics of this node: the ego
@@ -218,7 +225,6 @@ class Mcts {
     sampler_ = sample_hypotheses;
     node_chunks_.clear();
     pose_chunks_.clear();
-    cc_chunks_.clear();
     n_nodes_ = 0;
     awaiting_prior_.clear();
     cc_params_ = p_;
@@ -253,7 +259,7 @@ class Mcts {
   RootStats GetRootStats() const {
     RootStats s;
     s.Resize(n_actions_);
-    const UctStatistic& r = ego_mode_ == EgoMode::kUct ? root_->ego_uct : root_->ego_cc->reward_statistic();
+    const UctStatistic& r = ego_mode_ == EgoMode::kUct ? *root_->ego_uct : root_->ego_cc->reward_statistic();
     for (int a = 0; a < n_actions_; ++a) {
       s.count[a] = r.pairs()[a].count;
       s.ret_sum[a] = r.pairs()[a].value * r.pairs()[a].count;
@@ -287,7 +293,7 @@ class Mcts {
   std::vector<int> RootExpandedActions() const {
     std::vector<int> n(A_, 0);
     for (int a = 0; a < n_actions_; ++a) {
-      const UctStatistic& r = ego_mode_ == EgoMode::kUct ? root_->ego_uct : root_->ego_cc->reward_statistic();
+      const UctStatistic& r = ego_mode_ == EgoMode::kUct ? *root_->ego_uct : root_->ego_cc->reward_statistic();
       n[0] += r.pairs()[a].count > 0;
     }
     for (int s = 1; s < A_; ++s) {
@@ -321,12 +327,9 @@ class Mcts {
     if (slot == 0) {
       node_chunks_.emplace_back(new Node[kChunk]);
       pose_chunks_.emplace_back(new float[kChunk * (size_t)A_ * 4]);
-      if (ego_mode_ == EgoMode::kCostConstrained)
-        cc_chunks_.emplace_back(new CostConstrainedStatistic[kChunk]);
     }
     Node* n = &node_chunks_.back()[slot];
     n->pose = &pose_chunks_.back()[slot * (size_t)A_ * 4];
-    if (ego_mode_ == EgoMode::kCostConstrained) n->ego_cc = &cc_chunks_.back()[slot];
     n_nodes_++;
     n->parent = parent;
     n->tree_depth = parent ? parent->tree_depth + 1 : 0;
@@ -336,9 +339,6 @@ class Mcts {
     n->alive = alive;
     n->terminal = terminal;
     if (other_mode_ == OtherMode::kUct) n->edge_reward.assign(A_, 0.0);
-    // Most nodes are leaves that only ever receive one heuristic estimate: the statistics
-    // objects exist (they hold the latest return / cost), their action tables do not yet.
-    if (ego_mode_ == EgoMode::kCostConstrained) n->ego_cc->InitLight(n_costs_);
     if (other_mode_ == OtherMode::kUct) n->latest_ret_other.assign(A_, 0.0);
     if (prior_ && !terminal && ego_mode_ == EgoMode::kCostConstrained) awaiting_prior_.push_back(n);
     return n;
@@ -348,11 +348,15 @@ class Mcts {
     if (n->stats_ready) return;
     n->stats_ready = true;
     if (ego_mode_ == EgoMode::kUct) {
-      n->ego_uct.Init(n_actions_, p_.uct_statistic.LOWER_BOUND, p_.uct_statistic.UPPER_BOUND,
-                      p_.uct_statistic.EXPLORATION_CONSTANT, p_.DISCOUNT_FACTOR,
-                      p_.USE_BOUND_ESTIMATION);
+      n->ego_uct = std::make_unique<UctStatistic>();
+      n->ego_uct->Init(n_actions_, p_.uct_statistic.LOWER_BOUND, p_.uct_statistic.UPPER_BOUND,
+                       p_.uct_statistic.EXPLORATION_CONSTANT, p_.DISCOUNT_FACTOR,
+                       p_.USE_BOUND_ESTIMATION);
+      n->ego_uct->SeedHeuristic(n->h_return, n->h_visits);
     } else {
+      n->ego_cc = std::make_unique<CostConstrainedStatistic>();
       n->ego_cc->Init(n_actions_, n_costs_, cc_params_);
+      n->ego_cc->SeedHeuristic(n->h_return, n->h_cost, n->h_visits);
       if (n->prior) {
         const NodePrior& pr = *n->prior;
         const bool vals = (pr.mask & kPriorHasValues) != 0;
@@ -394,7 +398,7 @@ class Mcts {
         st.other_idx[s] = -1;
         st.other_new[s] = 0;
       }
-      st.ego_action = ego_mode_ == EgoMode::kUct ? node->ego_uct.ChooseNextAction(gen_)
+      st.ego_action = ego_mode_ == EgoMode::kUct ? node->ego_uct->ChooseNextAction(gen_)
                                                  : node->ego_cc->ChooseNextAction(lambdas_, gen_);
       JointKey joint(A_);
       joint[0] = (ActionKey)st.ego_action;
@@ -539,10 +543,7 @@ class Mcts {
   }
 
   void SetHeuristic(Node* n, double ret, const double* cost, const float* ret_agents, int k) {
-    if (ego_mode_ == EgoMode::kUct)
-      n->ego_uct.UpdateFromHeuristic(ret);
-    else
-      n->ego_cc->UpdateFromHeuristic(ret, cost);
+    SetEgoHeuristic(n, ret, cost);
     if (other_mode_ == OtherMode::kHypothesis) {
       n->latest_cost_other = cost[0];
     } else {
@@ -615,11 +616,13 @@ class Mcts {
       PathStep& st = sel.path[i];
       Node* n = st.node;
       if (ego_mode_ == EgoMode::kUct) {
-        n->ego_uct.ReleasePending(st.ego_action);
-        n->ego_uct.UpdateStatistic(st.ego_action, child->edge_reward_ego, child->ego_uct.latest_return());
+        n->ego_uct->ReleasePending(st.ego_action);
+        n->ego_uct->UpdateStatistic(st.ego_action, child->edge_reward_ego, child->LatestReturn());
       } else {
         n->ego_cc->ReleasePending(st.ego_action);
-        n->ego_cc->UpdateStatistic(st.ego_action, child->edge_reward_ego, child->edge_cost, *child->ego_cc);
+        const double child_cost[2] = {child->LatestCost(0), child->LatestCost(1)};
+        n->ego_cc->UpdateStatistic(st.ego_action, child->edge_reward_ego, child->edge_cost,
+                                   child->LatestReturn(), child_cost);
       }
       for (int s = 1; s < A_; ++s) {
         if (st.other_idx[s] < 0) continue;
@@ -640,11 +643,22 @@ class Mcts {
     }
   }
 
+  // NodeStatistic::update_from_heuristic of the ego statistic (plain fields while the node has none)
+  void SetEgoHeuristic(Node* n, double ret, const double* cost) {
+    if (n->ego_uct) {
+      n->ego_uct->UpdateFromHeuristic(ret);
+    } else if (n->ego_cc) {
+      n->ego_cc->UpdateFromHeuristic(ret, cost);
+    } else {
+      n->h_return = ret;
+      n->h_cost[0] = cost[0];
+      n->h_cost[1] = cost[1];
+      n->h_visits++;
+    }
+  }
+
   void SetHeuristicZero(Node* n, const double* zero) {
-    if (ego_mode_ == EgoMode::kUct)
-      n->ego_uct.UpdateFromHeuristic(0.0);
-    else
-      n->ego_cc->UpdateFromHeuristic(0.0, zero);
+    SetEgoHeuristic(n, 0.0, zero);
     n->latest_cost_other = 0.0;
     for (double& v : n->latest_ret_other) v = 0.0;
   }
@@ -675,7 +689,6 @@ class Mcts {
   static constexpr size_t kChunk = 256;
   std::vector<std::unique_ptr<Node[]>> node_chunks_;
   std::vector<std::unique_ptr<float[]>> pose_chunks_;
-  std::vector<std::unique_ptr<CostConstrainedStatistic[]>> cc_chunks_;
   size_t n_nodes_ = 0;
   Node* root_ = nullptr;
   WaveBuffers wave_;

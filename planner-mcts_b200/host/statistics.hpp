@@ -130,6 +130,14 @@ class UctStatistic {
     if (total_pending_) total_pending_--;
   }
 
+  // what `visits` heuristic updates, the last one with this value, have left behind (a node
+  // keeps its heuristic estimates in plain fields until it needs its action tables)
+  void SeedHeuristic(double heuristic_value, unsigned visits) {
+    value_ = heuristic_value;
+    latest_return_ = heuristic_value;
+    total_visits_ = visits;
+  }
+
   // mamcts update_from_heuristic
   void UpdateFromHeuristic(double heuristic_value) {
     value_ = heuristic_value;
@@ -611,11 +619,19 @@ class CostConstrainedStatistic {
     for (int i = 0; i < num_costs(); ++i) costs_[i].UpdateFromHeuristic(cost[i]);
   }
 
-  void UpdateStatistic(int action, double reward, const double* cost,
-                       const CostConstrainedStatistic& child) {
-    reward_.UpdateStatistic(action, reward, child.reward_.latest_return());
+  void SeedHeuristic(double ret, const double* cost, unsigned visits) {
+    reward_.SeedHeuristic(ret, visits);
+    for (int i = 0; i < num_costs(); ++i) costs_[i].SeedHeuristic(cost[i], visits);
+  }
+  double latest_return() const { return reward_.latest_return(); }
+  double latest_cost(int i) const { return costs_[i].latest_return(); }
+
+  // update_statistic(changed_child_statistic): the child's latest return and costs
+  void UpdateStatistic(int action, double reward, const double* cost, double child_return,
+                       const double* child_cost) {
+    reward_.UpdateStatistic(action, reward, child_return);
     for (int i = 0; i < num_costs(); ++i) {
-      costs_[i].UpdateStatistic(action, cost[i], child.costs_[i].latest_return());
+      costs_[i].UpdateStatistic(action, cost[i], child_cost[i]);
       step_cost_sum_[action][i] += cost[i];
     }
     step_cost_n_[action]++;
