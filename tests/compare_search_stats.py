@@ -4,7 +4,7 @@
 planner library must be bit-identical.
 
     git archive <old commit> | tar -x -C /tmp/old && make -C /tmp/old/oracle
-    python tools/compare_search_stats.py /tmp/old/oracle/_build/liboracle_planner.so \
+    python tests/compare_search_stats.py /tmp/old/oracle/_build/liboracle_planner.so \
         oracle/_build/liboracle_planner.so
 """
 import ctypes as C
@@ -15,7 +15,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))  # test infrastructure: uses the CPU oracle
 import oracle, planner_worlds as W
 from planner_mcts_b200 import planner as P
 def run(libpath):
