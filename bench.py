@@ -166,11 +166,15 @@ def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_
         pl = cls(params, hyp_arg, device=device) if hyp_arg is not None else cls(params, device=device)
     pl.set_tree_index(tree_index)
     pl.Plan(0.2, world)   # warm-up: buffers, first launches
-    t0 = time.perf_counter()
-    pl.Plan(0.2, world)
-    wall = time.perf_counter() - t0
+    walls = []
+    for _ in range(3 if backend == "gpu" else 1):   # median of three Plan() calls (host noise)
+        t0 = time.perf_counter()
+        pl.Plan(0.2, world)
+        walls.append(time.perf_counter() - t0)
+    wall = sorted(walls)[len(walls) // 2]
     return {"iterations_per_s": pl.last_num_iterations / wall, "iterations": pl.last_num_iterations,
-            "plan_ms": wall * 1e3, "search_ms": pl.last_solution_time, "wave": wave,
+            "plan_ms": wall * 1e3, "plan_ms_all": [round(w * 1e3, 2) for w in walls],
+            "search_ms": pl.last_solution_time, "wave": wave,
             "trees_per_process": trees, "threads_per_process": threads or (os.cpu_count() or 1),
             "iterations_per_tree": iterations,
             "nodes": pl.last_num_nodes, "best_action": pl.last_macro_action,
