@@ -121,6 +121,32 @@ int main() {
   coop.Plan(0.2, world);
   CHECK(coop.GetLastAction().acc < 0.0);
 
+  // root-belief sampling of a tree (alias tables over the beliefs): frequencies follow the
+  // beliefs, a hypothesis with belief zero is never drawn, a fixed hypothesis is kept
+  {
+    MctsParameters mp;
+    HypothesisBeliefTracker tracker(mp);
+    tracker.belief_update({{7u, {0.1, 0.6, 0.3, 0.0}}, {9u, {0.25, 0.25, 0.25, 0.25}}});
+    const std::vector<double> want = tracker.get_beliefs().at(7u);
+    CHECK(std::fabs(want[0] + want[1] + want[2] + want[3] - 1.0) < 1e-12 && want[3] == 0.0);
+    tracker.update_fixed_hypothesis_set({{9u, 2u}});
+    auto sampler = tracker.SamplerForSlots({1u, 7u, 9u, 11u}, 4, 3);  // slot 3: no belief yet
+    std::vector<uint8_t> hyp(4, 0);
+    std::vector<long> count7(4, 0), count11(4, 0);
+    const long draws = 400000;
+    for (long i = 0; i < draws; ++i) {
+      sampler(&hyp);
+      count7[hyp[1]]++;
+      CHECK(hyp[2] == 2);
+      count11[hyp[3]]++;
+    }
+    CHECK(count7[3] == 0);
+    for (int h = 0; h < 4; ++h) {
+      CHECK(std::fabs((double)count7[h] / draws - want[h]) < 0.005);
+      CHECK(std::fabs((double)count11[h] / draws - 0.25) < 0.005);  // uniform without a belief
+    }
+  }
+
   std::printf("ok\n");
   return 0;
 }
