@@ -572,7 +572,7 @@ class Mcts {
             ActionKey key = KeyOfAcceleration(wave_.last_action[wave_.at(s, k)]);
             st.other_idx[s] = parent->other_hyp[s].Resolve(h, st.other_idx[s], key);
           }
-          joint[s] = parent->other_hyp[s].table(h)[st.other_idx[s]].key;
+          joint[s] = parent->other_hyp[s].KeyOf(h, st.other_idx[s]);
         } else {
           joint[s] = (ActionKey)st.other_idx[s];
         }

@@ -401,6 +401,8 @@ class HypothesisStatistic {
 
   double latest_ego_cost() const { return latest_ego_cost_; }
   const std::vector<Entry>& table(int h) const { return tables_[h].cold; }
+  // key of a resolved live entry from the compact key array (one cache line per table)
+  ActionKey KeyOf(int h, int idx) const { return tables_[h].keys[idx]; }
   double ego_cost(int h, int idx) const { return tables_[h].hot[idx].ego_cost; }
   int num_hypotheses() const { return (int)tables_.size(); }
   int NumExpandedActions() const {  // distinct resolved actions over all hypotheses
