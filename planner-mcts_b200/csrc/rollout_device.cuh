@@ -105,6 +105,13 @@ __device__ __forceinline__ bool wait_chunk(const KernelArgs& p, uint32_t rid) {
   return false;
 }
 
+// unroll factors as build-time macros (tools/sweep_unroll.sh): a pragma does not expand macros
+#define BM_UNROLL_STR(x) #x
+#define BM_UNROLL(n) _Pragma(BM_UNROLL_STR(unroll n))
+#ifndef BMCTS_PROJECT_UNROLL
+#define BMCTS_PROJECT_UNROLL 1
+#endif
+
 struct Proj {
   float s, d;
   int seg;
@@ -118,7 +125,7 @@ __device__ __forceinline__ Proj project(const bmcts_corridor& c, float x, float 
   const int nseg = c.n_pts - 1;
   float best_d2 = kBig, best_u = 0.0f, best_raw = 0.0f, best_cross = 0.0f;
   int best = 0;
-#pragma unroll 1
+BM_UNROLL(BMCTS_PROJECT_UNROLL)
   for (int k = 0; k < nseg; ++k) {
     const float tx = c.tx[k], ty = c.ty[k];
     const float rx = x - c.px[k];

@@ -136,6 +136,13 @@ __device__ __forceinline__ bool in_rects(const float* rc, float x, float y) {
 }
 
 // IDM sub-step loop (BaseIDM::Plan, spec item 4): returns the travelled distance
+#ifndef BMCTS_EGO_UNROLL
+#define BMCTS_EGO_UNROLL 1
+#endif
+#ifndef BMCTS_IDM_UNROLL
+#define BMCTS_IDM_UNROLL 2  // tools/sweep_unroll.sh (profiles/README.md): 2 / 1 / 1 is the fastest
+#endif
+
 template <bool EXP4>
 __device__ __forceinline__ float idm_substeps(const IdmLimits& hl, const IdmParams& ip,
                                               float inv_v0, float inv_2sab, bool has_leader,
@@ -144,7 +151,7 @@ __device__ __forceinline__ float idm_substeps(const IdmLimits& hl, const IdmPara
   const float half_dt2 = (0.5f * dt) * dt;
   const uint32_t lead_mask = has_leader ? 0xffffffffu : 0u;
   float trav = 0.0f, acc = 0.0f;
-#pragma unroll 2
+BM_UNROLL(BMCTS_IDM_UNROLL)
   for (int q = 0; q < nsub; ++q) {
     const float xr = nv * inv_v0;
     const float pw = EXP4 ? ((xr * xr) * xr) * xr : bm_powi(xr, hl.exponent);
@@ -408,7 +415,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
       const float inv_wb = bm_div(1.0f, wb);
       float nx = ex, ny = ey, nth = eth, nv = ev;
       float sn = esn, cs = ecs;  // sin / cos of the current heading (published values)
-#pragma unroll 1
+BM_UNROLL(BMCTS_EGO_UNROLL)
       for (int q = 0; q < nsub; ++q) {
         const float fx = bm_fma(wb, cs, nx);
         const float fy = bm_fma(wb, sn, ny);
