@@ -202,6 +202,9 @@ def load_library(path=None):
     lib.bmcts_step_batch.argtypes = [C.c_void_p, P(StepIn), P(StepOut)]
     lib.bmcts_expand_rollout_batch.argtypes = [C.c_void_p, P(StepIn), P(StepOut), u64,
                                                P(RolloutOut)]
+    lib.bmcts_expand_rollout_batch_begin.argtypes = [C.c_void_p, P(StepIn), P(StepOut), u64,
+                                                     P(RolloutOut)]
+    lib.bmcts_expand_rollout_batch_end.argtypes = [C.c_void_p]
     lib.bmcts_likelihood_batch.argtypes = [C.c_void_p, P(LikelihoodIn), C.c_void_p]
     lib.bmcts_sync.argtypes = [C.c_void_p]
     lib.bmcts_last_kernel_ms.argtypes = [C.c_void_p, P(C.c_float)]

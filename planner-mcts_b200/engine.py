@@ -170,7 +170,8 @@ class RolloutEngine:
         return o
 
     def expand_rollout(self, pose, alive, hyp_id, action, draw_id=None, depth=None, seed=1000,
-                       stream=0, first_rollout_id=0, want_agents=False, want_final=False):
+                       stream=0, first_rollout_id=0, want_agents=False, want_final=False,
+                       _async=False):
         A = self.A
         n, pose, alive, hyp_id, depth, action, draw_id = self._step_buffers(
             pose, alive, hyp_id, depth, action, draw_id)
@@ -188,8 +189,23 @@ class RolloutEngine:
         so = _abi.StepOut(_ptr(o["next_pose"]), _ptr(o["next_alive"]), _ptr(o["reward"]),
                           _ptr(o["cost"]), _ptr(o["flags"]), _ptr(o["last_action"]))
         ro = _abi.RolloutOut(_ptr(o["result"]), _ptr(o.get("ret_agents")), _ptr(o.get("final_pose")))
+        if _async:
+            # the two halves of the call: the arrays must stay alive until expand_rollout_end()
+            self._check(self._lib.bmcts_expand_rollout_batch_begin(
+                self._h, C.byref(inb), C.byref(so), int(first_rollout_id), C.byref(ro)))
+            self._pending = (o, pose, alive, hyp_id, depth, action, draw_id)
+            return None
         self._check(self._lib.bmcts_expand_rollout_batch(self._h, C.byref(inb), C.byref(so),
                                                          int(first_rollout_id), C.byref(ro)))
+        return o
+
+    def expand_rollout_begin(self, *args, **kw):
+        """bmcts_expand_rollout_batch_begin: enqueue and return; collect with expand_rollout_end()"""
+        return self.expand_rollout(*args, _async=True, **kw)
+
+    def expand_rollout_end(self):
+        self._check(self._lib.bmcts_expand_rollout_batch_end(self._h))
+        o, self._pending = self._pending[0], None
         return o
 
     # -- likelihood (BehaviorHypothesisIDM::GetProbability) -----------------

@@ -113,6 +113,40 @@ def test_step_and_expand_parity(name):
     parity.assert_results_match(g, c)
 
 
+@pytest.mark.parametrize("n", [40, 3000])
+def test_asynchronous_halves_of_the_fused_call(n):
+    """bmcts_expand_rollout_batch_begin / _end on three engines at once (what a host thread does
+    for the trees it interleaves): same bytes as the synchronous call, small waves (zero copy)
+    and larger ones (packed copies); the engine refuses other work while a batch is pending"""
+    cfg, scn, meta = scenarios.workload("c3_merge_risk", horizon=15)
+    rng = np.random.default_rng(41)
+    A = scn.n_agents
+    engines = [RolloutEngine(cfg, scn) for _ in range(3)]
+    inputs = []
+    for k, eng in enumerate(engines):
+        pose, alive, hyp = scenarios.sample_leaves(scn, n, meta["lane_of"], meta["s_of"], rng,
+                                                   dead_prob=0.05)
+        action = rng.integers(0, scn.n_ego_actions, size=(A, n)).astype(np.uint8)
+        draw = rng.integers(0, 2**62, size=(A, n)).astype(np.uint64)
+        inputs.append((pose, alive, hyp, action, draw))
+        eng.expand_rollout_begin(pose, alive, hyp, action, draw, seed=3, stream=k,
+                                 first_rollout_id=100 * k, want_agents=True)
+    with pytest.raises(_abi.BmctsError):
+        engines[0].rollout(*inputs[0][:3])          # a batch is pending on this engine
+    for k, eng in enumerate(engines):
+        got = eng.expand_rollout_end()
+        pose, alive, hyp, action, draw = inputs[k]
+        want = eng.expand_rollout(pose, alive, hyp, action, draw, seed=3, stream=k,
+                                  first_rollout_id=100 * k, want_agents=True)
+        for key in want:
+            assert got[key].tobytes() == want[key].tobytes(), (k, key)
+        c = oracle.expand_rollout(cfg, scn, pose, alive, hyp, action, draw, seed=3, stream=k,
+                                  first_rollout_id=100 * k)
+        parity.assert_steps_match(got, c)
+        parity.assert_results_match(got, c)
+    assert engines[0]._lib.bmcts_expand_rollout_batch_end(engines[0]._h) == _abi.OK   # nothing pending
+
+
 def test_prediction_alpha_and_long_horizon():
     cfg, scn, meta = scenarios.workload("c1_highway_mdp", horizon=200)
     cfg.prediction_k, cfg.prediction_alpha = 0.2, 0.3
