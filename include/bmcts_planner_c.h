@@ -91,6 +91,12 @@ int bmcts_planner_set_tree_index(bmcts_planner* p, uint32_t tree_index);
 /* BehaviorUCT*::Plan(delta_time, observed_world) */
 int bmcts_planner_plan(bmcts_planner* p, double delta_time, double world_time, uint32_t ego_id,
                        const bmcts_agent_state* agents, int n_agents, bmcts_plan_result* out);
+/* BeliefCalculator::BeliefUpdate (belief_calculator/belief_calculator.hpp:23-47) on a
+ * hypothesis-based planner handle: one belief update from this observed world without planning
+ * (Plan() does the same update itself); bmcts_planner_reset_beliefs = BeliefCalculator::Reset */
+int bmcts_planner_update_beliefs(bmcts_planner* p, double world_time, uint32_t ego_id,
+                                 const bmcts_agent_state* agents, int n_agents);
+int bmcts_planner_reset_beliefs(bmcts_planner* p);
 /* GetCurrentBeliefs()[agent_id]; returns the number of hypotheses written (<= max_h) */
 int bmcts_planner_get_beliefs(bmcts_planner* p, uint32_t agent_id, double* beliefs, int max_h);
 /* flattened root statistics of the last search (per action: visits, sum of returns, sum of

@@ -157,6 +157,12 @@ class BehaviorUCTHypothesisBase : public BehaviorUCTBase, public UctHypothesisDe
   std::vector<BehaviorHypothesisIDM> GetBehaviorHypotheses() const { return behavior_hypotheses_; }
   // behavior_uct_hypothesis_base.hpp:92-114 (all agents, not only the filtered ones)
   void UpdateBeliefs(const ObservedWorld& observed_world);
+  // forget the observation history (BeliefCalculator::Reset)
+  void ResetBeliefs() {
+    belief_tracker_ = HypothesisBeliefTracker(mcts_parameters_);
+    last_world_.reset();
+    current_beliefs_.clear();
+  }
 
  protected:
   Mcts::HypothesisSampler MakeSampler(const SearchWorld& sw, unsigned tree_index);
@@ -240,6 +246,26 @@ class BehaviorUCTNHeuristicRiskConstraint : public BehaviorUCTRiskConstraint {
   std::shared_ptr<BehaviorUCTBase> Clone() const {
     return std::make_shared<BehaviorUCTNHeuristicRiskConstraint>(*this);
   }
+};
+
+// belief_calculator/belief_calculator.hpp:23-47: the beliefs over a hypothesis set from a sequence
+// of observed worlds, without a planner around them (the likelihoods come from the same engine
+// call as in BehaviorUCTHypothesisBase::UpdateBeliefs)
+class BeliefCalculator {
+ public:
+  BeliefCalculator(const ParamsPtr& params, const std::vector<BehaviorHypothesisIDM>& h, int device = 0)
+      : impl_(params, h, device) {}
+  BeliefCalculator(const ParamsPtr& params, const std::vector<BehaviorHypothesisIDM>& h,
+                   std::shared_ptr<LeafEvaluator> evaluator)
+      : impl_(params, h, evaluator) {}
+  void BeliefUpdate(const ObservedWorld& observed_world) { impl_.UpdateBeliefs(observed_world); }
+  Beliefs GetBeliefs() const { return impl_.GetCurrentBeliefs(); }
+  std::vector<BehaviorHypothesisIDM> GetBehaviorHypotheses() const { return impl_.GetBehaviorHypotheses(); }
+  ParamsPtr GetParams() const { return impl_.GetParams(); }
+  void Reset() { impl_.ResetBeliefs(); }
+
+ private:
+  BehaviorUCTHypothesis impl_;
 };
 
 class BehaviorUCTCooperative : public BehaviorUCTBase {

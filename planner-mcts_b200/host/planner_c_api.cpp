@@ -128,6 +128,25 @@ void FillResult(bmcts_planner* p, bmcts_plan_result* out) {
   out->engine_launches = b.EngineLaunchCount();
 }
 
+ObservedWorld WorldOf(const bmcts_planner* p, double world_time, uint32_t ego_id,
+                             const bmcts_agent_state* agents, int n_agents) {
+  ObservedWorld w;
+  w.world_time = world_time;
+  w.ego_id = ego_id;
+  w.map = p->map;
+  for (int i = 0; i < n_agents; ++i) {
+    Agent a;
+    a.id = agents[i].id;
+    a.state = {world_time, agents[i].x, agents[i].y, agents[i].theta, agents[i].v};
+    a.length = agents[i].length;
+    a.width = agents[i].width;
+    a.rear = agents[i].rear;
+    a.last_action.acc = agents[i].last_acc;
+    w.agents.push_back(a);
+  }
+  return w;
+}
+
 }  // namespace
 
 extern "C" {
@@ -185,26 +204,37 @@ int bmcts_planner_set_tree_index(bmcts_planner* p, uint32_t tree_index) {
   return BMCTS_OK;
 }
 
+int bmcts_planner_update_beliefs(bmcts_planner* p, double world_time, uint32_t ego_id,
+                                 const bmcts_agent_state* agents, int n_agents) {
+  if (!p || !agents || n_agents < 1) return BMCTS_ERR_INVALID_ARG;
+  if (!p->map) return Fail(p, BMCTS_ERR_NO_SCENARIO, "bmcts_planner_set_map was not called");
+  try {
+    EnsurePlanner(p);
+    auto* h = dynamic_cast<BehaviorUCTHypothesisBase*>(p->planner.get());
+    if (!h) return Fail(p, BMCTS_ERR_INVALID_ARG, "this planner has no behaviour hypotheses");
+    h->UpdateBeliefs(WorldOf(p, world_time, ego_id, agents, n_agents));
+  } catch (const std::exception& e) {
+    return Fail(p, BMCTS_ERR_CUDA, e.what());
+  }
+  return BMCTS_OK;
+}
+
+int bmcts_planner_reset_beliefs(bmcts_planner* p) {
+  if (!p) return BMCTS_ERR_INVALID_ARG;
+  if (!p->planner) return BMCTS_OK;  // nothing observed yet
+  auto* h = dynamic_cast<BehaviorUCTHypothesisBase*>(p->planner.get());
+  if (!h) return Fail(p, BMCTS_ERR_INVALID_ARG, "this planner has no behaviour hypotheses");
+  h->ResetBeliefs();
+  return BMCTS_OK;
+}
+
 int bmcts_planner_plan(bmcts_planner* p, double delta_time, double world_time, uint32_t ego_id,
                        const bmcts_agent_state* agents, int n_agents, bmcts_plan_result* out) {
   if (!p || !agents || n_agents < 1 || !out) return BMCTS_ERR_INVALID_ARG;
   if (!p->map) return Fail(p, BMCTS_ERR_NO_SCENARIO, "bmcts_planner_set_map was not called");
   try {
     EnsurePlanner(p);
-    ObservedWorld w;
-    w.world_time = world_time;
-    w.ego_id = ego_id;
-    w.map = p->map;
-    for (int i = 0; i < n_agents; ++i) {
-      Agent a;
-      a.id = agents[i].id;
-      a.state = {world_time, agents[i].x, agents[i].y, agents[i].theta, agents[i].v};
-      a.length = agents[i].length;
-      a.width = agents[i].width;
-      a.rear = agents[i].rear;
-      a.last_action.acc = agents[i].last_acc;
-      w.agents.push_back(a);
-    }
+    ObservedWorld w = WorldOf(p, world_time, ego_id, agents, n_agents);
     p->planner->Plan(delta_time, w);
     FillResult(p, out);
   } catch (const std::exception& e) {

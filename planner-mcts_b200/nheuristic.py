@@ -172,6 +172,9 @@ class BehaviorUCTNHeuristicRiskConstraint(BehaviorUCTRiskConstraint):
     def GetNNToValueConverter(self):
         return self.nn_to_value_converter
 
+    observer_ = property(lambda self: self.observer)
+    model_filename = property(lambda self: self.model_file_name)
+
     def _make_prior(self):
         m = self.model_file_name
         if m is None:

@@ -47,7 +47,8 @@ PLANNER_SYMBOLS = [
     "bmcts_planner_plan", "bmcts_planner_get_beliefs", "bmcts_planner_root_stats",
     "bmcts_planner_decide_from_root_stats", "bmcts_planner_parameter_sampling_probability",
     "bmcts_planner_last_error", "bmcts_planner_set_node_prior", "bmcts_planner_observation_size",
-    "bmcts_planner_observe", "bmcts_planner_node_prior_stats",
+    "bmcts_planner_observe", "bmcts_planner_node_prior_stats", "bmcts_planner_update_beliefs",
+    "bmcts_planner_reset_beliefs",
 ]
 
 
@@ -68,6 +69,9 @@ def declare_planner_api(lib):
     lib.bmcts_planner_root_stats.argtypes = [C.c_void_p, P(C.c_double), C.c_int]
     lib.bmcts_planner_decide_from_root_stats.argtypes = [C.c_void_p, P(C.c_double), C.c_int,
                                                          P(PlanResult)]
+    lib.bmcts_planner_update_beliefs.argtypes = [C.c_void_p, C.c_double, C.c_uint32, P(AgentState),
+                                                 C.c_int]
+    lib.bmcts_planner_reset_beliefs.argtypes = [C.c_void_p]
     lib.bmcts_planner_parameter_sampling_probability.argtypes = [C.c_void_p, C.c_int]
     lib.bmcts_planner_parameter_sampling_probability.restype = C.c_double
     lib.bmcts_planner_last_error.argtypes = [C.c_void_p]
@@ -105,6 +109,15 @@ class HypothesisIDM:
     num_buckets: int = 100
     buckets_lower_bound: float = -10.0
     buckets_upper_bound: float = 10.0
+
+    @property
+    def parameter_regions(self):
+        """BehaviorHypothesisIDM::GetParameterRegions: {distribution name: (lower, upper)}"""
+        names = ["BehaviorIDMStochastic::HeadwayDistribution", "BehaviorIDMStochastic::SpacingDistribution",
+                 "BehaviorIDMStochastic::MaxAccDistribution", "BehaviorIDMStochastic::DesiredVelDistribution",
+                 "BehaviorIDMStochastic::ComftBrakingDistribution",
+                 "BehaviorIDMStochastic::CoolnessFactorDistribution"]
+        return {n: (float(self.region.lo[i]), float(self.region.hi[i])) for i, n in enumerate(names)}
 
     # pickling (python_wrapper/python_planner_uct.cpp:206-248 pickles hypotheses with their
     # parameters): the ctypes region travels as its raw bytes
@@ -214,6 +227,9 @@ class _BehaviorUCT:
     def last_macro_action(self):
         return int(self.last.best_action)
 
+    def GetLastMacroAction(self):
+        return self.last_macro_action
+
     @property
     def last_return_values(self):
         v = self._vec("return_values")
@@ -271,6 +287,59 @@ class BehaviorUCTHypothesis(_BehaviorUCT):
 
     def parameter_sampling_probability(self, h):
         return float(self._lib.bmcts_planner_parameter_sampling_probability(self._h, int(h)))
+
+
+class BeliefCalculator:
+    """BeliefCalculator(params, hypotheses) (python_planner_uct.cpp:355-372,
+    belief_calculator/belief_calculator.hpp:23-47): beliefs over the hypothesis set from a sequence
+    of observed worlds, without planning.  The likelihoods are computed by the same engine call as
+    inside the planners."""
+
+    def __init__(self, params=None, hypotheses=(), device=0, _lib=None, _create=None):
+        self._planner = BehaviorUCTHypothesis(params, hypotheses, device=device, _lib=_lib,
+                                              _create=_create)
+        self._agent_ids = []
+
+    def BeliefUpdate(self, observed_world):
+        pl = self._planner
+        if pl._map is not observed_world.map:
+            pl._check(pl._lib.bmcts_planner_set_map(pl._h, C.byref(observed_world.map)))
+            pl._map = observed_world.map
+        n = len(observed_world.agents)
+        arr = (AgentState * n)()
+        for i, a in enumerate(observed_world.agents):
+            arr[i] = AgentState(a.id, a.x, a.y, a.theta, a.v, a.length, a.width, a.rear, a.last_acc)
+        pl._check(pl._lib.bmcts_planner_update_beliefs(pl._h, float(observed_world.world_time),
+                                                       int(observed_world.ego_id), arr, n))
+        for a in observed_world.agents:
+            if a.id != observed_world.ego_id and a.id not in self._agent_ids:
+                self._agent_ids.append(a.id)
+
+    def GetBeliefs(self):
+        """{agent id: [belief per hypothesis]} for every other agent observed so far"""
+        out = {}
+        for agent_id in self._agent_ids:
+            b = self._planner.current_beliefs(agent_id)
+            if len(b):
+                out[agent_id] = b.tolist()
+        return out
+
+    def GetBehaviorHypotheses(self):
+        return list(self._planner.hypotheses)
+
+    def GetParams(self):
+        return self._planner.params
+
+    def Reset(self):
+        pl = self._planner
+        pl._check(pl._lib.bmcts_planner_reset_beliefs(pl._h))
+        self._agent_ids = []
+
+    def __getstate__(self):
+        return {"params": self._planner.params, "hypotheses": self._planner.hypotheses}
+
+    def __setstate__(self, st):
+        self.__init__(st["params"], st["hypotheses"])
 
 
 class BehaviorUCTRiskConstraint(BehaviorUCTHypothesis):

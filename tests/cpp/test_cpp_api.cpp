@@ -121,6 +121,18 @@ int main() {
   coop.Plan(0.2, world);
   CHECK(coop.GetLastAction().acc < 0.0);
 
+  // BeliefCalculator (belief_calculator_test.cc:97-123): beliefs without a planner
+  {
+    BeliefCalculator calc(params, hyps, evaluator);
+    calc.BeliefUpdate(world);
+    Beliefs b = calc.GetBeliefs();
+    CHECK(b.size() == 1 && b.begin()->first == 2u && b.begin()->second.size() == 2);
+    CHECK(std::fabs(b.begin()->second[0] + b.begin()->second[1] - 1.0) < 1e-12);
+    CHECK(calc.GetBehaviorHypotheses().size() == 2);
+    calc.Reset();
+    CHECK(calc.GetBeliefs().empty());
+  }
+
   // root-belief sampling of a tree (alias tables over the beliefs): frequencies follow the
   // beliefs, a hypothesis with belief zero is never drawn, a fixed hypothesis is kept
   {

@@ -272,6 +272,50 @@ def test_wave_batched_search_agrees_with_sequential_search_within_monte_carlo_ci
         assert set(best[wave]) == {4}, (wave, best[wave])
 
 
+def test_belief_calculator_tracks_the_planners_beliefs():
+    """BeliefCalculator (python_wrapper/tests/py_belief_calculator_test.py:21-34,
+    tests/belief_calculator_test.cc:97-123): beliefs for every other agent over the hypothesis set,
+    equal to what a planner holds after Plan() on the same worlds, and forgotten by Reset()"""
+    lib = oracle.planner_lib()
+    kw = dict(_lib=lib, _create=lambda kind, out: lib.oracle_planner_create(kind, out))
+    hyps = W.hypotheses(num_samples=2000)
+    calc = P.BeliefCalculator(W.base_params(32), hyps, **kw)
+    planner = P.BehaviorUCTHypothesis(W.base_params(32), hyps, **kw)
+    world = W.observed_world(2, 6.0, 5.0, 1.0, goal_center=(150.0, -1.75))
+    assert calc.GetBeliefs() == {}
+    for step in range(3):
+        world.world_time = 0.2 * step
+        for a in world.agents[1:]:
+            a.x += 0.2 * a.v
+            a.last_acc = 0.4                       # the acceleration the others were seen to apply
+        calc.BeliefUpdate(world)
+        planner.Plan(0.2, world)
+        beliefs = calc.GetBeliefs()
+        assert sorted(beliefs) == [2, 3]            # one entry per other agent
+        for agent_id, b in beliefs.items():
+            assert len(b) == 2 and sum(b) == pytest.approx(1.0)
+            assert b == planner.current_beliefs(agent_id).tolist()
+    assert len(calc.GetBehaviorHypotheses()) == 2
+    assert calc.GetBehaviorHypotheses()[0].parameter_regions[
+        "BehaviorIDMStochastic::HeadwayDistribution"] == (1.0, 1.5)
+    calc.Reset()
+    assert calc.GetBeliefs() == {}
+    calc.BeliefUpdate(world)                        # starts over: first update = same state twice
+    fresh = P.BeliefCalculator(W.base_params(32), hyps, **kw)
+    fresh.BeliefUpdate(world)
+    assert calc.GetBeliefs() == fresh.GetBeliefs()
+    # two identical hypotheses cannot be told apart (py_belief_calculator_test.py:21-34): equal
+    # beliefs up to the Monte-Carlo noise of two histograms of 2000 samples with their own streams
+    same = P.BeliefCalculator(W.base_params(32), [hyps[0], hyps[0]], **kw)
+    same.BeliefUpdate(world)
+    for b in same.GetBeliefs().values():
+        assert b == pytest.approx([0.5, 0.5], abs=0.06)
+    # a cooperative planner has no hypotheses to update
+    coop = P.BehaviorUCTCooperative(W.base_params(8), **kw)
+    coop.Plan(0.2, world)
+    assert lib.bmcts_planner_reset_beliefs(coop._h) != 0
+
+
 def test_planners_survive_pickle_and_deepcopy():
     """python_wrapper/tests/pickle_unpickle_test.py:24-110: planners and hypotheses keep their
     parameters through pickle and deepcopy (the native planner is rebuilt)"""
