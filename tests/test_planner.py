@@ -316,6 +316,26 @@ def test_belief_calculator_tracks_the_planners_beliefs():
     assert lib.bmcts_planner_reset_beliefs(coop._h) != 0
 
 
+@pytest.mark.gpu
+def test_gpu_belief_calculator_equals_cpu_backed_one():
+    """the likelihood histograms are exact counts on both sides: identical beliefs"""
+    lib = oracle.planner_lib()
+    hyps = W.hypotheses(num_samples=3000)
+    g = P.BeliefCalculator(W.base_params(32), hyps)
+    c = P.BeliefCalculator(W.base_params(32), hyps, _lib=lib,
+                           _create=lambda kind, out: lib.oracle_planner_create(kind, out))
+    world = W.observed_world(3, 6.0, 5.0, 1.0, goal_center=(150.0, -1.75))
+    for step in range(3):
+        world.world_time = 0.2 * step
+        for k, a in enumerate(world.agents[1:]):
+            a.x += 0.2 * a.v
+            a.last_acc = 0.3 + 0.2 * k
+        g.BeliefUpdate(world)
+        c.BeliefUpdate(world)
+        assert g.GetBeliefs() == c.GetBeliefs()
+    assert sorted(g.GetBeliefs()) == [2, 3, 4]
+
+
 def test_planners_survive_pickle_and_deepcopy():
     """python_wrapper/tests/pickle_unpickle_test.py:24-110: planners and hypotheses keep their
     parameters through pickle and deepcopy (the native planner is rebuilt)"""
