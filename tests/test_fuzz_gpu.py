@@ -119,3 +119,13 @@ def test_random_scenario_parity(seed, monkeypatch):
                               stream=1, first_rollout_id=9)
     parity.assert_steps_match(g, c)
     parity.assert_results_match(g, c)
+    # belief likelihoods (BehaviorHypothesisIDM::GetProbability for every agent x hypothesis):
+    # the histograms are counts, so the probabilities are equal exactly
+    if scn.n_hypotheses > 0 and A > 1:
+        W = min(n, 4)
+        obs = rng.uniform(-5.0, 3.0, size=(A, W)).astype(np.float32)
+        kw = dict(n_samples=int(rng.choice([100, 1000])), n_buckets=int(rng.choice([10, 100, 1000])),
+                  lower=-6.0, upper=float(rng.choice([4.0, 8.0])), seed=3 + seed)
+        gl = eng.likelihood(pose[:, :W], alive[:W], obs, **kw)
+        cl = oracle.likelihood(cfg, scn, pose[:, :W], alive[:W], obs, **kw)
+        assert np.array_equal(gl, cl)
