@@ -129,3 +129,53 @@ def test_random_scenario_parity(seed, monkeypatch):
         gl = eng.likelihood(pose[:, :W], alive[:W], obs, **kw)
         cl = oracle.likelihood(cfg, scn, pose[:, :W], alive[:W], obs, **kw)
         assert np.array_equal(gl, cl)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("BMCTS_FUZZ_PLANNER_SEEDS", "16"))))
+def test_random_world_planner_parity(seed, monkeypatch):
+    """the planners on random worlds: the GPU-backed search builds exactly the tree of the
+    oracle-backed one (same host code, bit-identical leaf evaluations) whatever the wave size,
+    the number of trees and how they are spread over threads"""
+    from planner_mcts_b200 import planner as P
+    monkeypatch.delenv("BMCTS_LANE_T", raising=False)
+    cfg, scn, lane_of, s_of, rng = random_case(seed)
+    pose, _, _ = scenarios.sample_leaves(scn, 1, lane_of, s_of, rng, s_jitter=2.0, v_range=(2.0, 15.0))
+    A = scn.n_agents
+    agents = [P.Agent(id=10 + 3 * a, x=float(pose[a, 0, 0]), y=float(pose[a, 0, 1]),
+                      theta=float(pose[a, 0, 2]), v=float(pose[a, 0, 3]),
+                      length=float(scn.agent_length[a]), width=float(scn.agent_width[a]),
+                      rear=float(scn.agent_rear[a]), last_acc=float(rng.uniform(-1.0, 1.0)))
+              for a in range(A)]
+    world = P.ObservedWorld(ego_id=10, agents=agents, map=scn, world_time=1.4)
+    b = "BehaviorUctBase::"
+    trees = int(rng.choice([1, 1, 3, 7]))
+    params = {b + "Mcts::MaxNumIterations": int(rng.choice([64, 300])), b + "Mcts::MaxSearchTime": 1e9,
+              b + "Mcts::Engine::WaveSize": int(rng.choice([1, 7, 32, 0])),
+              b + "Mcts::NumParallelMcts": trees, b + "Mcts::UseMultiThreading": int(rng.integers(0, 2)),
+              b + "Mcts::Engine::MaxThreads": int(rng.choice([0, 2])),
+              b + "MaxNearestAgents": A - 1, b + "Mcts::RandomHeuristic::MaxNumIterations": 15,
+              b + "Mcts::RandomSeed": 1000 + seed,
+              b + "Mcts::State::EvaluationParameters::AddSafeDist": int(cfg.add_safe_dist),
+              b + "Mcts::State::SplitSafeDistCollision": int(cfg.split_safe_dist_collision),
+              b + "Mcts::HypothesisStatistic::CostBasedActionSelection": int(rng.integers(0, 2)),
+              "BehaviorUctRiskConstraint::DefaultAvailableRisk": [0.1, 0.0]}
+    hyps = [P.HypothesisIDM(scn.hypotheses[h], num_samples=300) for h in range(scn.n_hypotheses)]
+    if cfg.state_kind == _abi.STATE_COOPERATIVE:
+        cls, args = P.BehaviorUCTCooperative, (params,)
+    elif cfg.state_kind == _abi.STATE_RISK_CONSTRAINT:
+        cls, args = P.BehaviorUCTRiskConstraint, (params, hyps)
+    else:
+        cls, args = P.BehaviorUCTHypothesis, (params, hyps)
+    lib = oracle.planner_lib()
+    g = cls(*args)
+    c = cls(*args, _lib=lib, _create=lambda kind, out: lib.oracle_planner_create(kind, out))
+    for step in range(2):                                   # the second call updates the beliefs
+        world.world_time = 1.4 + 0.2 * step
+        tg, tc = g.Plan(0.2, world), c.Plan(0.2, world)
+        assert np.array_equal(g.root_stats(), c.root_stats()), step
+        assert g.last_macro_action == c.last_macro_action and np.array_equal(tg, tc)
+        assert g.last_num_nodes == c.last_num_nodes
+        if hasattr(g, "current_beliefs"):
+            for a in agents[1:]:
+                assert np.array_equal(g.current_beliefs(a.id), c.current_beliefs(a.id))
+    assert g.engine_launches > 0 and c.engine_launches == 0
