@@ -441,14 +441,28 @@ __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p)
   const float gap = s_gap, v_l = s_vl, v_own = s_vown;
   const float bucket_size = bm_div(p.upper - p.lower, (float)p.n_buckets);
   const int target = s_bucket;
+  // Exact skips, as in the rollout kernels: a Philox block none of whose words reaches a ranged
+  // parameter is not drawn (u * 0 + lo = lo whatever u), and the reciprocals of parameters that
+  // are FixedValues are the same for every sample.
+  const bool need0 = hy.hi[0] != hy.lo[0] || hy.hi[1] != hy.lo[1] || hy.hi[2] != hy.lo[2] ||
+                     hy.hi[3] != hy.lo[3];
+  const bool need1 = hy.hi[4] != hy.lo[4];
+  const bool fixed_v0 = hy.hi[3] == hy.lo[3];
+  const bool fixed_ab = hy.hi[2] == hy.lo[2] && hy.hi[4] == hy.lo[4];
+  const float inv_v0_fixed = bm_div(1.0f, bm_max(hy.lo[3], 1.0e-3f));
+  const float inv_2sab_fixed = bm_div(1.0f, 2.0f * bm_sqrt(bm_max(hy.lo[2] * hy.lo[4], 1.0e-6f)));
   unsigned cnt = 0;
   for (int smp = t; smp < p.n_samples; smp += blockDim.x) {
     uint64_t id = (uint64_t)(uint32_t)smp | ((uint64_t)(uint32_t)w << 32);
-    uint4 r0 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h);
-    uint4 r1 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h + 1u);
+    uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+    if (need0) r0 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h);
+    if (need1)
+      r1 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h + 1u);
     IdmParams ip = sample_idm_params(hy, r0, r1);
-    float inv_v0 = bm_div(1.0f, bm_max(ip.v0, 1.0e-3f));
-    float inv_2sab = bm_div(1.0f, 2.0f * bm_sqrt(bm_max(ip.a_max * ip.b, 1.0e-6f)));
+    const float inv_v0 = fixed_v0 ? inv_v0_fixed : bm_div(1.0f, bm_max(ip.v0, 1.0e-3f));
+    const float inv_2sab =
+        fixed_ab ? inv_2sab_fixed
+                 : bm_div(1.0f, 2.0f * bm_sqrt(bm_max(ip.a_max * ip.b, 1.0e-6f)));
     float acc = idm_acc(hl, ip, inv_v0, inv_2sab, has_leader, v_own, v_l, gap);
     if (acc < p.lower || acc > p.upper) continue;
     int b = (int)floorf(bm_div(acc - p.lower, bucket_size));
