@@ -360,7 +360,6 @@ struct LikelihoodArgs {
 };
 
 __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p) {
-  __shared__ float s_s[BMCTS_MAX_AGENTS], s_d[BMCTS_MAX_AGENTS], s_v[BMCTS_MAX_AGENTS];
   __shared__ int s_cur;
   __shared__ float s_gap, s_vl, s_vown;
   __shared__ int s_has_leader, s_skip, s_bucket;
@@ -372,31 +371,40 @@ __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p)
   const int t = threadIdx.x;
   const uint32_t am = p.alive[w];
   const size_t out_idx = ((size_t)a * p.H + h) * p.n_worlds + w;
-  if (t == 0) {
-    s_count = 0;
-    s_skip = 0;
-    // current corridor of agent a (publish(): argmin |d| over in-range corridors)
-    float4 q = p.pose[(size_t)a * p.n_worlds + w];
-    float best = kBig;
-    int bc = 0;
-    for (int c = 0; c < p.C; ++c) {
-      Proj pr = project(scn.corridors[c], q.x, q.y);
-      float m = pr.in ? bm_abs(pr.d) : kBig;
-      if (m < best) {
-        best = m;
-        bc = c;
-      }
+  // Prologue on warp 0 (one lane per corridor, then one lane per candidate leader, reduced with
+  // shuffles); the other warps wait at two barriers instead of behind a serial thread.
+  if (t < 32) {
+    // current corridor of agent a (publish(): argmin |d| over in-range corridors, lowest index
+    // on ties)
+    const float4 q = p.pose[(size_t)a * p.n_worlds + w];
+    float m = kBig;
+    if (t < p.C) {
+      const Proj pr = project(scn.corridors[t], q.x, q.y);
+      m = pr.in ? bm_abs(pr.d) : kBig;
     }
-    s_cur = bc;
-    s_vown = q.w;
-    if (!((am >> a) & 1u)) s_skip = 1;
-    const float act = p.action[(size_t)a * p.n_worlds + w];
-    if (act > p.upper || act < p.lower) s_skip = 1;
-    const float bucket_size = bm_div(p.upper - p.lower, (float)p.n_buckets);
-    int b = (int)floorf(bm_div(act - p.lower, bucket_size));
-    if (b > p.n_buckets - 1) b = p.n_buckets - 1;
-    if (b < 0) b = 0;
-    s_bucket = b;
+    int bc = t < p.C ? t : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      const bool take = om < m || (om == m && oc < bc);
+      m = take ? om : m;
+      bc = take ? oc : bc;
+    }
+    if (t == 0) {
+      s_count = 0;
+      s_cur = m < kBig ? bc : 0;  // no corridor in range: corridor 0, as the serial scan
+      s_vown = q.w;
+      int skip = !((am >> a) & 1u);
+      const float act = p.action[(size_t)a * p.n_worlds + w];
+      if (act > p.upper || act < p.lower) skip = 1;
+      s_skip = skip;
+      const float bucket_size = bm_div(p.upper - p.lower, (float)p.n_buckets);
+      int b = (int)floorf(bm_div(act - p.lower, bucket_size));
+      if (b > p.n_buckets - 1) b = p.n_buckets - 1;
+      if (b < 0) b = 0;
+      s_bucket = b;
+    }
   }
   __syncthreads();
   if (s_skip) {
@@ -404,34 +412,40 @@ __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p)
     return;
   }
   const int cur = s_cur;
-  if (t < p.A) {
-    float4 q = p.pose[(size_t)t * p.n_worlds + w];
-    Proj pr = project(scn.corridors[cur], q.x, q.y);
-    s_s[t] = pr.s;
-    s_d[t] = pr.in ? pr.d : kBig;
-    s_v[t] = q.w;
-  }
-  __syncthreads();
-  if (t == 0) {
-    // BaseIDM::CalcRelativeValues (find_leader)
-    float best = kBig;
-    int lead = -1;
+  if (t < 32) {
+    // BaseIDM::CalcRelativeValues (find_leader): nearest alive agent ahead in the corridor,
+    // lowest slot on equal distances
     const float hwc = scn.corridors[cur].half_width;
-    for (int j = 0; j < p.A; ++j) {
-      if (j == a || !((am >> j) & 1u)) continue;
-      if (!(bm_abs(s_d[j]) <= hwc)) continue;
-      float ds = s_s[j] - s_s[a];
-      if (ds > 0.0f && ds < best) {
-        best = ds;
-        lead = j;
+    const float4 qa = p.pose[(size_t)a * p.n_worlds + w];
+    const float s_own = project(scn.corridors[cur], qa.x, qa.y).s;
+    float ds = kBig, vj = 0.0f;
+    int j = 0x7fffffff;
+    if (t < p.A && t != a && ((am >> t) & 1u)) {
+      const float4 qj = p.pose[(size_t)t * p.n_worlds + w];
+      const Proj pr = project(scn.corridors[cur], qj.x, qj.y);
+      const float dj = pr.in ? pr.d : kBig;
+      const float d = pr.s - s_own;
+      if (bm_abs(dj) <= hwc && d > 0.0f) {
+        ds = d;
+        j = t;
+        vj = qj.w;
       }
     }
-    s_has_leader = lead >= 0;
-    s_gap = 0.0f;
-    s_vl = 0.0f;
-    if (lead >= 0) {
-      s_gap = best - ((scn.agent_length[a] - scn.agent_rear[a]) + scn.agent_rear[lead]);
-      s_vl = s_v[lead];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ods = __shfl_xor_sync(0xffffffffu, ds, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+      const float ov = __shfl_xor_sync(0xffffffffu, vj, o);
+      const bool take = ods < ds || (ods == ds && oj < j);
+      ds = take ? ods : ds;
+      j = take ? oj : j;
+      vj = take ? ov : vj;
+    }
+    if (t == 0) {
+      const bool found = ds < kBig;
+      s_has_leader = found;
+      s_gap = found ? ds - ((scn.agent_length[a] - scn.agent_rear[a]) + scn.agent_rear[j]) : 0.0f;
+      s_vl = found ? vj : 0.0f;
     }
   }
   __syncthreads();
