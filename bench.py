@@ -222,6 +222,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: keep this process (its pinned staging memory is first touched by it, and
+    its tree-search threads) on the CPUs next to its GPU, as NVML reports them; the ranks of one
+    box otherwise stream their host batches across the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -235,6 +254,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the rollout engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -383,7 +403,8 @@ def run_ours(args):
                    "mean_rollout_steps": mean_rollout_len,
                    "l2": "inputs larger than L2 (leaf batch %.0f MB per step)" %
                          (n * (A * 17 + 4) / 1e6),
-                   "rollouts_per_s": n * world / (elapsed_ms / args.steps * 1e-3)},
+                   "rollouts_per_s": n * world / (elapsed_ms / args.steps * 1e-3),
+                   "cpus_bound_per_rank": numa},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(n * (A * 17 + 4)), "d2h_bytes_per_step": int(n * 32)},
@@ -457,6 +478,8 @@ def main():
     ap.add_argument("--cpu-rollouts", type=int, default=65536, help="reference arm: leaves per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-plan", action="store_true", help="skip the Plan() iterations/s arm")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="multi-rank runs: do not bind the process to the CPUs next to its GPU")
     ap.add_argument("--plan-iterations", type=int, default=32768)
     ap.add_argument("--plan-wave", type=int, default=0,
                     help="iterations per engine batch; 0 = the planner's default (iterations / 128, "
