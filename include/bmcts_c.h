@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BMCTS_ABI_VERSION 1
+#define BMCTS_ABI_VERSION 2
 
 #define BMCTS_MAX_AGENTS 32
 #define BMCTS_MAX_CORRIDORS 4
@@ -96,6 +96,11 @@ enum {
   BMCTS_ACT_CHANGE_RIGHT = 2
 };
 
+/* bmcts_step_in.action[slot 0] of an element that is NOT to be expanded: the rollout starts from
+ * the given state itself (a non-terminal node at Mcts::MaxSearchDepth: mamcts iterate() runs the
+ * heuristic on it).  Its step outputs are left untouched.  Only with a rollout. */
+#define BMCTS_ACTION_NONE 0xFFu
+
 enum { BMCTS_GOAL_NONE = 0, BMCTS_GOAL_POLYGON = 1, BMCTS_GOAL_FRENET_LIMITS = 2 };
 
 enum { BMCTS_MEM_HOST = 0, BMCTS_MEM_DEVICE = 1 };
@@ -159,8 +164,16 @@ typedef struct bmcts_config {
   float lon_acc_min;               /* DynamicModel::LonAccelerationMin -8 */
   float lon_acc_max;               /* DynamicModel::LonAccelerationMax 4 */
   float ego_max_velocity;          /* BehaviorIDMClassic::MaxVelocity 50 */
-  int32_t num_substeps;            /* NumTrajectoryTimePoints - 1 = 10 */
+  int32_t num_substeps;            /* NumTrajectoryTimePoints - 1 = 10 (IDM sub-steps of the others) */
   int32_t state_kind;              /* BMCTS_STATE_* */
+  /* macro-action integration (tests/data/nheuristic_test.json:153-155,183-196) */
+  int32_t limit_steering_rate;     /* BehaviorIDMLaneTracking::LimitSteeringRate true: the steering
+                                      angle is kept inside the lateral-acceleration limits,
+                                      v^2 tan(delta) / wheel_base in [LatAccMin, LatAccMax] */
+  float lat_acc_max;               /* DynamicModel::LatAccMax 4 */
+  float lat_acc_min;               /* DynamicModel::LatAccMin -4 */
+  float ego_integration_dt;        /* BehaviorMotionPrimitives::IntegrationTimeDelta 0.02: a macro
+                                      action is ceil(dt / this) Euler steps; <= 0: num_substeps */
 } bmcts_config;
 
 /* One lane corridor: centre line + half width.  The *derived* arrays are

@@ -407,6 +407,13 @@ static void idm_agent_step(const bmcts_config* cfg, const bmcts_scenario* scn, c
   *last_action = acc;
 }
 
+int oracle_ego_substeps(const bmcts_config* cfg, float Dt) {
+  if (!(cfg->ego_integration_dt > 0.0f)) return cfg->num_substeps;
+  float k = ceilf(bm_div(Dt, cfg->ego_integration_dt) - 1.0e-3f);
+  k = bm_clamp(k, 1.0f, 1024.0f);
+  return (int)k;
+}
+
 /* BehaviorMPMacroActions primitive on the single-track model (spec item 8) */
 static void macro_agent_step(const bmcts_config* cfg, const bmcts_scenario* scn, const world_t* w,
                              int i, int action, float Dt, agent_t* out, float* last_action) {
@@ -419,7 +426,9 @@ static void macro_agent_step(const bmcts_config* cfg, const bmcts_scenario* scn,
   else if (act->type == BMCTS_ACT_CHANGE_RIGHT && scn->corridors[tgt].right >= 0)
     tgt = scn->corridors[tgt].right;
   const bmcts_corridor* corr = &scn->corridors[tgt];
-  int nsub = cfg->num_substeps;
+  /* BehaviorMotionPrimitives::IntegrationTimeDelta: ceil(Dt / delta) Euler steps of equal
+   * length (1e-3 of slack: 0.5 / float(0.02) is 25.0000006) */
+  int nsub = oracle_ego_substeps(cfg, Dt);
   float dt = bm_div(Dt, (float)nsub);
   float inv_wb = bm_div(1.0f, cfg->wheel_base);
   float x = a->x, y = a->y, th = a->th, v = a->v;
@@ -435,6 +444,12 @@ static void macro_agent_step(const bmcts_config* cfg, const bmcts_scenario* scn,
     float delta = th_err + bm_atan2(-(cfg->crosstrack_gain * pd), v);
     delta = bm_clamp(delta, -cfg->delta_max, cfg->delta_max);
     float tn = bm_tan_small(delta);
+    if (cfg->limit_steering_rate) {
+      /* BARK CalculateSteeringAngle(limit_steering): lateral acceleration v^2 tan(delta) / L
+       * kept inside [LatAccMin, LatAccMax], i.e. tan(delta) inside [LatAccMin, LatAccMax] L / v^2 */
+      float r = bm_div(cfg->wheel_base, bm_max(v * v, 1.0e-6f));
+      tn = bm_clamp(tn, cfg->lat_acc_min * r, cfg->lat_acc_max * r);
+    }
     float dv = dt * v;
     x = bm_fma(dv, cs, x);
     y = bm_fma(dv, sn, y);
@@ -858,6 +873,16 @@ static void step_element(const bmcts_config* cfg, const bmcts_scenario* scn,
   gather_u8(in->hyp_id, A, n, k, hyp);
   gather_u8(in->action, A, n, k, act);
   gather_u64(in->draw_id, A, n, k, did);
+  if (act[0] == BMCTS_ACTION_NONE) {
+    /* no expansion: the heuristic runs on the given (depth-capped) node itself */
+    if (!ro) return;
+    float ra0[MAXA], fp0[MAXA * 4];
+    oracle_rollout(cfg, scn, pose, in->alive[k], hyp, depth, in->seed, in->stream,
+                   first_rollout_id + (uint64_t)k, &ro->result[k], ra0, fp0);
+    if (ro->ret_agents) scatter_f1(ro->ret_agents, A, n, k, ra0);
+    if (ro->final_pose) scatter_f4(ro->final_pose, A, n, k, fp0);
+    return;
+  }
   oracle_step(cfg, scn, pose, in->alive[k], hyp, depth, act, did, in->seed, in->stream, np, &na,
               rw, c2, &f, la);
   if (out) {

@@ -32,6 +32,8 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 
 /* MctsStateBase::calculate_prediction_time_span (mcts_state_base.hpp:238-241) */
 float oracle_prediction_time_span(const bmcts_config* cfg, unsigned depth);
+/* Euler steps of one macro action of duration Dt (BehaviorMotionPrimitives::IntegrationTimeDelta) */
+int oracle_ego_substeps(const bmcts_config* cfg, float Dt);
 
 /* reward_from_evaluation_results (mcts_state_base.hpp:107-118) */
 float oracle_reward_from_flags(const bmcts_config* cfg, uint32_t flags, float dt);

@@ -30,6 +30,7 @@ STATE_HYPOTHESIS, STATE_RISK_CONSTRAINT, STATE_COOPERATIVE = 0, 1, 2
 ACT_CONST_ACC_STAY_LANE, ACT_CHANGE_LEFT, ACT_CHANGE_RIGHT = 0, 1, 2
 GOAL_NONE, GOAL_POLYGON, GOAL_FRENET_LIMITS = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
+ACTION_NONE = 0xFF   # bmcts_step_in.action[slot 0]: no expansion step for this element
 
 f32, i32, u32, u64 = C.c_float, C.c_int32, C.c_uint32, C.c_uint64
 
@@ -52,6 +53,8 @@ class Config(C.Structure):
         ("wheel_base", f32), ("delta_max", f32), ("crosstrack_gain", f32),
         ("lon_acc_min", f32), ("lon_acc_max", f32), ("ego_max_velocity", f32),
         ("num_substeps", i32), ("state_kind", i32),
+        ("limit_steering_rate", i32), ("lat_acc_max", f32), ("lat_acc_min", f32),
+        ("ego_integration_dt", f32),
     ]
 
 

@@ -148,20 +148,27 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cuda
   };
   const int NC = 32 / T;
   const long need_warps = ((long)a.n + NC - 1) / NC;
-  // the kernel may use all the shared memory the SM offers: set once per process and variant
-  // (engines on several host threads share the function, the attribute only ever grows)
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
+  // the kernel may use all the shared memory the SM offers.  cudaFuncSetAttribute applies to the
+  // CURRENT device only, so the opt-in is made once per (variant, device): an engine on a second
+  // GPU of the same process needs its own (engines on several host threads share the flags)
+  constexpr int kMaxDevices = 64;
+  static std::once_flag attr_once[kMaxDevices];
+  static cudaError_t attr_err[kMaxDevices];
+  if (e->device < 0 || e->device >= kMaxDevices)
+    return fail(e, BMCTS_ERR_INVALID_ARG, "device ordinal out of range");
   const int optin = e->max_smem_optin;
-  std::call_once(attr_once, [&]() {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared);
+  std::call_once(attr_once[e->device], [&]() {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared);
+    attr_err[e->device] = ce;
   });
-  if (attr_err != cudaSuccess) return cuda_fail(e, attr_err, "cudaFuncSetAttribute");
+  if (attr_err[e->device] != cudaSuccess)
+    return cuda_fail(e, attr_err[e->device], "cudaFuncSetAttribute");
   // geometry per (variant, scenario size, batch class): occupancy queries are cached
-  const unsigned long long key = ((unsigned long long)COOP << 60) | ((unsigned long long)T << 56) |
+  // (COOP has its own top bit: T = 16 is 1 << 60 in the T field)
+  const unsigned long long key = ((unsigned long long)COOP << 63) | ((unsigned long long)T << 56) |
                                  ((unsigned long long)a.A << 48) | ((unsigned long long)a.C << 44) |
                                  ((unsigned long long)a.H << 36) | ((unsigned long long)force_W << 28) |
                                  (unsigned long long)std::min<long>(need_warps, (1L << 28) - 1);
@@ -700,6 +707,7 @@ int bmcts_set_config(bmcts_engine* e, const bmcts_config* cfg) {
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->stream));
   e->cfg = *cfg;
+  e->geometry.clear();  // the state kind (kernel variant, shared-memory layout) may have changed
   CU(cudaMemcpyAsync(e->d_cfg, &e->cfg, sizeof(bmcts_config), cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   return upload_dt_table(e);
@@ -1056,6 +1064,8 @@ int bmcts_math_probe(bmcts_engine* e, int op, const float* a, const float* b, in
   if (!e || !a || !b || !out || n < 0 || op < 0 || op >= BMCTS_MATH_NUM_OPS)
     return e ? fail(e, BMCTS_ERR_INVALID_ARG, "math_probe: bad argument") : BMCTS_ERR_INVALID_ARG;
   if (n == 0) return BMCTS_OK;
+  if (e->async_pending)  // the probe shares the packed staging buffers with a wave in flight
+    return fail(e, BMCTS_ERR_INVALID_ARG, "bmcts_expand_rollout_batch_end has not been called");
   CU(cudaSetDevice(e->device));
   const size_t bytes = sizeof(float) * (size_t)n;
   int st;

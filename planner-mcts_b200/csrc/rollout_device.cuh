@@ -297,6 +297,15 @@ __device__ __forceinline__ uint32_t terminal_from_flags(const bmcts_config& cfg,
   return t ? (uint32_t)BMCTS_F_TERMINAL : 0u;
 }
 
+// Euler steps of one macro action (BehaviorMotionPrimitives::IntegrationTimeDelta; oracle
+// oracle_ego_substeps): ceil(Dt / delta) with 1e-3 of slack, or num_substeps when delta <= 0
+__device__ __forceinline__ int ego_substeps(const bmcts_config& cfg, float Dt) {
+  if (!(cfg.ego_integration_dt > 0.0f)) return cfg.num_substeps;
+  float k = ceilf(bm_div(Dt, cfg.ego_integration_dt) - 1.0e-3f);
+  k = bm_clamp(k, 1.0f, 1024.0f);
+  return (int)k;
+}
+
 struct IdmParams {
   float T, s0, a_max, v0, b;
 };

@@ -74,7 +74,6 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
   const uint32_t my_group = (blockIdx.x * (uint32_t)warps + warp) * NC + g;
   const uint32_t gmask = T == 32 ? 0xffffffffu : (((1u << T) - 1u) << (lane & ~(T - 1)));
 
-  const int nsub = cfg.num_substeps;
   const bool add_sd = cfg.add_safe_dist != 0;
   const bool goal_poly = scn.goal.kind == BMCTS_GOAL_POLYGON;
   const bool goal_frenet = scn.goal.kind == BMCTS_GOAL_FRENET_LIMITS;
@@ -107,8 +106,9 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
         rid = next;
         am = p.alive[rid];
         depth = p.depth ? (int)p.depth[rid] : 1;
-        expand = p.do_expand != 0;
-        active = true;
+        // BMCTS_ACTION_NONE: no expansion step, the rollout starts from the given state
+        expand = p.do_expand != 0 && p.action[rid] != BMCTS_ACTION_NONE;
+        active = expand || p.do_rollout != 0;
         fresh = true;
         n = 0;
         agent_steps = 0;
@@ -125,7 +125,6 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
     const float Dt = p.dt_table
                          ? p.dt_table[depth < BMCTS_MAX_DEPTH ? depth : BMCTS_MAX_DEPTH - 1]
                          : cfg.prediction_k;
-    const float dt = bm_div(Dt, (float)nsub);
     const uint64_t rollout_id = p.first_rollout_id + (uint64_t)rid;
 
     // ------------------------------------------- predict() + post-step world of own agents
@@ -179,6 +178,10 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
           const float wb = cfg.wheel_base, kct = cfg.crosstrack_gain, dmax = cfg.delta_max;
           const float vmax = cfg.ego_max_velocity;
           const float inv_wb = bm_div(1.0f, wb);
+          const int nsub_e = ego_substeps(cfg, Dt);
+          const float dt_e = bm_div(Dt, (float)nsub_e);
+          const bool limit = cfg.limit_steering_rate != 0;
+          const float lat_lo = cfg.lat_acc_min, lat_hi = cfg.lat_acc_max;
           x = ca[K_X * fstride];
           y = ca[K_Y * fstride];
           th = ca[K_TH * fstride];
@@ -186,20 +189,24 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
           cs = ca[K_CS * fstride];
           sn = ca[K_SN * fstride];
 #pragma unroll 1
-          for (int q = 0; q < nsub; ++q) {
+          for (int q = 0; q < nsub_e; ++q) {
             const float fx = bm_fma(wb, cs, x);
             const float fy = bm_fma(wb, sn, y);
             const Proj pr = project(corr, fx, fy);
             const float th_err = bm_norm_angle(corr.angle[pr.seg] - th);
             float delta = th_err + bm_atan2(-(kct * pr.d), v);
             delta = bm_clamp(delta, -dmax, dmax);
-            const float tn = bm_tan_small(delta);
-            const float dv = dt * v;
+            float tn = bm_tan_small(delta);
+            if (limit) {  // lateral acceleration v^2 tan(delta) / L inside [LatAccMin, LatAccMax]
+              const float r = bm_div(wb, bm_max(v * v, 1.0e-6f));
+              tn = bm_clamp(tn, lat_lo * r, lat_hi * r);
+            }
+            const float dv = dt_e * v;
             x = bm_fma(dv, cs, x);
             y = bm_fma(dv, sn, y);
             th = bm_fma(dv, tn * inv_wb, th);
-            v = bm_clamp(bm_fma(dt, acc, v), 0.0f, vmax);
-            if (q + 1 == nsub) th = bm_norm_angle(th);
+            v = bm_clamp(bm_fma(dt_e, acc, v), 0.0f, vmax);
+            if (q + 1 == nsub_e) th = bm_norm_angle(th);
             bm_sincos(th, &sn, &cs);
           }
           la = acc;

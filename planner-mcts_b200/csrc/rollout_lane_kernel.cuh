@@ -303,8 +303,9 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         rid = next;
         am = p.alive[rid];
         depth = p.depth ? (int)p.depth[rid] : 1;
-        expand = p.do_expand != 0;
-        active = true;
+        // BMCTS_ACTION_NONE: no expansion step, the rollout starts from the given state
+        expand = p.do_expand != 0 && p.action[rid] != BMCTS_ACTION_NONE;
+        active = expand || p.do_rollout != 0;
         fresh = true;
         n = 0;
         agent_steps = 0;
@@ -413,24 +414,32 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
       const float wb = cfg.wheel_base, kct = cfg.crosstrack_gain, dmax = cfg.delta_max;
       const float vmax = cfg.ego_max_velocity;
       const float inv_wb = bm_div(1.0f, wb);
+      const int nsub_e = ego_substeps(cfg, Dt);
+      const float dt_e = bm_div(Dt, (float)nsub_e);
+      const bool limit = cfg.limit_steering_rate != 0;
+      const float lat_lo = cfg.lat_acc_min, lat_hi = cfg.lat_acc_max;
       float nx = ex, ny = ey, nth = eth, nv = ev;
       float sn = esn, cs = ecs;  // sin / cos of the current heading (published values)
 BM_UNROLL(BMCTS_EGO_UNROLL)
-      for (int q = 0; q < nsub; ++q) {
+      for (int q = 0; q < nsub_e; ++q) {
         const float fx = bm_fma(wb, cs, nx);
         const float fy = bm_fma(wb, sn, ny);
         const Proj pr = project(corr, fx, fy);
         const float th_err = bm_norm_angle(corr.angle[pr.seg] - nth);
         float delta = th_err + bm_atan2(-(kct * pr.d), nv);
         delta = bm_clamp(delta, -dmax, dmax);
-        const float tn = bm_tan_small(delta);
-        const float dv = dt * nv;
+        float tn = bm_tan_small(delta);
+        if (limit) {  // lateral acceleration v^2 tan(delta) / L inside [LatAccMin, LatAccMax]
+          const float r = bm_div(wb, bm_max(nv * nv, 1.0e-6f));
+          tn = bm_clamp(tn, lat_lo * r, lat_hi * r);
+        }
+        const float dv = dt_e * nv;
         nx = bm_fma(dv, cs, nx);
         ny = bm_fma(dv, sn, ny);
         nth = bm_fma(dv, tn * inv_wb, nth);
-        nv = bm_clamp(bm_fma(dt, acc, nv), 0.0f, vmax);
+        nv = bm_clamp(bm_fma(dt_e, acc, nv), 0.0f, vmax);
         // heading for the next sub-step; after the last one: of the wrapped final heading
-        if (q + 1 == nsub) nth = bm_norm_angle(nth);
+        if (q + 1 == nsub_e) nth = bm_norm_angle(nth);
         bm_sincos(nth, &sn, &cs);
       }
       ex = nx;

@@ -55,6 +55,10 @@ void bmcts_config_default(bmcts_config* c) {
   c->ego_max_velocity = 50.0f;
   c->num_substeps = 10;
   c->state_kind = BMCTS_STATE_HYPOTHESIS;
+  c->limit_steering_rate = 1;      // tests/data/nheuristic_test.json:183-186
+  c->lat_acc_max = 4.0f;           // :191-196
+  c->lat_acc_min = -4.0f;
+  c->ego_integration_dt = 0.02f;   // :153-155 (0.019999999552965164 = float(0.02))
 }
 
 int bmcts_config_validate(const bmcts_config* c) {
@@ -66,6 +70,11 @@ int bmcts_config_validate(const bmcts_config* c) {
   if (!(c->delta_max > 0.0f) || c->delta_max > BM_PIO4) return BMCTS_ERR_INVALID_ARG;
   if (!(c->prediction_k > 0.0f)) return BMCTS_ERR_INVALID_ARG;
   if (!(c->dyn_max_other_decel > 0.0f) || !(c->dyn_max_ego_decel > 0.0f))
+    return BMCTS_ERR_INVALID_ARG;
+  if (c->limit_steering_rate && !(c->lat_acc_min <= 0.0f && c->lat_acc_max >= 0.0f))
+    return BMCTS_ERR_INVALID_ARG;
+  // at most 1024 Euler steps per macro action at the shortest prediction span
+  if (c->ego_integration_dt > 0.0f && c->prediction_k / c->ego_integration_dt > 1024.0f)
     return BMCTS_ERR_INVALID_ARG;
   if (c->state_kind < BMCTS_STATE_HYPOTHESIS || c->state_kind > BMCTS_STATE_COOPERATIVE)
     return BMCTS_ERR_INVALID_ARG;

@@ -180,7 +180,10 @@ Trajectory BehaviorUCTBase::MacroActionTrajectory(const SearchWorld& sw, unsigne
   if (act.type == BMCTS_ACT_CHANGE_LEFT && scn.corridors[tgt].left >= 0) tgt = scn.corridors[tgt].left;
   else if (act.type == BMCTS_ACT_CHANGE_RIGHT && scn.corridors[tgt].right >= 0) tgt = scn.corridors[tgt].right;
   const bmcts_corridor& corr = scn.corridors[tgt];
-  const int nsub = cfg.num_substeps;
+  // BehaviorMotionPrimitives::IntegrationTimeDelta: ceil(delta_time / delta) Euler steps
+  int nsub = cfg.num_substeps;
+  if (cfg.ego_integration_dt > 0.0f)
+    nsub = (int)bm_clamp(std::ceil(bm_div((float)delta_time, cfg.ego_integration_dt) - 1.0e-3f), 1.0f, 1024.0f);
   const float dt = bm_div((float)delta_time, (float)nsub);
   const float inv_wb = bm_div(1.0f, cfg.wheel_base);
   Trajectory traj;
@@ -195,6 +198,10 @@ Trajectory BehaviorUCTBase::MacroActionTrajectory(const SearchWorld& sw, unsigne
     delta = th_err + bm_atan2(-(cfg.crosstrack_gain * pr.d), v);
     delta = bm_clamp(delta, -cfg.delta_max, cfg.delta_max);
     float tn = bm_tan_small(delta);
+    if (cfg.limit_steering_rate) {
+      const float r = bm_div(cfg.wheel_base, bm_max(v * v, 1.0e-6f));
+      tn = bm_clamp(tn, cfg.lat_acc_min * r, cfg.lat_acc_max * r);
+    }
     float dv = dt * v;
     x = bm_fma(dv, cs, x);
     y = bm_fma(dv, sn, y);

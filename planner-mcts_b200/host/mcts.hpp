@@ -317,6 +317,7 @@ class Mcts {
     std::vector<PathStep> path;  // path.back() is the expansion step (unless no_expand)
     std::vector<uint8_t> hyp;    // sampled hypothesis per slot for this iteration
     bool needs_engine = false;
+    bool rollout_only = false;   // reached a non-terminal node at MAX_SEARCH_DEPTH: heuristic only
     Node* reached = nullptr;     // existing terminal / max-depth node reached instead
   };
 
@@ -344,6 +345,25 @@ class Mcts {
     return n;
   }
 
+  // the one node that stands in for children created beyond MAX_NUMBER_OF_NODES
+  Node* ScratchNode(Node* parent, uint32_t alive, unsigned state_depth, bool terminal) {
+    if (!scratch_) {
+      scratch_.reset(new Node());
+      scratch_pose_.reset(new float[(size_t)A_ * 4]);
+    }
+    *scratch_ = Node();
+    Node* n = scratch_.get();
+    n->pose = scratch_pose_.get();
+    n->parent = parent;
+    n->tree_depth = parent ? parent->tree_depth + 1 : 0;
+    n->state_depth = state_depth;
+    n->alive = alive;
+    n->terminal = terminal;
+    if (other_mode_ == OtherMode::kUct) n->edge_reward.assign(A_, 0.0);
+    if (other_mode_ == OtherMode::kUct) n->latest_ret_other.assign(A_, 0.0);
+    return n;
+  }
+
   void EnsureStats(Node* n) {
     if (n->stats_ready) return;
     n->stats_ready = true;
@@ -351,7 +371,8 @@ class Mcts {
       n->ego_uct = std::make_unique<UctStatistic>();
       n->ego_uct->Init(n_actions_, p_.uct_statistic.LOWER_BOUND, p_.uct_statistic.UPPER_BOUND,
                        p_.uct_statistic.EXPLORATION_CONSTANT, p_.DISCOUNT_FACTOR,
-                       p_.USE_BOUND_ESTIMATION);
+                       p_.USE_BOUND_ESTIMATION, p_.uct_statistic.PROGRESSIVE_WIDENING_K,
+                       p_.uct_statistic.PROGRESSIVE_WIDENING_ALPHA);
       n->ego_uct->SeedHeuristic(n->h_return, n->h_visits);
     } else {
       n->ego_cc = std::make_unique<CostConstrainedStatistic>();
@@ -373,7 +394,8 @@ class Mcts {
       for (int s = 1; s < A_; ++s)
         n->other_uct[s].Init(n_actions_, p_.uct_statistic.LOWER_BOUND, p_.uct_statistic.UPPER_BOUND,
                              p_.uct_statistic.EXPLORATION_CONSTANT, p_.DISCOUNT_FACTOR,
-                             p_.USE_BOUND_ESTIMATION);
+                             p_.USE_BOUND_ESTIMATION, p_.uct_statistic.PROGRESSIVE_WIDENING_K,
+                             p_.uct_statistic.PROGRESSIVE_WIDENING_ALPHA);
     }
   }
 
@@ -382,6 +404,7 @@ class Mcts {
   void Select(const HypothesisSampler& sample_hypotheses, Selection& sel) {
     sel.path.clear();
     sel.needs_engine = false;
+    sel.rollout_only = false;
     sel.reached = nullptr;
     sel.hyp.assign(A_, 0);
     if (sample_hypotheses) sample_hypotheses(&sel.hyp);
@@ -389,6 +412,8 @@ class Mcts {
     for (;;) {
       if (node->terminal || node->tree_depth >= p_.MAX_SEARCH_DEPTH) {
         sel.reached = node;
+        // mamcts iterate(): the heuristic also runs on a non-terminal node at the depth cap
+        sel.rollout_only = sel.needs_engine = !node->terminal;
         return;
       }
       EnsureStats(node);
@@ -460,6 +485,18 @@ class Mcts {
       for (int i = 0; i < w; ++i) {
         if (slot[i] < 0) continue;
         const int k = slot[i];
+        if (sels[i].rollout_only) {  // no expansion step: BMCTS_ACTION_NONE in the ego's slot
+          const Node* nd = sels[i].reached;
+          wave_.alive[k] = nd->alive;
+          wave_.depth[k] = (uint16_t)std::min<unsigned>(nd->state_depth, BMCTS_MAX_DEPTH - 1);
+          for (int a = 0; a < A_; ++a) {
+            const size_t e = wave_.at(a, k);
+            for (int f = 0; f < 4; ++f) wave_.pose[e * 4 + f] = nd->pose[(size_t)a * 4 + f];
+            wave_.hyp_id[e] = sels[i].hyp[a];
+            wave_.action[e] = a == 0 ? (uint8_t)BMCTS_ACTION_NONE : (uint8_t)0;
+          }
+          continue;
+        }
         const PathStep& st = sels[i].path.back();
         const Node* nd = st.node;
         wave_.alive[k] = nd->alive;
@@ -554,8 +591,12 @@ class Mcts {
 
   void Backup(Selection& sel, int k) {
     Node* leaf = sel.reached;
-    std::vector<int> resolved_idx;
-    if (sel.needs_engine) {
+    if (sel.rollout_only) {
+      // RandomHeuristic on the depth-capped node itself (node->update_statistics(heuristic))
+      const bmcts_rollout_result& r = wave_.result[k];
+      const double cost[2] = {r.cost0, r.cost1};
+      SetHeuristic(leaf, r.ret_ego, cost, wave_.ret_agents.data(), k);
+    } else if (sel.needs_engine) {
       PathStep& st = sel.path.back();
       Node* parent = st.node;
       // resolve the others' newly planned actions and build the joint action key
@@ -588,11 +629,33 @@ class Mcts {
       } else {
         existing = parent->children.Find(jh);
       }
+      const bmcts_rollout_result& r = wave_.result[k];
+      const double cost[2] = {r.cost0, r.cost1};
       if (existing) {
-        leaf = existing;  // same joint action expanded earlier (in this wave or by value merge)
+        // The newly planned joint action is one that was expanded before (in this wave, or its
+        // actions resolved to known ones): the engine has rolled out from that same child state.
+        // mamcts would descend through the child; here the fresh rollout is the sample the
+        // parents back up, and a child that already has action statistics keeps its own value
+        // estimate and visit count.
+        leaf = existing;
+        if (leaf->stats_ready) {
+          if (leaf->ego_uct) leaf->ego_uct->SetLatestReturn(r.ret_ego);
+          if (leaf->ego_cc) leaf->ego_cc->SetLatest(r.ret_ego, cost);
+          if (other_mode_ == OtherMode::kHypothesis) {
+            leaf->latest_cost_other = cost[0];
+          } else {
+            for (int s = 1; s < A_; ++s)
+              leaf->latest_ret_other[s] = (double)wave_.ret_agents[wave_.at(s, k)];
+          }
+        } else {
+          SetHeuristic(leaf, r.ret_ego, cost, wave_.ret_agents.data(), k);
+        }
       } else {
         const bool terminal = (wave_.flags[k] & BMCTS_F_TERMINAL) != 0;
-        leaf = NewNode(parent, nullptr, wave_.next_alive[k], parent->state_depth + 1, terminal);
+        // beyond the node cap the child is evaluated but neither linked nor kept: one scratch
+        // node is reused, so the memory of the tree is bounded by MaxNumNodes
+        leaf = link ? NewNode(parent, nullptr, wave_.next_alive[k], parent->state_depth + 1, terminal)
+                    : ScratchNode(parent, wave_.next_alive[k], parent->state_depth + 1, terminal);
         for (int a = 0; a < A_; ++a)
           for (int f = 0; f < 4; ++f) leaf->pose[(size_t)a * 4 + f] = wave_.next_pose[wave_.at(a, k) * 4 + f];
         leaf->edge_reward_ego = wave_.reward[wave_.at(0, k)];
@@ -600,13 +663,10 @@ class Mcts {
         leaf->edge_cost[0] = wave_.cost[k];
         leaf->edge_cost[1] = wave_.cost[(size_t)wave_.n + k];
         if (link) *place = leaf;
-        // beyond the node cap the child is evaluated but not linked (bounded memory)
+        SetHeuristic(leaf, r.ret_ego, cost, wave_.ret_agents.data(), k);
       }
-      const bmcts_rollout_result& r = wave_.result[k];
-      const double cost[2] = {r.cost0, r.cost1};
-      SetHeuristic(leaf, r.ret_ego, cost, wave_.ret_agents.data(), k);
     } else {
-      // existing terminal (or depth-capped) node: RandomHeuristic returns a zero estimate
+      // existing terminal node: RandomHeuristic returns a zero estimate
       const double zero[2] = {0.0, 0.0};
       SetHeuristicZero(leaf, zero);
     }
@@ -690,6 +750,8 @@ class Mcts {
   std::vector<std::unique_ptr<Node[]>> node_chunks_;
   std::vector<std::unique_ptr<float[]>> pose_chunks_;
   size_t n_nodes_ = 0;
+  std::unique_ptr<Node> scratch_;
+  std::unique_ptr<float[]> scratch_pose_;
   Node* root_ = nullptr;
   WaveBuffers wave_;
   std::vector<Selection> sels_;

@@ -227,6 +227,11 @@ inline bmcts_config EngineConfigFromParamServer(const Params& p, const std::stri
   c.lon_acc_max = (float)p.GetReal(eg + "DynamicModel::LonAccelerationMax", 4.0);
   c.ego_max_velocity = (float)p.GetReal(eg + "BehaviorIDMClassic::MaxVelocity", 50.0);
   c.num_substeps = (int)p.GetInt(eg + "BehaviorIDMClassic::NumTrajectoryTimePoints", 11) - 1;
+  c.limit_steering_rate = p.GetBool(eg + "BehaviorIDMLaneTracking::LimitSteeringRate", true);
+  c.lat_acc_max = (float)p.GetReal(eg + "DynamicModel::LatAccMax", 4.0);
+  c.lat_acc_min = (float)p.GetReal(eg + "DynamicModel::LatAccMin", -4.0);
+  c.ego_integration_dt =
+      (float)p.GetReal(eg + "BehaviorMotionPrimitives::IntegrationTimeDelta", 0.02);
   c.state_kind = state_kind;
   return c;
 }

@@ -63,8 +63,13 @@ class UctStatistic {
     bool expanded = false;
   };
 
+  // pw_k / pw_alpha: Mcts::UctStatistic::ProgressiveWidening::{K, Alpha}
+  // (param_config/mcts_parameters_from_param_server.hpp:63-64); pw_alpha <= 0 switches the
+  // widening off (every action is expanded before UCB is used)
   void Init(int num_actions, double lower, double upper, double exploration, double gamma,
-            bool bound_estimation) {
+            bool bound_estimation, double pw_k = 1.0, double pw_alpha = 0.0) {
+    pw_k_ = pw_k;
+    pw_alpha_ = pw_alpha;
     pairs_.assign(num_actions, Pair());
     lower_ = lower;
     upper_ = upper;
@@ -82,10 +87,22 @@ class UctStatistic {
   double latest_return() const { return latest_return_; }
   const std::vector<Pair>& pairs() const { return pairs_; }
 
-  // mamcts UctStatistic::choose_next_action: random unexpanded action first, then UCB1
+  // progressive widening of the ego / cooperative action set: a new action is opened only while
+  // #expanded <= K * N^alpha (the form HypothesisStatistic uses per hypothesis); with the
+  // reference defaults K = 1, alpha = 0.1 that is two actions until 1024 visits
+  bool WideningAllowed() const {
+    if (unexpanded_.empty()) return false;
+    if (!(pw_alpha_ > 0.0)) return true;
+    const double n_exp = (double)(pairs_.size() - unexpanded_.size());
+    if (n_exp < 1.0) return true;
+    return n_exp <= pw_k_ * std::pow((double)(total_visits_ + total_pending_), pw_alpha_);
+  }
+
+  // mamcts UctStatistic::choose_next_action: a random unexpanded action while progressive
+  // widening allows one, else UCB1 over the expanded actions
   int ChooseNextAction(std::mt19937& gen) {
     int a;
-    if (!unexpanded_.empty()) {
+    if (WideningAllowed()) {
       std::uniform_int_distribution<size_t> d(0, unexpanded_.size() - 1);
       size_t i = d(gen);
       a = unexpanded_[i];
@@ -113,6 +130,11 @@ class UctStatistic {
       double v;
       if (n <= 0.0) {
         v = std::numeric_limits<double>::max();
+      } else if (p.count == 0) {
+        // only visits in flight (same wave): nothing is known about the action yet, and its
+        // initial value of 0 must not attract the rest of the wave.  Chosen again only if every
+        // expanded action is in this state.
+        v = -std::numeric_limits<double>::max();
       } else {
         const double q = (hi > lo) ? (p.value - lo) / (hi - lo) : 0.0;
         v = q + 2.0 * c_ * std::sqrt(two_log_n / n);
@@ -144,6 +166,11 @@ class UctStatistic {
     latest_return_ = heuristic_value;
     total_visits_ += 1;
   }
+
+  // a fresh rollout from a node that already has action statistics (a newly planned joint
+  // action resolved to this existing child): the sample is what the parents back up, the
+  // node's own value estimate and visit count stay as they are
+  void SetLatestReturn(double ret) { latest_return_ = ret; }
 
   // mamcts update_statistic(changed_child_statistic)
   void UpdateStatistic(int action, double collected_reward, double child_latest_return) {
@@ -205,6 +232,7 @@ class UctStatistic {
   std::vector<Pair> pairs_;
   std::vector<int> unexpanded_;
   double lower_ = 0, upper_ = 1, c_ = 0.7, gamma_ = 0.9;
+  double pw_k_ = 1.0, pw_alpha_ = 0.0;
   bool bound_estimation_ = true;
   unsigned total_visits_ = 0, total_pending_ = 0;
   double value_ = 0.0, latest_return_ = 0.0;
@@ -619,6 +647,11 @@ class CostConstrainedStatistic {
   void UpdateFromHeuristic(double ret, const double* cost) {
     reward_.UpdateFromHeuristic(ret);
     for (int i = 0; i < num_costs(); ++i) costs_[i].UpdateFromHeuristic(cost[i]);
+  }
+
+  void SetLatest(double ret, const double* cost) {
+    reward_.SetLatestReturn(ret);
+    for (int i = 0; i < num_costs(); ++i) costs_[i].SetLatestReturn(cost[i]);
   }
 
   void SeedHeuristic(double ret, const double* cost, unsigned visits) {

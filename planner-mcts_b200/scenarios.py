@@ -228,22 +228,26 @@ def place_agents(n_agents, lanes, rng, s_start=20.0, gap=(8.0, 40.0), ego_lane=N
 
 # ------------------------------------------------------------- BASELINE.json configs
 
-def _base_config(state_kind, horizon):
+def _base_config(state_kind, horizon, ego_dt):
     cfg = _abi.default_config()
     cfg.state_kind = state_kind
     cfg.max_rollout_steps = horizon
+    cfg.ego_integration_dt = ego_dt
     return cfg
 
 
-def workload(name, horizon=20, seed=1000):
+def workload(name, horizon=20, seed=1000, ego_dt=0.05):
     """Returns (config, scenario, meta) for one of the BASELINE.json configs:
     'c1_highway_mdp', 'c2_merge_sbg', 'c3_merge_risk', 'c4_coop', 'c5_rsbg' (+ the test
-    geometry 'x_curved_max')."""
+    geometry 'x_curved_max').  ego_dt is the Euler step of the ego's macro action: 0.05 s gives
+    the K_ego = 10 steps per 0.5 s that SURVEY.md section 8d's FLOP formula is stated for; the
+    reference default (BehaviorMotionPrimitives::IntegrationTimeDelta) is 0.02 s = 25 steps."""
     rng = np.random.default_rng(seed)
+    _cfg = lambda kind, hz: _base_config(kind, hz, ego_dt)
     if name == "c1_highway_mdp":
         cors, road = highway_geometry(300.0)
         A, hyps = 4, hypothesis_set(1, 1, headway=(1.0, 3.0))
-        cfg = _base_config(_abi.STATE_HYPOTHESIS, horizon)
+        cfg = _cfg(_abi.STATE_HYPOTHESIS, horizon)
         goal = polygon_goal([(250.0, 0.0), (300.0, 0.0), (300.0, -3.5), (250.0, -3.5)])
         lanes, ego_lane, length = [0, 1], 0, 300.0
     elif name in ("c2_merge_sbg", "c3_merge_risk", "c5_rsbg"):
@@ -252,13 +256,13 @@ def workload(name, horizon=20, seed=1000):
         cors, road, ramp = merge_geometry(length, n_main_lanes=n_main)
         if name == "c2_merge_sbg":
             A, hyps = 10, hypothesis_set(8, 1)
-            cfg = _base_config(_abi.STATE_HYPOTHESIS, horizon)
+            cfg = _cfg(_abi.STATE_HYPOTHESIS, horizon)
         elif name == "c3_merge_risk":
             A, hyps = 16, hypothesis_set(8, 1)
-            cfg = _base_config(_abi.STATE_RISK_CONSTRAINT, horizon)
+            cfg = _cfg(_abi.STATE_RISK_CONSTRAINT, horizon)
         else:
             A, hyps = 32, hypothesis_set(8, 8)
-            cfg = _base_config(_abi.STATE_RISK_CONSTRAINT, horizon)
+            cfg = _cfg(_abi.STATE_RISK_CONSTRAINT, horizon)
         if name != "c2_merge_sbg":
             cfg.add_safe_dist, cfg.split_safe_dist_collision = 1, 1
         goal = polygon_goal([(length - 60.0, 1.75), (length, 1.75), (length, -1.75),
@@ -267,14 +271,14 @@ def workload(name, horizon=20, seed=1000):
     elif name == "c4_coop":
         cors, road = highway_geometry(500.0)
         A, hyps = 20, []
-        cfg = _base_config(_abi.STATE_COOPERATIVE, horizon)
+        cfg = _cfg(_abi.STATE_COOPERATIVE, horizon)
         goal = polygon_goal([(440.0, 0.0), (500.0, 0.0), (500.0, -3.5), (440.0, -3.5)])
         lanes, ego_lane, length = [0, 1], 1, 500.0
     elif name == "x_curved_max":
         # not a BASELINE.json config: geometry at the structure limits for the parity tests
         cors, road = curved_geometry()
         A, hyps = 12, hypothesis_set(2, 2)
-        cfg = _base_config(_abi.STATE_RISK_CONSTRAINT, horizon)
+        cfg = _cfg(_abi.STATE_RISK_CONSTRAINT, horizon)
         cfg.add_safe_dist, cfg.split_safe_dist_collision = 1, 1
         goal = frenet_goal(2, max_lat=(0.6, 0.6), max_angle=(0.15, 0.15), vel=(3.0, 30.0))
         lanes, ego_lane, length = [0, 1, 2, 3], 1, 300.0

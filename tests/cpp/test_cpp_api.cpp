@@ -72,6 +72,9 @@ int main() {
   params->SetInt("BehaviorUctBase::Mcts::MaxSearchTime", 1000000);
   params->SetListFloat("BehaviorUctBase::EgoBehavior::AccelerationInputs", {0, 1, 4, -1, -8});
   params->SetBool("BehaviorUctBase::EgoBehavior::AddLaneChangeActions", false);
+  // behavior_uct_hypothesis_test.cc:253-254 (the defaults open a third ego action after 1024 visits)
+  params->SetReal("BehaviorUctBase::Mcts::UctStatistic::ProgressiveWidening::Alpha", 0.5);
+  params->SetReal("BehaviorUctBase::Mcts::UctStatistic::ProgressiveWidening::K", 0.4);
   params->SetReal("BehaviorUctBase::Mcts::State::GoalReward", 200.0);
   params->SetReal("BehaviorUctBase::Mcts::State::CollisionReward", -2000.0);
 

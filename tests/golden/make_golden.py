@@ -28,10 +28,14 @@ from planner_mcts_b200 import scenarios  # noqa: E402
 WORKLOADS = ["c1_highway_mdp", "c2_merge_sbg", "c3_merge_risk", "c4_coop", "c5_rsbg",
              "x_curved_max"]
 SEED, STREAM, FIRST_ID = 1000, 2, 4242
+# Euler step of the ego's macro action: the reference default (0.02 s = 25 steps per 0.5 s,
+# tests/data/nheuristic_test.json:153-155) on three fixtures, the benchmark setting of
+# SURVEY.md 8d (0.05 s = 10 steps) on the others
+EGO_DT = {"c1_highway_mdp": 0.02, "c3_merge_risk": 0.02, "c4_coop": 0.02}
 
 
 def inputs(name):
-    cfg, scn, meta = scenarios.workload(name, horizon=20)
+    cfg, scn, meta = scenarios.workload(name, horizon=20, ego_dt=EGO_DT.get(name, 0.05))
     rng = np.random.default_rng(99)
     pose, alive, hyp = scenarios.sample_leaves(scn, 24, meta["lane_of"], meta["s_of"], rng,
                                                dead_prob=0.08)

@@ -20,6 +20,10 @@ def base_params(iterations, acc_inputs=(0, 1, 4, -1, -8), search_time_ms=1e9, se
         P0 + "Mcts::State::GoalCost": 10.0,
         P0 + "Mcts::State::CollisionCost": 300.0,
         P0 + "MaxNearestAgents": 5,
+        # :253-254 (the defaults, K = 1 and alpha = 0.1, keep the ego at two actions for the
+        # first 1024 visits)
+        P0 + "Mcts::UctStatistic::ProgressiveWidening::Alpha": 0.5,
+        P0 + "Mcts::UctStatistic::ProgressiveWidening::K": 0.4,
     }
 
 

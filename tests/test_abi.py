@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libbmcts.so does not export {name}"
     assert sorted(_abi.EXPORTED_SYMBOLS) == declared
-    assert lib.bmcts_abi_version() == 1
+    assert lib.bmcts_abi_version() == 2
     # the planner ABI (include/bmcts_planner_c.h)
     from planner_mcts_b200 import planner
     declared = [f for f in _declared_functions("bmcts_planner_c.h") if f.startswith("bmcts_planner_")]
@@ -69,6 +69,11 @@ def test_config_defaults_are_the_reference_defaults():
     assert not (c.split_safe_dist_collision or c.chance_costs or c.add_safe_dist)
     assert c.discount_factor == pytest.approx(0.9) and c.max_rollout_steps == 1000
     assert c.num_substeps == 10
+    # ego macro-action integration: tests/data/nheuristic_test.json:153-155 (IntegrationTimeDelta
+    # 0.019999999552965164 = float32(0.02)), :183-186 (LimitSteeringRate true), :191-196 (LatAcc)
+    assert c.limit_steering_rate == 1
+    assert (c.lat_acc_max, c.lat_acc_min) == (4.0, -4.0)
+    assert c.ego_integration_dt == np.float32(0.019999999552965164)
     assert _abi.load_library().bmcts_config_validate(C.byref(c)) == _abi.OK
     c.delta_max = 1.0   # > pi/4: outside the validity range of bm_tan_small
     assert _abi.load_library().bmcts_config_validate(C.byref(c)) == _abi.ERR_INVALID_ARG

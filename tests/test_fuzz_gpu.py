@@ -72,6 +72,12 @@ def random_case(seed):
     cfg.step_reward = float(rng.choice([0.0, -1.0]))
     cfg.safe_dist_violated_reward = float(-rng.uniform(0.0, 50.0))
     cfg.crosstrack_gain = float(rng.uniform(0.3, 2.0))
+    # macro-action integration: steering limit on / off, lateral acceleration limits, Euler step
+    # (0 = num_substeps steps; 0.02 = the reference default)
+    cfg.limit_steering_rate = int(rng.integers(0, 2))
+    cfg.lat_acc_max = float(rng.uniform(0.5, 6.0))
+    cfg.lat_acc_min = float(-rng.uniform(0.5, 6.0))
+    cfg.ego_integration_dt = float(rng.choice([0.0, 0.02, 0.05, 0.07]))
     goal = scenarios.frenet_goal(int(rng.integers(0, len(cors))), max_lat=(0.5, 0.7),
                                  max_angle=(0.1, 0.2), vel=(2.0, 40.0)) \
         if seed % 3 == 1 else scenarios.polygon_goal(
@@ -112,12 +118,13 @@ def test_random_scenario_parity(seed, monkeypatch):
     parity.assert_results_match(g, c)
     A = scn.n_agents
     action = rng.integers(0, scn.n_ego_actions, size=(A, n)).astype(np.uint8)
+    action[0, rng.random(n) < 0.15] = _abi.ACTION_NONE   # not expanded: rolled out as they are
     draw = rng.integers(0, 2**62, size=(A, n)).astype(np.uint64)
     g = eng.expand_rollout(pose, alive, hyp, action, draw, depth=depth, seed=5 + seed, stream=1,
                            first_rollout_id=9, want_agents=True)
     c = oracle.expand_rollout(cfg, scn, pose, alive, hyp, action, draw, depth=depth, seed=5 + seed,
                               stream=1, first_rollout_id=9)
-    parity.assert_steps_match(g, c)
+    parity.assert_steps_match(g, c, expanded=action[0] != _abi.ACTION_NONE)
     parity.assert_results_match(g, c)
     # belief likelihoods (BehaviorHypothesisIDM::GetProbability for every agent x hypothesis):
     # the histograms are counts, so the probabilities are equal exactly
@@ -158,6 +165,11 @@ def test_random_world_planner_parity(seed, monkeypatch):
               b + "Mcts::State::EvaluationParameters::AddSafeDist": int(cfg.add_safe_dist),
               b + "Mcts::State::SplitSafeDistCollision": int(cfg.split_safe_dist_collision),
               b + "Mcts::HypothesisStatistic::CostBasedActionSelection": int(rng.integers(0, 2)),
+              b + "Mcts::MaxSearchDepth": int(rng.choice([1000, 1000, 2, 4])),
+              b + "Mcts::MaxNumNodes": int(rng.choice([2000, 40])),
+              b + "Mcts::UctStatistic::ProgressiveWidening::Alpha": float(rng.choice([0.1, 0.5])),
+              b + "EgoBehavior::BehaviorIDMLaneTracking::LimitSteeringRate": int(cfg.limit_steering_rate),
+              b + "EgoBehavior::BehaviorMotionPrimitives::IntegrationTimeDelta": float(rng.choice([0.02, 0.05])),
               "BehaviorUctRiskConstraint::DefaultAvailableRisk": [0.1, 0.0]}
     hyps = [P.HypothesisIDM(scn.hypotheses[h], num_samples=300) for h in range(scn.n_hypotheses)]
     if cfg.state_kind == _abi.STATE_COOPERATIVE:

@@ -64,7 +64,8 @@ def test_hypothesis_planner_brakes_behind_slow_agent_and_tree_shape(make):
     pl.Plan(0.5, world)
     assert pl.last_action[0] < 0.0            # some deceleration must occur (:279)
     exp = pl.last_root_expanded_actions
-    assert 6 <= pl.last_max_tree_depth <= 10  # :299
+    # :299 asserts 6..10 on the EXTRACTED edges, which stop at MaxExtractionDepth = 10 (:259)
+    assert 6 <= min(pl.last_max_tree_depth, 10) <= 10
     assert 4 <= exp[0] <= 10                  # ego (:301)
     assert 3 <= exp[1] <= 10                  # nearest agent: progressive widening (:302)
     # the second agent follows the first at its desired speed whatever the hypothesis says:
@@ -138,6 +139,7 @@ def test_cooperative_planner(make):
     slow agent"""
     params = W.base_params(1500)
     params[P0 + "Mcts::State::CooperationFactor"] = 0.75
+    params[P0 + "Mcts::UctStatistic::ProgressiveWidening::K"] = 4.0   # :173-174
     world = W.observed_world(0, 5.0, 5.0, 0.0, goal_center=(60.0, -1.75))
     pl = make(P.BehaviorUCTCooperative, params)
     pl.Plan(0.2, world)
@@ -146,6 +148,39 @@ def test_cooperative_planner(make):
     pl = make(P.BehaviorUCTCooperative, params)
     pl.Plan(0.2, world)
     assert pl.last_action[0] < 0.0
+
+
+def test_uct_progressive_widening_and_search_limits():
+    """Mcts::UctStatistic::ProgressiveWidening::{K, Alpha} (param_config/
+    mcts_parameters_from_param_server.hpp:63-64) gate how many ego actions the root opens:
+    #expanded <= K N^alpha.  Defaults K = 1, alpha = 0.1: two actions until 1024 visits.
+    MaxNumNodes bounds the tree; a non-terminal node at MaxSearchDepth is rolled out, not zeroed."""
+    world = W.observed_world(1, 12.0, 5.0, 0.0, goal_center=(150.0, -1.75))
+    for k, alpha, iters, expect in ((1.0, 0.1, 600, 2), (1.0, 0.1, 1100, 3), (0.4, 0.5, 600, 5),
+                                    (1.0, 0.0, 50, 5)):
+        params = W.base_params(iters)
+        params[P0 + "Mcts::UctStatistic::ProgressiveWidening::K"] = k
+        params[P0 + "Mcts::UctStatistic::ProgressiveWidening::Alpha"] = alpha
+        params[P0 + "Mcts::MaxNumNodes"] = 100000
+        pl = cpu(P.BehaviorUCTHypothesis, params, W.hypotheses())
+        pl.Plan(0.2, world)
+        assert pl.last_root_expanded_actions[0] == expect, (k, alpha, iters)
+    # node cap
+    params = W.base_params(500)
+    params[P0 + "Mcts::MaxNumNodes"] = 60
+    pl = cpu(P.BehaviorUCTHypothesis, params, W.hypotheses())
+    pl.Plan(0.2, world)
+    assert pl.last_num_nodes <= 60 and pl.last_num_iterations == 500
+    # depth cap: the values of a depth-1 tree are rollout returns, as different from zero as those
+    # of the unbounded search (the road is free: every rollout collects the step-free return)
+    params = W.base_params(400)
+    params[P0 + "Mcts::MaxSearchDepth"] = 1
+    params[P0 + "Mcts::State::StepReward"] = -1.0
+    pl = cpu(P.BehaviorUCTHypothesis, params, W.hypotheses())
+    pl.Plan(0.2, world)
+    assert pl.last_max_tree_depth == 1
+    # a depth-1 value = step reward + gamma * rollout return of (further) step rewards < -1
+    assert all(v < -1.5 for v in pl.last_return_values.values())
 
 
 def test_root_parallel_merge_of_two_trees():
