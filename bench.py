@@ -2,14 +2,19 @@
 """bench.py -- rollout agent-steps/s of the MCTS leaf-evaluation path on B200.
 
 Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
-A step = one rollout batch (bmcts_rollout_batch) over `--rollouts` synthetic leaf states of
-the configured BASELINE.json workload (default: configs[1], "BehaviorUCTHypothesis SBG, 8
-behavior hypotheses, merge scenario, 10 agents"), horizon 20 steps with terminal early
-exit.  `value` is measured with the leaves resident in HBM (CUDA events on the engine's
-stream); `e2e` is the same metric through the C-ABI call with pinned HOST buffers
-(host->device copy of the leaves and device->host read of the results inside the timed
-region).  `--impl reference` times the CPU oracle (the reference itself cannot be built
-here) on all host cores on a bounded sample of the same workload.
+A step = one rollout batch (bmcts_rollout_batch) over `--rollouts` synthetic leaves of the
+configured BASELINE.json workload -- default: configs[4], the largest one ("RSBG
+risk-constrained, 32 agents, 64 hypotheses"), horizon 20 steps with terminal early exit.  The
+leaves come in the unique-state form of the C ABI (a table of rollouts / 16 distinct leaf states,
+each rolled out under 16 freshly sampled hypothesis assignments: SURVEY.md Appendix G).
+`value` is measured with the inputs resident in HBM (CUDA events on the engine's stream); `e2e`
+is the same metric through the C-ABI call with pinned HOST buffers (host->device copies of the
+inputs and the device->host path of the results inside the timed region).  The same line carries
+`workloads` (the other four BASELINE.json configs, short runs), `likelihood` (the belief-update
+kernel at C5 size), `plan` (MCTS iterations/s of one Plan() with 10^6 iterations on C5,
+root-parallel over the ranks) and `plan_default_budget` (the reference's default budget: 2000
+iterations, one tree).  `--impl reference` times the CPU oracle (the reference itself cannot be
+built here) on all host cores on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -41,9 +46,16 @@ def flop_per_agent_step(A, cooperative=False):
     return ((A - 1) * (480.0 + 60.0 * (A - 1)) + 400.0 + (A - 1) * 168.0 + 680.0) / A
 
 
-def hbm_bytes_per_rollout(A):
-    """algorithmic HBM bytes of one rollout: leaf state in, 32-byte result record out"""
-    return A * (16 + 1) + 4 + 32
+def hbm_bytes_per_rollout(A, share=1):
+    """algorithmic HBM bytes of one rollout: its share of a leaf state (16 B per agent + alive
+    mask; `share` rollouts start from the same state), one hypothesis id per agent, the state
+    index, and the 32-byte result record"""
+    return (A * 16 + 4) / share + A + (4 if share > 1 else 0) + 32
+
+
+def input_bytes_per_step(A, n, share):
+    ns = n // share if share > 1 else n
+    return int(ns * (A * 16 + 4) + n * A + (4 * n if share > 1 else 0))
 
 
 class ClockSampler(threading.Thread):
@@ -147,7 +159,9 @@ def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_
               b + "MaxNearestAgents": A - 1, b + "Mcts::RandomHeuristic::MaxNumIterations": horizon,
               b + "EgoBehavior::AccelerationInputs": [0.0, 1.0, 4.0, -1.0, -8.0],
               b + "Mcts::NumParallelMcts": trees, b + "Mcts::UseMultiThreading": 1 if trees > 1 else 0,
-              b + "Mcts::Engine::MaxThreads": threads}
+              b + "Mcts::Engine::MaxThreads": threads,
+              # the workload's Euler step of the ego's macro action (10 per 0.5 s)
+              b + "EgoBehavior::BehaviorMotionPrimitives::IntegrationTimeDelta": float(cfg.ego_integration_dt)}
     if cfg.add_safe_dist:
         params[b + "Mcts::State::EvaluationParameters::AddSafeDist"] = 1
         params[b + "Mcts::State::SplitSafeDistCollision"] = 1
@@ -181,6 +195,154 @@ def plan_benchmark(workload, horizon, iterations, wave, backend, device=0, tree_
             "root_stats": pl.root_stats().tolist()}
 
 
+def make_batch(scn, meta, n, share, seed):
+    """n synthetic leaves in the unique-state form: n / share distinct leaf states (poses around
+    the workload's placement), each rolled out `share` times under independently sampled
+    hypothesis ids; share == 1 is the plain form (one state per rollout)."""
+    from planner_mcts_b200 import scenarios
+    ns = n // share if share > 1 else n
+    pose, alive, _ = scenarios.leaves_for(scn, meta, ns, seed=seed)
+    rng = np.random.default_rng(seed + 7919)
+    hyp = rng.integers(0, max(1, scn.n_hypotheses), size=(scn.n_agents, n), dtype=np.uint8)
+    index = None
+    if share > 1:
+        index = np.repeat(np.arange(ns, dtype=np.uint32), share)
+        rng.shuffle(index)   # a wave does not come sorted by state
+    return pose, alive, hyp, index
+
+
+class Arm:
+    """device-resident and host (pinned) copies of one batch + the calls that roll it out"""
+
+    def __init__(self, eng, scn, meta, n, share, seed, dev, rank, want_host=True):
+        import torch
+        from planner_mcts_b200 import _abi
+        self.eng, self.n, self.rank, self._abi, self.torch = eng, n, rank, _abi, torch
+        pose, alive, hyp, index = make_batch(scn, meta, n, share, seed)
+        self.ns = pose.shape[1]
+        self.indexed = index is not None
+        t = lambda a: None if a is None else torch.from_numpy(a)
+        host = [t(pose), t(alive.view(np.int32)), t(hyp), t(None if index is None else index.view(np.int32))]
+        self.dev = [None if x is None else x.to(dev) for x in host]
+        self.d_res = torch.zeros(n, 8, dtype=torch.float32, device=dev)
+        if want_host:
+            self.host = [None if x is None else x.pin_memory() for x in host]
+            self.h_res = torch.zeros(n, 8, dtype=torch.float32).pin_memory()
+        torch.cuda.synchronize()
+
+    def _call(self, mem, bufs, res, i):
+        pose, alive, hyp, index = bufs
+        self.eng.rollout_raw(self.n, mem, pose, alive, hyp, None, res, seed=1000, stream=self.rank,
+                             first_rollout_id=i * self.n, n_states=self.ns if self.indexed else 0,
+                             state_index=index)
+
+    def step_device(self, i):
+        self._call(self._abi.MEM_DEVICE, self.dev, self.d_res, i)
+
+    def step_host(self, i):   # returns when the results are in the pinned host buffer
+        self._call(self._abi.MEM_HOST, self.host, self.h_res, i)
+
+
+def measure(eng, arm, steps, warmup, stream, barrier, sampler_index=None, want_e2e=True):
+    """K timed steps device-resident (CUDA events on the engine's stream), the agent-steps they
+    executed (recounted outside the timed region: rollouts are deterministic per (leaf, id)), the
+    per-launch kernel time, and the same steps end to end from pinned host buffers."""
+    import torch
+    from planner_mcts_b200 import RESULT_DTYPE
+    for i in range(warmup):
+        arm.step_device(i)
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(sampler_index) if sampler_index is not None else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(steps):
+        arm.step_device(warmup + i)
+    ev1.record(stream)
+    barrier()
+    out = {"elapsed_ms": ev0.elapsed_time(ev1), "launches": eng.launch_count() - launches0,
+           "clocks": sampler.summary() if sampler else None}
+    kernel_ms, total = [], 0
+    count_steps = min(steps, 4)   # the step totals of the other steps differ by < 0.1 %
+    for i in range(count_steps):
+        arm.step_device(warmup + i)
+        eng.sync()
+        kernel_ms.append(eng.last_kernel_ms())
+        res = arm.d_res.cpu().numpy().view(RESULT_DTYPE).reshape(-1)
+        total += int(res["agent_steps"].sum())
+    out["agent_steps_per_step"] = total / count_steps
+    out["kernel_ms"] = float(np.mean(kernel_ms))
+    out["mean_rollout_steps"] = float(res["n_steps"].mean())
+    out["lane_T"] = None
+    if want_e2e:
+        for i in range(max(1, min(warmup, 2))):
+            arm.step_host(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            arm.step_host(warmup + i)
+        torch.cuda.synchronize()
+        out["e2e_s"] = time.perf_counter() - t0
+        arm.step_host(warmup + count_steps - 1)
+        last = arm.h_res.numpy().view(RESULT_DTYPE).reshape(-1)
+        assert np.array_equal(last, res), "host-memory path and device-resident path disagree"
+    return out
+
+
+def roofline_of(m, A, coop, sm_mhz, peaks):
+    flop = flop_per_agent_step(A, coop)
+    achieved = m["agent_steps_per_step"] * flop / (m["kernel_ms"] * 1e-3) / 1e12
+    peak = 2 * 128 * 148 * sm_mhz * 1e6 / 1e12
+    return achieved, peak, flop
+
+
+def likelihood_benchmark(device, peaks, sm_mhz):
+    """bmcts_likelihood_batch at C5 size (32 agents x 64 hypotheses x 10^4 samples per world,
+    hypothesis/idm/hypothesis_idm.cpp:40-126), 16 worlds per call, device-resident"""
+    import torch
+    from planner_mcts_b200 import RolloutEngine, _abi, scenarios
+    cfg, scn, meta = scenarios.workload("c5_rsbg")
+    worlds, samples = 16, 10000
+    pose, alive, _ = scenarios.leaves_for(scn, meta, worlds, seed=11)
+    rng = np.random.default_rng(0)
+    action = rng.uniform(-3, 2, size=(scn.n_agents, worlds)).astype(np.float32)
+    eng = RolloutEngine(cfg, scn, device=device)
+    dev = torch.device("cuda", device)
+    d_pose = torch.from_numpy(pose).to(dev)
+    d_alive = torch.from_numpy(alive.view(np.int32)).to(dev)
+    d_action = torch.from_numpy(action).to(dev)
+    d_prob = torch.zeros(scn.n_agents * scn.n_hypotheses * worlds, dtype=torch.float32, device=dev)
+    ms = []
+    for i in range(13):
+        eng.likelihood_raw(worlds, _abi.MEM_DEVICE, d_pose, d_alive, d_action, d_prob,
+                           n_samples=samples, n_buckets=100, seed=3 + i)
+        eng.sync()
+        if i >= 3:
+            ms.append(eng.last_kernel_ms())
+    k_ms = float(np.median(ms))
+    evals = worlds * scn.n_agents * scn.n_hypotheses * samples
+    # per evaluation: the IDM acceleration (F_idm = 48 FLOP of SURVEY.md 8d) -- the Philox draw and
+    # the bucket test are integer work on top of it
+    achieved = evals * 48.0 / (k_ms * 1e-3) / 1e12
+    peak = 2 * 128 * 148 * sm_mhz * 1e6 / 1e12
+    # host call on one world: what a Plan() pays for its belief update
+    p1, a1, _ = scenarios.leaves_for(scn, meta, 1, seed=12)
+    act1 = action[:, :1].copy()
+    eng.likelihood(p1, a1, act1, n_samples=samples, n_buckets=100)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        eng.likelihood(p1, a1, act1, n_samples=samples, n_buckets=100)
+    call_ms = (time.perf_counter() - t0) / 10 * 1e3
+    return {"kernel": "bmcts::likelihood_kernel", "workload": "c5_rsbg", "worlds_per_call": worlds,
+            "evaluations_per_call": evals, "kernel_ms": k_ms,
+            "evaluations_per_s": evals / (k_ms * 1e-3),
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "flop_per_evaluation": 48},
+            "belief_update_of_one_plan_ms": call_ms}
+
+
 def run_reference(args):
     """CPU arm: the oracle (kind 'port') on all host cores, bounded sample per step."""
     import oracle
@@ -191,14 +353,15 @@ def run_reference(args):
     cfg, scn, meta = scenarios.workload(args.workload, horizon=args.horizon)
     cores = os.cpu_count() or 1
     n = args.cpu_rollouts
-    pose, alive, hyp = scenarios.leaves_for(scn, meta, n, seed=1)
+    pose, alive, hyp, index = make_batch(scn, meta, n, args.share, seed=1)
     oracle.load()
-    for w in range(args.warmup):
-        oracle.rollout(cfg, scn, pose[:, :max(64, n // 16)], alive[:max(64, n // 16)],
-                       hyp[:, :max(64, n // 16)], n_threads=cores)
+    kw = dict(state_index=index, n_threads=cores)
+    w = max(64, n // 16)
+    for _ in range(args.warmup):
+        oracle.rollout(cfg, scn, pose, alive, hyp[:, :w], **dict(kw, state_index=None if index is None else index[:w]))
     total, t0 = 0, time.perf_counter()
     for s in range(args.steps):
-        r = oracle.rollout(cfg, scn, pose, alive, hyp, first_rollout_id=s * n, n_threads=cores)
+        r = oracle.rollout(cfg, scn, pose, alive, hyp, first_rollout_id=s * n, **kw)
         total += int(r["result"]["agent_steps"].sum())
     dt = time.perf_counter() - t0
     val = total / dt
@@ -208,18 +371,32 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "agents": meta["A"], "hypotheses": meta["H"],
-                   "horizon": args.horizon, "rollouts_per_step": n},
+        "config": workload_config(args, meta, n, None),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "plan": None if args.no_plan else {k: v for k, v in plan_benchmark(
-            args.workload, args.horizon, args.cpu_plan_iterations, 1, "cpu").items() if k != "root_stats"},
+            args.workload, args.horizon, args.cpu_plan_iterations, 1, "cpu", trees=cores).items()
+            if k != "root_stats"},
         "note": "reference cannot be compiled here (Bazel + BARK + mamcts absent); this is the "
                 "in-repo CPU oracle, which has none of BARK's heap cloning and is therefore "
-                "faster than the real reference would be",
+                "faster than the real reference would be; the sample is a bounded batch of the "
+                "same workload (the GPU arm's step is rollouts_per_step_per_gpu of them)",
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_config(args, meta, n, extra):
+    """`config` of the JSON line: identical keys on both arms (the reference arm's step is a
+    bounded sample, its size is in cpu_baseline.sample)"""
+    c = {"workload": args.workload, "agents": meta["A"], "hypotheses": meta["H"],
+         "horizon": args.horizon, "ego_substeps": 10,
+         "leaf_form": ("unique-state table: rollouts / %d distinct leaf states, each under %d sampled "
+                       "hypothesis assignments" % (args.share, args.share)) if args.share > 1
+         else "one state per rollout"}
+    if extra:
+        c.update(extra)
+    return c
 
 
 def bind_to_gpu_numa_node(index):
@@ -241,11 +418,15 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
+OTHER_WORKLOADS = [("c1_highway_mdp", 1 << 20), ("c2_merge_sbg", 1 << 20), ("c3_merge_risk", 1 << 19),
+                   ("c4_coop", 1 << 19), ("c5_rsbg", 1 << 19)]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from planner_mcts_b200 import RESULT_DTYPE, RolloutEngine, _abi, scenarios
+    from planner_mcts_b200 import RolloutEngine, _abi, scenarios
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -258,101 +439,71 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg, scn, meta = scenarios.workload(args.workload, horizon=args.horizon)
-    A, n = meta["A"], args.rollouts
-    coop = cfg.state_kind == _abi.STATE_COOPERATIVE
-    pose, alive, hyp = scenarios.leaves_for(scn, meta, n, seed=1 + rank)
-    eng = RolloutEngine(cfg, scn, device=local_rank)
-    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
-
-    # ---- device-resident arm
-    d_pose = torch.from_numpy(pose).to(dev)
-    d_alive = torch.from_numpy(alive.view(np.int32)).to(dev)
-    d_hyp = torch.from_numpy(hyp).to(dev)
-    d_res = torch.zeros(n, 8, dtype=torch.float32, device=dev)
-    d_stats = torch.zeros(8, dtype=torch.float64, device=dev)
-    torch.cuda.synchronize()
-
-    def step_device(i):
-        eng.rollout_raw(n, _abi.MEM_DEVICE, d_pose, d_alive, d_hyp, None, d_res, seed=1000,
-                        stream=rank, first_rollout_id=i * n)
-
-    def merge_root_stats():
-        # root-parallel merge: sum of the per-rank root statistics over NVLink
-        with torch.cuda.stream(stream):
-            d_stats[:4] = d_res[:, :4].sum(0, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(d_stats)
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step_device(i)
-        merge_root_stats()
-    barrier()
-    launches0 = eng.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, total_steps = [], 0
-    ev0.record(stream)
-    for i in range(args.steps):
-        step_device(args.warmup + i)
-        merge_root_stats()
-    ev1.record(stream)
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - launches0
-    clocks = sampler.summary()
-    # agent-steps are deterministic per (leaf, rollout id): recount them outside the timed region
-    for i in range(args.steps):
-        step_device(args.warmup + i)
-        eng.sync()
-        kernel_ms.append(eng.last_kernel_ms())
-        res = d_res.cpu().numpy().view(RESULT_DTYPE).reshape(-1)
-        total_steps += int(res["agent_steps"].sum())
-    mean_rollout_len = float(res["n_steps"].mean())
+    peaks, peak_kind = measured_peaks()
 
-    # ---- end-to-end arm: pinned host buffers through the C ABI, copies inside the timed region
-    h_pose = torch.from_numpy(pose).pin_memory()
-    h_alive = torch.from_numpy(alive.view(np.int32)).pin_memory()
-    h_hyp = torch.from_numpy(hyp).pin_memory()
-    h_res = torch.zeros(n, 8, dtype=torch.float32).pin_memory()
+    # ---- the headline workload
+    cfg, scn, meta = scenarios.workload(args.workload, horizon=args.horizon)
+    A, n = meta["A"], args.rollouts
+    coop = cfg.state_kind == _abi.STATE_COOPERATIVE
+    eng = RolloutEngine(cfg, scn, device=local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+    arm = Arm(eng, scn, meta, n, args.share, 1 + rank, dev, rank)
+    m = measure(eng, arm, args.steps, args.warmup, stream, barrier, sampler_index=local_rank)
+    clocks = m["clocks"]
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    total_steps = m["agent_steps_per_step"] * args.steps
+    del arm
+    torch.cuda.empty_cache()
 
-    def step_host(i):
-        eng.rollout_raw(n, _abi.MEM_HOST, h_pose, h_alive, h_hyp, None, h_res, seed=1000,
-                        stream=rank, first_rollout_id=i * n)
+    # ---- the other BASELINE.json configs (short runs, device-resident + end to end)
+    table = {}
+    if not args.no_workloads:
+        for name, n_w in OTHER_WORKLOADS:
+            if name == args.workload:
+                continue
+            for tag, ego_dt, hz in ((name, 0.05, args.horizon),) + (
+                    (("c2_merge_sbg@reference_ego_dt_0.02", 0.02, args.horizon),
+                     ("c2_merge_sbg@rollout_cap_1000", 0.05, 1000)) if name == "c2_merge_sbg" else ()):
+                cfg_w, scn_w, meta_w = scenarios.workload(name, horizon=hz, ego_dt=ego_dt)
+                n_t = n_w if hz <= 100 else n_w // 4
+                eng_w = RolloutEngine(cfg_w, scn_w, device=local_rank)
+                st_w = torch.cuda.ExternalStream(eng_w.stream_ptr(), device=dev)
+                arm_w = Arm(eng_w, scn_w, meta_w, n_t, args.share, 11 + rank, dev, rank)
+                mw = measure(eng_w, arm_w, 5, 3, st_w, barrier)
+                coop_w = cfg_w.state_kind == _abi.STATE_COOPERATIVE
+                ach, peak, flop = roofline_of(mw, meta_w["A"], coop_w, sm_mhz, peaks)
+                table[tag] = {
+                    "agents": meta_w["A"], "hypotheses": meta_w["H"], "horizon": hz,
+                    "rollouts_per_step": n_t, "ego_substeps": 25 if ego_dt == 0.02 else 10,
+                    "value": mw["agent_steps_per_step"] * 5 / (mw["elapsed_ms"] * 1e-3),
+                    "e2e": mw["agent_steps_per_step"] * 5 / mw["e2e_s"],
+                    "kernel_ms": mw["kernel_ms"], "mean_rollout_steps": mw["mean_rollout_steps"],
+                    "roofline_frac": ach / peak, "flop_per_agent_step": flop,
+                    "kernel": "bmcts::rollout_lane_coop_kernel" if coop_w else "bmcts::rollout_lane_kernel"}
+                del arm_w, eng_w
+                torch.cuda.empty_cache()
 
-    for i in range(max(1, args.warmup)):
-        step_host(i)
-    barrier()
-    # the timed steps use the rollout ids of the device-resident arm, so the agent-steps
-    # they execute are the ones counted above (checked on the last step, outside the timing)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_host(args.warmup + i)   # returns when the results are in the pinned host buffer
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_steps = total_steps
-    last = h_res.numpy().view(RESULT_DTYPE).reshape(-1)
-    assert np.array_equal(last, res), "host-memory path and device-resident path disagree"
+    # ---- belief-update kernel
+    lik = None
+    if rank == 0 and not args.no_workloads:
+        lik = likelihood_benchmark(local_rank, peaks, sm_mhz)
 
-    # ---- Plan() arm: one BehaviorUCT*::Plan per rank (root-parallel: tree index = rank), root
-    # statistics merged with an NCCL all-reduce
+    # ---- Plan() arm: one BehaviorUCT*::Plan() of --plan-iterations MCTS iterations in total,
+    # root-parallel over the ranks (tree indices are disjoint), root statistics merged with one
+    # NCCL all-reduce (BASELINE.json configs[4]: 10^6 rollouts per Plan())
     plan = None
     if not args.no_plan:
         threads = max(1, min(16, (os.cpu_count() or 1) // world))
-        if args.plan_trees <= 0:
-            # two trees per host thread: a thread interleaves their waves, so the GPU works on
-            # one tree while the thread selects / backs up the other
-            args.plan_trees = 2 * threads
-        g = plan_benchmark(args.workload, args.horizon, args.plan_iterations, args.plan_wave, "gpu",
-                           device=local_rank, tree_index=rank, trees=args.plan_trees,
-                           threads=threads)
+        trees = args.plan_trees if args.plan_trees > 0 else 2 * threads
+        per_tree = max(1, args.plan_iterations // (world * trees))
+        g = plan_benchmark(args.workload, args.horizon, per_tree, args.plan_wave, "gpu",
+                           device=local_rank, tree_index=rank, trees=trees, threads=threads)
         from planner_mcts_b200 import root_parallel
         ms = torch.tensor([g["plan_ms"]], dtype=torch.float64, device=dev)
         torch.cuda.synchronize()
@@ -367,47 +518,43 @@ def run_ours(args):
         mean = np.where(cnt > 0, ret / np.maximum(cnt, 1), -np.inf)
         plan = dict(g, iterations=int(st[-2]), plan_ms=float(ms[0]), merge_ms=merge_ms,
                     iterations_per_s=float(st[-2]) / (float(ms[0]) * 1e-3),
-                    merged_best_action=int(np.argmax(mean)), trees=world)
+                    merged_best_action=int(np.argmax(mean)), trees=world * trees,
+                    workload=args.workload, host_cores=os.cpu_count())
 
     # ---- reduce over ranks: time = max, work = sum
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    w = torch.tensor([float(total_steps), float(e2e_steps), float(launches)], dtype=torch.float64,
-                     device=dev)
+    t = torch.tensor([m["elapsed_ms"], m["e2e_s"] * 1e3], dtype=torch.float64, device=dev)
+    w = torch.tensor([float(total_steps), float(m["launches"])], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
     elapsed_ms, e2e_ms = float(t[0]), float(t[1])
-    total_all, e2e_all, launches_all = float(w[0]), float(w[1]), int(w[2])
+    total_all, launches_all = float(w[0]), int(w[1])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     value = total_all / (elapsed_ms * 1e-3)
-    e2e_value = e2e_all / (e2e_ms * 1e-3)
-    peaks, peak_kind = measured_peaks()
-    k_ms = float(np.mean(kernel_ms))
-    steps_per_launch = total_steps / args.steps
-    flop = flop_per_agent_step(A, coop)
-    achieved_tflops = steps_per_launch * flop / (k_ms * 1e-3) / 1e12
-    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    peak_tflops = 2 * 128 * 148 * sm_mhz * 1e6 / 1e12
+    e2e_value = total_all / (e2e_ms * 1e-3)
+    k_ms = m["kernel_ms"]
+    achieved_tflops, peak_tflops, flop = roofline_of(m, A, coop, sm_mhz, peaks)
     peak_tflops_max = 2 * 128 * 148 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
-    hbm_gbs = n * hbm_bytes_per_rollout(A) / (k_ms * 1e-3) / 1e9
+    alg_bytes = n * hbm_bytes_per_rollout(A, args.share)
+    hbm_gbs = alg_bytes / (k_ms * 1e-3) / 1e9
+    in_bytes = input_bytes_per_step(A, n, args.share)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "agents": A, "hypotheses": meta["H"],
-                   "horizon": args.horizon, "rollouts_per_step_per_gpu": n,
-                   "mean_rollout_steps": mean_rollout_len,
-                   "l2": "inputs larger than L2 (leaf batch %.0f MB per step)" %
-                         (n * (A * 17 + 4) / 1e6),
-                   "rollouts_per_s": n * world / (elapsed_ms / args.steps * 1e-3),
-                   "cpus_bound_per_rank": numa},
+        "config": workload_config(args, meta, n, {
+            "rollouts_per_step_per_gpu": n, "mean_rollout_steps": m["mean_rollout_steps"],
+            "l2": "inputs larger than L2 (%.0f MB of leaf states, hypothesis ids and indices per "
+                  "step)" % (in_bytes / 1e6),
+            "rollouts_per_s": n * world / (elapsed_ms / args.steps * 1e-3),
+            "timed_region_s": elapsed_ms * 1e-3, "cpus_bound_per_rank": numa}),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": int(n * (A * 17 + 4)), "d2h_bytes_per_step": int(n * 32)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": int(n * 32)},
         "gpu_launches": launches_all,
         "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops,
                      "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
@@ -415,72 +562,98 @@ def run_ours(args):
                      "peak_def": "2 x 128 FP32 lanes x 148 SMs x SM clock under load (%s MHz); "
                                  "algorithmic FLOPs per agent-step = %.0f (SURVEY.md 8d)" %
                                  (sm_mhz, flop),
-                     "kernel": "bmcts::rollout_lane_coop_kernel" if coop else "bmcts::rollout_lane_kernel", "kernel_ms": k_ms, "traffic": measured_traffic(args.workload, n),
-                     "traffic_algorithmic": n * hbm_bytes_per_rollout(A)},
+                     "kernel": "bmcts::rollout_lane_coop_kernel" if coop else "bmcts::rollout_lane_kernel",
+                     "kernel_ms": k_ms, "traffic": measured_traffic(args.workload, n),
+                     "traffic_algorithmic": alg_bytes},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks.get("hbm_gbs"),
                          "unit": "GB/s", "frac": hbm_gbs / peaks.get("hbm_gbs", 6650.0),
                          "peak_kind": peak_kind, "traffic": None},
     }
+    if table:
+        line["workloads"] = table
+    if lik is not None:
+        line["likelihood"] = lik
     if plan is not None:
         line["plan"] = plan
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cfg, scn, meta)
         if plan is not None:
+            cores = os.cpu_count() or 1
             c = plan_benchmark(args.workload, args.horizon, args.cpu_plan_iterations, 1, "cpu")
             c.pop("root_stats")
             line["cpu_baseline"]["plan"] = c   # the reference's default: one sequential tree
-            cores = os.cpu_count() or 1
             c = plan_benchmark(args.workload, args.horizon, args.cpu_plan_iterations, 1, "cpu", trees=cores)
             c.pop("root_stats")
             line["cpu_baseline"]["plan_all_cores"] = c   # NumParallelMcts = cores, UseMultiThreading
+    if world == 1 and not args.no_plan:
+        # the reference's default budget (Mcts::MaxNumIterations 2000, one tree, default wave) on
+        # c2 with 20-step rollouts: what one BARK agent pays per Plan()
+        gd = plan_benchmark("c2_merge_sbg", 20, 2000, 0, "gpu", device=local_rank)
+        cd = plan_benchmark("c2_merge_sbg", 20, 2000, 1, "cpu")
+        line["plan_default_budget"] = {
+            "workload": "c2_merge_sbg", "iterations": 2000, "trees": 1, "wave": "default",
+            "gpu_plan_ms": gd["plan_ms"], "gpu_plan_ms_all": gd["plan_ms_all"],
+            "cpu_plan_ms": cd["plan_ms"], "speedup": cd["plan_ms"] / gd["plan_ms"]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def cpu_baseline(args, cfg, scn, meta):
-    """oracle ('port') on the host cores, bounded to roughly 10-20 s of CPU work"""
+    """oracle ('port') on the host cores, bounded to roughly 10-20 s of CPU work; the same
+    per-call batch as the reference arm (--cpu-rollouts)"""
     import oracle
-    from planner_mcts_b200 import scenarios
     cores = os.cpu_count() or 1
-    n = 16384
-    pose, alive, hyp = scenarios.leaves_for(scn, meta, n, seed=1)
+    n = args.cpu_rollouts
+    pose, alive, hyp, index = make_batch(scn, meta, n, args.share, seed=1)
     oracle.load()
-    oracle.rollout(cfg, scn, pose[:, :256], alive[:256], hyp[:, :256], n_threads=cores)  # warm-up
+    w = max(64, n // 64)
+    oracle.rollout(cfg, scn, pose, alive, hyp[:, :w], n_threads=cores,
+                   state_index=None if index is None else index[:w])  # warm-up
 
-    def timed(n_threads, budget_s):
+    def timed(n_threads, budget_s, m):
         steps, calls, t0 = 0, 0, time.perf_counter()
         while time.perf_counter() - t0 < budget_s:
-            r = oracle.rollout(cfg, scn, pose, alive, hyp, first_rollout_id=calls * n,
-                               n_threads=n_threads)
+            r = oracle.rollout(cfg, scn, pose, alive, hyp[:, :m], first_rollout_id=calls * n,
+                               n_threads=n_threads,
+                               state_index=None if index is None else index[:m])
             steps += int(r["result"]["agent_steps"].sum())
             calls += 1
         dt = time.perf_counter() - t0
         return steps / dt, calls, dt
 
-    one_thread, c1, t1 = timed(1, 4.0)
-    val, c2, t2 = timed(cores, 10.0)
+    m1 = max(256, n // 16)
+    one_thread, c1, t1 = timed(1, 4.0, m1)
+    val, c2, t2 = timed(cores, 10.0, n)
     return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
             "one_thread_value": one_thread,
             "sample": f"{c2 * n} rollouts of {args.workload} (horizon {args.horizon}) on {cores} "
-                      f"threads in {t2:.1f} s; {c1 * n} rollouts on 1 thread in {t1:.1f} s"}
+                      f"threads in {t2:.1f} s ({n} per call); {c1 * m1} rollouts on 1 thread in {t1:.1f} s"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2_merge_sbg")
+    ap.add_argument("--workload", default="c5_rsbg")
     ap.add_argument("--horizon", type=int, default=20)
-    ap.add_argument("--rollouts", type=int, default=1 << 20, help="leaf states per step per GPU")
-    ap.add_argument("--cpu-rollouts", type=int, default=65536, help="reference arm: leaves per step")
+    ap.add_argument("--rollouts", type=int, default=1 << 22, help="rollouts per step per GPU")
+    ap.add_argument("--share", type=int, default=16,
+                    help="rollouts per distinct leaf state (unique-state form of the C ABI); 1 = one "
+                         "state per rollout")
+    ap.add_argument("--cpu-rollouts", type=int, default=65536,
+                    help="CPU arms (reference arm, cpu_baseline): rollouts per call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-plan", action="store_true", help="skip the Plan() iterations/s arm")
+    ap.add_argument("--no-plan", action="store_true", help="skip the Plan() iterations/s arms")
+    ap.add_argument("--no-workloads", action="store_true",
+                    help="skip the table of the other workloads and the likelihood kernel")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="multi-rank runs: do not bind the process to the CPUs next to its GPU")
-    ap.add_argument("--plan-iterations", type=int, default=32768)
+    ap.add_argument("--plan-iterations", type=int, default=1 << 20,
+                    help="MCTS iterations of the Plan() arm in total, split over ranks and trees "
+                         "(BASELINE.json configs[4]: 10^6 rollouts per Plan())")
     ap.add_argument("--plan-wave", type=int, default=0,
                     help="iterations per engine batch; 0 = the planner's default (iterations / 128, "
                          "at most 256), which keeps root values within Monte-Carlo noise of the "
@@ -488,8 +661,10 @@ def main():
     ap.add_argument("--plan-trees", type=int, default=0,
                     help="root-parallel trees per process (Mcts::NumParallelMcts); 0 = two per host "
                          "thread, with host threads = cores / ranks, at most 16")
-    ap.add_argument("--cpu-plan-iterations", type=int, default=4000)
+    ap.add_argument("--cpu-plan-iterations", type=int, default=2000)
     args = ap.parse_args()
+    if args.share < 1 or args.rollouts % args.share or args.cpu_rollouts % args.share:
+        raise SystemExit("--rollouts and --cpu-rollouts must be multiples of --share")
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)   # timing rule: at least three untimed warm-up steps
     if args.impl == "reference":

@@ -275,14 +275,20 @@ typedef struct bmcts_rollout_result {
 typedef struct bmcts_leaf_batch {
   int32_t n_leaves;
   int32_t memory;            /* BMCTS_MEM_HOST / BMCTS_MEM_DEVICE for ALL pointers below */
-  const float* pose;         /* [A][n][4] */
-  const uint32_t* alive;     /* [n] bit a = agent slot a present */
+  const float* pose;         /* [A][n][4]  ([A][n_states][4] in the unique-state form) */
+  const uint32_t* alive;     /* [n] bit a = agent slot a present  ([n_states]) */
   const uint8_t* hyp_id;     /* [A][n] sampled hypothesis per agent (slot 0 ignored) */
-  const uint16_t* depth;     /* [n] depth_ of the leaf state (root = 1), NULL = all 1 */
+  const uint16_t* depth;     /* [n] depth_ of the leaf state (root = 1), NULL = all 1  ([n_states]) */
   uint64_t seed;             /* Mcts::RandomSeed */
   uint32_t stream;           /* root-parallel stream (rank / tree index) */
   uint32_t pad_;
   uint64_t first_rollout_id; /* rollout k uses Philox counter id first_rollout_id + k */
+  /* Unique-state form (the waves of a search revisit few distinct states,
+   * under freshly sampled hypotheses): pose / alive / depth hold n_states distinct states and
+   * rollout k starts from state state_index[k].  n_states == 0: one state per leaf. */
+  int32_t n_states;
+  int32_t pad2_;
+  const uint32_t* state_index; /* [n], each < n_states; NULL when n_states == 0 */
 } bmcts_leaf_batch;
 
 typedef struct bmcts_rollout_out {

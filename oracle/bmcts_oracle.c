@@ -809,22 +809,33 @@ typedef struct {
   const bmcts_scenario* scn;
   const bmcts_leaf_batch* in;
   const bmcts_rollout_out* out;
-  int begin, end;
+  int* next; /* shared work counter: threads take chunks of rollouts until the batch is drained */
 } rollout_job_t;
+
+#define ROLLOUT_CHUNK 64
 
 static void* rollout_worker(void* arg) {
   rollout_job_t* j = (rollout_job_t*)arg;
   int A = j->scn->n_agents, n = j->in->n_leaves;
-  for (int k = j->begin; k < j->end; ++k) {
-    unsigned depth = j->in->depth ? j->in->depth[k] : 1u;
-    float pose[MAXA * 4], ra[MAXA], fp[MAXA * 4];
-    uint8_t hyp[MAXA];
-    gather_f4(j->in->pose, A, n, k, pose);
-    gather_u8(j->in->hyp_id, A, n, k, hyp);
-    oracle_rollout(j->cfg, j->scn, pose, j->in->alive[k], hyp, depth, j->in->seed, j->in->stream,
-                   j->in->first_rollout_id + (uint64_t)k, &j->out->result[k], ra, fp);
-    if (j->out->ret_agents) scatter_f1(j->out->ret_agents, A, n, k, ra);
-    if (j->out->final_pose) scatter_f4(j->out->final_pose, A, n, k, fp);
+  /* unique-state form: pose / alive / depth are tables of n_states rows */
+  int ns = j->in->n_states > 0 ? j->in->n_states : n;
+  for (;;) {
+    int begin = __atomic_fetch_add(j->next, ROLLOUT_CHUNK, __ATOMIC_RELAXED);
+    if (begin >= n) break;
+    int end = begin + ROLLOUT_CHUNK < n ? begin + ROLLOUT_CHUNK : n;
+    for (int k = begin; k < end; ++k) {
+      int row = j->in->n_states > 0 ? (int)j->in->state_index[k] : k;
+      unsigned depth = j->in->depth ? j->in->depth[row] : 1u;
+      float pose[MAXA * 4], ra[MAXA], fp[MAXA * 4];
+      uint8_t hyp[MAXA];
+      gather_f4(j->in->pose, A, ns, row, pose);
+      gather_u8(j->in->hyp_id, A, n, k, hyp);
+      oracle_rollout(j->cfg, j->scn, pose, j->in->alive[row], hyp, depth, j->in->seed,
+                     j->in->stream, j->in->first_rollout_id + (uint64_t)k, &j->out->result[k], ra,
+                     fp);
+      if (j->out->ret_agents) scatter_f1(j->out->ret_agents, A, n, k, ra);
+      if (j->out->final_pose) scatter_f4(j->out->final_pose, A, n, k, fp);
+    }
   }
   return NULL;
 }
@@ -835,26 +846,19 @@ int oracle_rollout_batch(const bmcts_config* cfg, const bmcts_scenario* scn,
   int st = check_args(cfg, scn);
   if (st) return st;
   if (!in || !out || !out->result || in->memory != BMCTS_MEM_HOST) return BMCTS_ERR_INVALID_ARG;
+  if (in->n_states < 0 || (in->n_states > 0 && !in->state_index)) return BMCTS_ERR_INVALID_ARG;
   if (n_threads < 1) n_threads = 1;
   if (n_threads > 256) n_threads = 256;
-  if (n_threads > in->n_leaves) n_threads = in->n_leaves > 0 ? in->n_leaves : 1;
-  rollout_job_t jobs[256];
-  pthread_t th[256];
-  int per = (in->n_leaves + n_threads - 1) / n_threads;
-  for (int t = 0; t < n_threads; ++t) {
-    jobs[t].cfg = cfg;
-    jobs[t].scn = scn;
-    jobs[t].in = in;
-    jobs[t].out = out;
-    jobs[t].begin = t * per;
-    jobs[t].end = (t + 1) * per < in->n_leaves ? (t + 1) * per : in->n_leaves;
-    if (jobs[t].begin > jobs[t].end) jobs[t].begin = jobs[t].end;
-  }
+  int max_useful = (in->n_leaves + ROLLOUT_CHUNK - 1) / ROLLOUT_CHUNK;
+  if (n_threads > max_useful) n_threads = max_useful > 0 ? max_useful : 1;
+  int next = 0;
+  rollout_job_t job = {cfg, scn, in, out, &next};
   if (n_threads == 1) {
-    rollout_worker(&jobs[0]);
+    rollout_worker(&job);
     return BMCTS_OK;
   }
-  for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, rollout_worker, &jobs[t]);
+  pthread_t th[256];
+  for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, rollout_worker, &job);
   for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
   return BMCTS_OK;
 }

@@ -115,6 +115,7 @@ class LeafBatch(C.Structure):
         ("n_leaves", i32), ("memory", i32), ("pose", C.c_void_p), ("alive", C.c_void_p),
         ("hyp_id", C.c_void_p), ("depth", C.c_void_p), ("seed", u64), ("stream", u32),
         ("pad_", u32), ("first_rollout_id", u64),
+        ("n_states", i32), ("pad2_", i32), ("state_index", C.c_void_p),
     ]
 
 

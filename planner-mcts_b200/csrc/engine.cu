@@ -74,7 +74,7 @@ struct bmcts_engine {
   struct PipeSlot {
     cudaStream_t stream = nullptr;
     unsigned int* d_counter = nullptr;
-    DevBuf pose, alive, hyp, depth, result, ret_agents, final_pose;
+    DevBuf pose, alive, hyp, depth, index, result, ret_agents, final_pose;
   };
   static const int kPipeSlots = 3;
   PipeSlot pipe[kPipeSlots];
@@ -83,7 +83,7 @@ struct bmcts_engine {
   unsigned int* h_ready = nullptr;   // pinned: h_ready[c] = c + 1
   int h_ready_cap = 0;
   // staging buffers for host-pointer calls
-  DevBuf b_pose, b_alive, b_hyp, b_depth, b_action, b_draw;
+  DevBuf b_pose, b_alive, b_hyp, b_depth, b_action, b_draw, b_index;
   DevBuf b_next_pose, b_next_alive, b_reward, b_cost, b_flags, b_last_action;
   DevBuf b_result, b_ret_agents, b_final_pose, b_prob, b_lik_action;
 };
@@ -277,6 +277,7 @@ void base_args(bmcts_engine* e, bmcts::KernelArgs& a, int n, uint64_t seed, uint
   a.cfg = e->d_cfg;
   a.dt_table = e->use_dt_table ? e->d_dt_table : nullptr;
   a.n = n;
+  a.ns = n;  // one start state per element unless a state index is given
   a.A = e->scn.n_agents;
   a.C = e->scn.n_corridors;
   a.H = e->scn.n_hypotheses;
@@ -353,12 +354,15 @@ int rollout_host_streamed(bmcts_engine* e, const bmcts_leaf_batch* in, const bmc
   const int n = in->n_leaves, A = e->scn.n_agents;
   const int chunk = stream_chunk(n);
   const int n_chunks = (n + chunk - 1) / chunk;
+  const bool indexed = in->n_states > 0;
+  const int ns = indexed ? in->n_states : n;
   int st;
-  if ((st = ensure(e, e->b_pose, sizeof(float) * 4 * (size_t)n * A))) return st;
-  if ((st = ensure(e, e->b_alive, sizeof(uint32_t) * (size_t)n))) return st;
+  if ((st = ensure(e, e->b_pose, sizeof(float) * 4 * (size_t)ns * A))) return st;
+  if ((st = ensure(e, e->b_alive, sizeof(uint32_t) * (size_t)ns))) return st;
   if ((st = ensure(e, e->b_result, sizeof(bmcts_rollout_result) * (size_t)n))) return st;
   if (in->hyp_id && (st = ensure(e, e->b_hyp, (size_t)n * A))) return st;
-  if (in->depth && (st = ensure(e, e->b_depth, sizeof(uint16_t) * (size_t)n))) return st;
+  if (in->depth && (st = ensure(e, e->b_depth, sizeof(uint16_t) * (size_t)ns))) return st;
+  if (indexed && (st = ensure(e, e->b_index, sizeof(uint32_t) * (size_t)n))) return st;
   if (out->ret_agents && (st = ensure(e, e->b_ret_agents, sizeof(float) * (size_t)n * A))) return st;
   if (out->final_pose && (st = ensure(e, e->b_final_pose, sizeof(float) * 4 * (size_t)n * A)))
     return st;
@@ -379,6 +383,7 @@ int rollout_host_streamed(bmcts_engine* e, const bmcts_leaf_batch* in, const bmc
   a.alive = (const uint32_t*)e->b_alive.ptr;
   a.hyp = in->hyp_id ? (const uint8_t*)e->b_hyp.ptr : nullptr;
   a.depth = in->depth ? (const uint16_t*)e->b_depth.ptr : nullptr;
+  a.state_index = indexed ? (const uint32_t*)e->b_index.ptr : nullptr;
   a.result = (bmcts_rollout_result*)e->b_result.ptr;
   // result records go straight into the caller's buffer when it is pinned host memory the
   // device can address (32-byte posted writes over PCIe while the kernel runs): no download
@@ -397,20 +402,37 @@ int rollout_host_streamed(bmcts_engine* e, const bmcts_leaf_batch* in, const bmc
   a.final_pose = out->final_pose ? (float4*)e->b_final_pose.ptr : nullptr;
   a.ready = e->d_ready;
   a.chunk = (unsigned int)chunk;
+  if (indexed) {
+    // unique-state form: the (small) state table goes first, on the copy stream, so the counter
+    // of chunk 0 also says that the table has arrived; the chunks carry hypothesis ids + indices
+    CU(cudaMemcpyAsync(e->b_pose.ptr, in->pose, sizeof(float) * 4 * (size_t)ns * A,
+                       cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(e->b_alive.ptr, in->alive, sizeof(uint32_t) * (size_t)ns,
+                       cudaMemcpyHostToDevice, cs));
+    if (in->depth)
+      CU(cudaMemcpyAsync(e->b_depth.ptr, in->depth, sizeof(uint16_t) * (size_t)ns,
+                         cudaMemcpyHostToDevice, cs));
+  }
   for (int c = 0; c < n_chunks; ++c) {
     const size_t k0 = (size_t)c * chunk;
     const size_t m = (n - k0 < (size_t)chunk) ? n - k0 : (size_t)chunk;
     // one strided (2-D) copy per array and chunk: A rows of m elements, row pitch n elements
-    CU(cudaMemcpy2DAsync((char*)e->b_pose.ptr + k0 * 16, (size_t)n * 16, in->pose + k0 * 4,
-                         (size_t)n * 16, m * 16, A, cudaMemcpyHostToDevice, cs));
+    if (!indexed)
+      CU(cudaMemcpy2DAsync((char*)e->b_pose.ptr + k0 * 16, (size_t)n * 16, in->pose + k0 * 4,
+                           (size_t)n * 16, m * 16, A, cudaMemcpyHostToDevice, cs));
     if (in->hyp_id)
       CU(cudaMemcpy2DAsync((char*)e->b_hyp.ptr + k0, (size_t)n, in->hyp_id + k0, (size_t)n, m, A,
                            cudaMemcpyHostToDevice, cs));
-    CU(cudaMemcpyAsync((char*)e->b_alive.ptr + k0 * 4, in->alive + k0, m * 4, cudaMemcpyHostToDevice,
-                       cs));
-    if (in->depth)
-      CU(cudaMemcpyAsync((char*)e->b_depth.ptr + k0 * 2, in->depth + k0, m * 2,
+    if (indexed) {
+      CU(cudaMemcpyAsync((char*)e->b_index.ptr + k0 * 4, in->state_index + k0, m * 4,
                          cudaMemcpyHostToDevice, cs));
+    } else {
+      CU(cudaMemcpyAsync((char*)e->b_alive.ptr + k0 * 4, in->alive + k0, m * 4,
+                         cudaMemcpyHostToDevice, cs));
+      if (in->depth)
+        CU(cudaMemcpyAsync((char*)e->b_depth.ptr + k0 * 2, in->depth + k0, m * 2,
+                           cudaMemcpyHostToDevice, cs));
+    }
     CU(cudaMemcpyAsync(e->d_ready, e->h_ready + c, sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
     if (c == 0) {  // the kernel starts while the first chunk is in flight
       CU(cudaEventRecord(e->ev_start, ks));
@@ -444,6 +466,21 @@ int rollout_host_pipelined(bmcts_engine* e, const bmcts_leaf_batch* in, const bm
                            const bmcts::KernelArgs& base) {
   const int n = in->n_leaves, A = e->scn.n_agents;
   const int chunk = pipeline_chunk(n);
+  const bool indexed = in->n_states > 0;
+  const int ns = indexed ? in->n_states : n;
+  int st;
+  if (indexed) {  // the state table is shared by every chunk: uploaded once, ahead of the slots
+    if ((st = ensure(e, e->b_pose, sizeof(float) * 4 * (size_t)ns * A))) return st;
+    if ((st = ensure(e, e->b_alive, sizeof(uint32_t) * (size_t)ns))) return st;
+    if (in->depth && (st = ensure(e, e->b_depth, sizeof(uint16_t) * (size_t)ns))) return st;
+    CU(cudaMemcpyAsync(e->b_pose.ptr, in->pose, sizeof(float) * 4 * (size_t)ns * A,
+                       cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->b_alive.ptr, in->alive, sizeof(uint32_t) * (size_t)ns,
+                       cudaMemcpyHostToDevice, e->stream));
+    if (in->depth)
+      CU(cudaMemcpyAsync(e->b_depth.ptr, in->depth, sizeof(uint16_t) * (size_t)ns,
+                         cudaMemcpyHostToDevice, e->stream));
+  }
   // the slots' streams start after everything already queued on the engine stream
   CU(cudaEventRecord(e->ev_pipe, e->stream));
   for (auto& sl : e->pipe) CU(cudaStreamWaitEvent(sl.stream, e->ev_pipe, 0));
@@ -451,34 +488,51 @@ int rollout_host_pipelined(bmcts_engine* e, const bmcts_leaf_batch* in, const bm
   for (int k0 = 0; k0 < n; k0 += chunk, ++idx) {
     const int m = (n - k0 < chunk) ? n - k0 : chunk;
     bmcts_engine::PipeSlot& sl = e->pipe[idx % bmcts_engine::kPipeSlots];
-    int st;
-    if ((st = ensure(e, sl.pose, sizeof(float) * 4 * (size_t)chunk * A))) return st;
-    if ((st = ensure(e, sl.alive, sizeof(uint32_t) * (size_t)chunk))) return st;
+    if (!indexed) {
+      if ((st = ensure(e, sl.pose, sizeof(float) * 4 * (size_t)chunk * A))) return st;
+      if ((st = ensure(e, sl.alive, sizeof(uint32_t) * (size_t)chunk))) return st;
+      if (in->depth && (st = ensure(e, sl.depth, sizeof(uint16_t) * (size_t)chunk))) return st;
+    } else if ((st = ensure(e, sl.index, sizeof(uint32_t) * (size_t)chunk))) {
+      return st;
+    }
     if ((st = ensure(e, sl.result, sizeof(bmcts_rollout_result) * (size_t)chunk))) return st;
     if (in->hyp_id && (st = ensure(e, sl.hyp, (size_t)chunk * A))) return st;
-    if (in->depth && (st = ensure(e, sl.depth, sizeof(uint16_t) * (size_t)chunk))) return st;
     if (out->ret_agents && (st = ensure(e, sl.ret_agents, sizeof(float) * (size_t)chunk * A))) return st;
     if (out->final_pose && (st = ensure(e, sl.final_pose, sizeof(float) * 4 * (size_t)chunk * A)))
       return st;
     cudaStream_t s = sl.stream;
     // ensure() may have re-allocated: safe, the slot's previous chunk is complete in stream order
-    CU(cudaMemcpy2DAsync(sl.pose.ptr, (size_t)m * 16, in->pose + (size_t)k0 * 4, (size_t)n * 16,
-                         (size_t)m * 16, A, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(sl.alive.ptr, in->alive + k0, sizeof(uint32_t) * (size_t)m,
-                       cudaMemcpyHostToDevice, s));
+    if (!indexed) {
+      CU(cudaMemcpy2DAsync(sl.pose.ptr, (size_t)m * 16, in->pose + (size_t)k0 * 4, (size_t)n * 16,
+                           (size_t)m * 16, A, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(sl.alive.ptr, in->alive + k0, sizeof(uint32_t) * (size_t)m,
+                         cudaMemcpyHostToDevice, s));
+      if (in->depth)
+        CU(cudaMemcpyAsync(sl.depth.ptr, in->depth + k0, sizeof(uint16_t) * (size_t)m,
+                           cudaMemcpyHostToDevice, s));
+    } else {
+      CU(cudaMemcpyAsync(sl.index.ptr, in->state_index + k0, sizeof(uint32_t) * (size_t)m,
+                         cudaMemcpyHostToDevice, s));
+    }
     if (in->hyp_id)
       CU(cudaMemcpy2DAsync(sl.hyp.ptr, (size_t)m, in->hyp_id + k0, (size_t)n, (size_t)m, A,
                            cudaMemcpyHostToDevice, s));
-    if (in->depth)
-      CU(cudaMemcpyAsync(sl.depth.ptr, in->depth + k0, sizeof(uint16_t) * (size_t)m,
-                         cudaMemcpyHostToDevice, s));
     bmcts::KernelArgs a = base;
     a.n = m;
     a.first_rollout_id = base.first_rollout_id + (uint64_t)k0;
-    a.pose = (const float4*)sl.pose.ptr;
-    a.alive = (const uint32_t*)sl.alive.ptr;
+    if (indexed) {
+      a.ns = ns;
+      a.pose = (const float4*)e->b_pose.ptr;
+      a.alive = (const uint32_t*)e->b_alive.ptr;
+      a.depth = in->depth ? (const uint16_t*)e->b_depth.ptr : nullptr;
+      a.state_index = (const uint32_t*)sl.index.ptr;
+    } else {
+      a.ns = m;
+      a.pose = (const float4*)sl.pose.ptr;
+      a.alive = (const uint32_t*)sl.alive.ptr;
+      a.depth = in->depth ? (const uint16_t*)sl.depth.ptr : nullptr;
+    }
     a.hyp = in->hyp_id ? (const uint8_t*)sl.hyp.ptr : nullptr;
-    a.depth = in->depth ? (const uint16_t*)sl.depth.ptr : nullptr;
     a.result = (bmcts_rollout_result*)sl.result.ptr;
     a.ret_agents = out->ret_agents ? (float*)sl.ret_agents.ptr : nullptr;
     a.final_pose = out->final_pose ? (float4*)sl.final_pose.ptr : nullptr;
@@ -675,7 +729,7 @@ void bmcts_destroy(bmcts_engine* e) {
                     &e->b_action,    &e->b_draw,       &e->b_next_pose,  &e->b_next_alive,
                     &e->b_reward,    &e->b_cost,       &e->b_flags,      &e->b_last_action,
                     &e->b_result,    &e->b_ret_agents, &e->b_final_pose, &e->b_prob,
-                    &e->b_lik_action};
+                    &e->b_lik_action, &e->b_index};
   for (DevBuf* b : bufs) free_buf(*b);
   if (e->d_cfg) cudaFree(e->d_cfg);
   if (e->d_scn) cudaFree(e->d_scn);
@@ -683,7 +737,7 @@ void bmcts_destroy(bmcts_engine* e) {
   if (e->d_counter) cudaFree(e->d_counter);
   for (auto& sl : e->pipe) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
-    DevBuf* sb[] = {&sl.pose, &sl.alive, &sl.hyp, &sl.depth, &sl.result, &sl.ret_agents, &sl.final_pose};
+    DevBuf* sb[] = {&sl.pose, &sl.alive, &sl.hyp, &sl.depth, &sl.index, &sl.result, &sl.ret_agents, &sl.final_pose};
     for (DevBuf* b : sb) free_buf(*b);
     if (sl.d_counter) cudaFree(sl.d_counter);
     if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -771,11 +825,17 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
   a.first_rollout_id = in->first_rollout_id;
   if (e->cfg.max_rollout_steps <= 0)
     return fail(e, BMCTS_ERR_INVALID_ARG, "rollout_batch: max_rollout_steps must be > 0");
+  const bool indexed = in->n_states > 0;
+  if (in->n_states < 0 || (indexed && !in->state_index) || (!indexed && in->state_index))
+    return fail(e, BMCTS_ERR_INVALID_ARG, "rollout_batch: n_states and state_index go together");
+  const int ns = indexed ? in->n_states : n;  // rows of the pose / alive / depth tables
+  a.ns = ns;
   if (in->memory == BMCTS_MEM_DEVICE) {
     a.pose = (const float4*)in->pose;
     a.alive = in->alive;
     a.hyp = in->hyp_id;
     a.depth = in->depth;
+    a.state_index = in->state_index;
     a.result = out->result;
     a.ret_agents = out->ret_agents;
     a.final_pose = (float4*)out->final_pose;
@@ -786,10 +846,11 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
   {
     const size_t nA = (size_t)n * A;
     Pack pin, pout;
-    const size_t i_pose = pin.add(in->pose, nullptr, sizeof(float) * 4 * nA);
-    const size_t i_alive = pin.add(in->alive, nullptr, sizeof(uint32_t) * (size_t)n);
+    const size_t i_pose = pin.add(in->pose, nullptr, sizeof(float) * 4 * (size_t)ns * A);
+    const size_t i_alive = pin.add(in->alive, nullptr, sizeof(uint32_t) * (size_t)ns);
     const size_t i_hyp = pin.add(in->hyp_id, nullptr, nA);
-    const size_t i_depth = pin.add(in->depth, nullptr, sizeof(uint16_t) * (size_t)n);
+    const size_t i_depth = pin.add(in->depth, nullptr, sizeof(uint16_t) * (size_t)ns);
+    const size_t i_index = pin.add(in->state_index, nullptr, sizeof(uint32_t) * (size_t)n);
     const size_t o_res = pout.add(nullptr, out->result, sizeof(bmcts_rollout_result) * (size_t)n);
     const size_t o_ra = pout.add(nullptr, out->ret_agents, sizeof(float) * nA);
     const size_t o_fp = pout.add(nullptr, out->final_pose, sizeof(float) * 4 * nA);
@@ -803,6 +864,7 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
       a.alive = (const uint32_t*)ip(i_alive);
       a.hyp = (const uint8_t*)ip(i_hyp);
       a.depth = (const uint16_t*)ip(i_depth);
+      a.state_index = (const uint32_t*)ip(i_index);
       a.result = (bmcts_rollout_result*)op(o_res);
       a.ret_agents = (float*)op(o_ra);
       a.final_pose = (float4*)op(o_fp);
@@ -812,14 +874,16 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
   }
   const void* d;
   void* o;
-  if ((st = h2d(e, e->b_pose, in->pose, sizeof(float) * 4 * (size_t)n * A, &d))) return st;
+  if ((st = h2d(e, e->b_pose, in->pose, sizeof(float) * 4 * (size_t)ns * A, &d))) return st;
   a.pose = (const float4*)d;
-  if ((st = h2d(e, e->b_alive, in->alive, sizeof(uint32_t) * (size_t)n, &d))) return st;
+  if ((st = h2d(e, e->b_alive, in->alive, sizeof(uint32_t) * (size_t)ns, &d))) return st;
   a.alive = (const uint32_t*)d;
   if ((st = h2d(e, e->b_hyp, in->hyp_id, (size_t)n * A, &d))) return st;
   a.hyp = (const uint8_t*)d;
-  if ((st = h2d(e, e->b_depth, in->depth, sizeof(uint16_t) * (size_t)n, &d))) return st;
+  if ((st = h2d(e, e->b_depth, in->depth, sizeof(uint16_t) * (size_t)ns, &d))) return st;
   a.depth = (const uint16_t*)d;
+  if ((st = h2d(e, e->b_index, in->state_index, sizeof(uint32_t) * (size_t)n, &d))) return st;
+  a.state_index = (const uint32_t*)d;
   if ((st = out_buf(e, e->b_result, out->result, sizeof(bmcts_rollout_result) * (size_t)n, &o)))
     return st;
   a.result = (bmcts_rollout_result*)o;

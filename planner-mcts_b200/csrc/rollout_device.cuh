@@ -60,6 +60,10 @@ struct KernelArgs {
   // set when a wait times out.  Null for every other call.
   unsigned int* ready;
   unsigned int chunk;
+  // unique-state form of a leaf batch (bmcts_leaf_batch.state_index): pose / alive / depth are
+  // tables of ns states and rollout k starts from state state_index[k]; null: ns == n, state k
+  const uint32_t* state_index;
+  int ns;
 };
 
 __host__ __device__ inline size_t smem_align16(size_t x) { return (x + 15) & ~size_t(15); }

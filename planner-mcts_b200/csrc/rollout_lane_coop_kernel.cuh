@@ -104,8 +104,10 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
         done = true;
       } else {
         rid = next;
-        am = p.alive[rid];
-        depth = p.depth ? (int)p.depth[rid] : 1;
+        // row of the start state in the pose table (re-read where needed: not kept in a register)
+        const uint32_t sid = p.state_index ? p.state_index[rid] : rid;
+        am = p.alive[sid];
+        depth = p.depth ? (int)p.depth[sid] : 1;
         // BMCTS_ACTION_NONE: no expansion step, the rollout starts from the given state
         expand = p.do_expand != 0 && p.action[rid] != BMCTS_ACTION_NONE;
         active = expand || p.do_rollout != 0;
@@ -140,7 +142,7 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
         const bool was_alive = (pre >> a) & 1u;
         float x, y, th, v, cs, sn, la = 0.0f;
         if (fresh) {
-          const float4 q = p.pose[gi];
+          const float4 q = p.pose[(size_t)a * p.ns + (p.state_index ? p.state_index[rid] : rid)];
           x = q.x;
           y = q.y;
           th = q.z;
@@ -153,7 +155,7 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
         } else {
           if (!was_alive) {
             if (expand) {
-              if (p.next_pose) p.next_pose[gi] = p.pose[gi];
+              if (p.next_pose) p.next_pose[gi] = p.pose[(size_t)a * p.ns + (p.state_index ? p.state_index[rid] : rid)];
               if (p.last_action) p.last_action[gi] = 0.0f;
             }
             continue;

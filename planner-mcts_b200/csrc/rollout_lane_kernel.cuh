@@ -301,8 +301,10 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         done = true;
       } else {
         rid = next;
-        am = p.alive[rid];
-        depth = p.depth ? (int)p.depth[rid] : 1;
+        // row of the start state in the pose table (re-read where needed: not kept in a register)
+        const uint32_t sid = p.state_index ? p.state_index[rid] : rid;
+        am = p.alive[sid];
+        depth = p.depth ? (int)p.depth[sid] : 1;
         // BMCTS_ACTION_NONE: no expansion step, the rollout starts from the given state
         expand = p.do_expand != 0 && p.action[rid] != BMCTS_ACTION_NONE;
         active = expand || p.do_rollout != 0;
@@ -313,7 +315,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         R = C0 = C1 = L = 0.0f;
         f_any = f_last = 0;
         inc0 = inc1 = inc2 = inc3 = 0;
-        const float4 q0 = p.pose[rid];  // ego pose (agent slot 0)
+        const float4 q0 = p.pose[sid];  // ego pose (agent slot 0)
         ex = q0.x;
         ey = q0.y;
         eth = q0.z;
@@ -480,7 +482,7 @@ BM_UNROLL(BMCTS_EGO_UNROLL)
         int word = 0;
         bool on_safe_arc = false;  // centre-line point with a margin to the road boundary
         if (fresh) {
-          const float4 q = p.pose[gi];
+          const float4 q = p.pose[(size_t)a * p.ns + (p.state_index ? p.state_index[rid] : rid)];
           x = q.x;
           y = q.y;
           th = q.z;
@@ -490,7 +492,7 @@ BM_UNROLL(BMCTS_EGO_UNROLL)
           if (!was_alive) ca[L_CUR * fstride] = __int_as_float(word);
         } else if (!was_alive) {
           if (expand) {
-            if (p.next_pose) p.next_pose[gi] = p.pose[gi];
+            if (p.next_pose) p.next_pose[gi] = p.pose[(size_t)a * p.ns + (p.state_index ? p.state_index[rid] : rid)];
             if (p.reward && a > 0) p.reward[gi] = 0.0f;
             if (p.last_action && a > 0) p.last_action[gi] = 0.0f;
           }

@@ -105,20 +105,25 @@ class RolloutEngine:
 
     # -- rollout (RandomHeuristic::calculate_heuristic_values) --------------
     def rollout(self, pose, alive, hyp_id=None, depth=None, seed=1000, stream=0,
-                first_rollout_id=0, want_agents=False, want_final=False):
-        """Host-buffer rollout batch.  Returns a dict of numpy arrays."""
+                first_rollout_id=0, want_agents=False, want_final=False, state_index=None):
+        """Host-buffer rollout batch.  Returns a dict of numpy arrays.  With state_index[n],
+        pose / alive / depth are tables of distinct states and rollout k starts from row
+        state_index[k] (hyp_id stays per rollout)."""
         A = self.A
         pose = _host(pose, np.float32, name="pose")
-        n = pose.shape[1]
-        pose = _host(pose, np.float32, (A, n, 4), "pose")
-        alive = _host(alive, np.uint32, (n,), "alive")
+        ns = pose.shape[1]
+        n = ns if state_index is None else len(state_index)
+        pose = _host(pose, np.float32, (A, ns, 4), "pose")
+        alive = _host(alive, np.uint32, (ns,), "alive")
         hyp_id = _host(hyp_id if hyp_id is not None else np.zeros((A, n)), np.uint8, (A, n), "hyp_id")
-        depth = _host(depth, np.uint16, (n,), "depth")
+        depth = _host(depth, np.uint16, (ns,), "depth")
+        state_index = _host(state_index, np.uint32, (n,), "state_index")
         res = np.zeros(n, dtype=RESULT_DTYPE)
         ret_agents = np.zeros((A, n), np.float32) if want_agents else None
         final_pose = np.zeros((A, n, 4), np.float32) if want_final else None
         inb = _abi.LeafBatch(n, _abi.MEM_HOST, _ptr(pose), _ptr(alive), _ptr(hyp_id), _ptr(depth),
-                             int(seed), int(stream), 0, int(first_rollout_id))
+                             int(seed), int(stream), 0, int(first_rollout_id),
+                             0 if state_index is None else ns, 0, _ptr(state_index))
         out = _abi.RolloutOut(_ptr(res), _ptr(ret_agents), _ptr(final_pose))
         self._check(self._lib.bmcts_rollout_batch(self._h, C.byref(inb), C.byref(out)))
         d = {"result": res}
@@ -129,14 +134,16 @@ class RolloutEngine:
         return d
 
     def rollout_raw(self, n, memory, pose, alive, hyp_id, depth, result, ret_agents=None,
-                    final_pose=None, seed=1000, stream=0, first_rollout_id=0):
+                    final_pose=None, seed=1000, stream=0, first_rollout_id=0, n_states=0,
+                    state_index=None):
         """Rollout batch over caller-owned buffers (numpy arrays, torch tensors or
         integer addresses); memory = MEM_HOST or MEM_DEVICE.  Asynchronous for
         MEM_DEVICE (call sync())."""
         def p(x):
             return x if (x is None or isinstance(x, int)) else _ptr(x)
         inb = _abi.LeafBatch(int(n), int(memory), p(pose), p(alive), p(hyp_id), p(depth), int(seed),
-                             int(stream), 0, int(first_rollout_id))
+                             int(stream), 0, int(first_rollout_id), int(n_states), 0,
+                             p(state_index))
         out = _abi.RolloutOut(p(result), p(ret_agents), p(final_pose))
         self._check(self._lib.bmcts_rollout_batch(self._h, C.byref(inb), C.byref(out)))
 
@@ -224,3 +231,14 @@ class RolloutEngine:
                                 int(seed), int(stream), 0)
         self._check(self._lib.bmcts_likelihood_batch(self._h, C.byref(inb), _ptr(prob)))
         return prob
+
+    def likelihood_raw(self, n_worlds, memory, pose, alive, action, prob, n_samples=10000,
+                       n_buckets=100, lower=-10.0, upper=10.0, seed=1000, stream=0):
+        """Likelihood batch over caller-owned buffers (numpy arrays, torch tensors or integer
+        addresses); asynchronous for MEM_DEVICE (call sync())."""
+        def p(x):
+            return x if (x is None or isinstance(x, int)) else _ptr(x)
+        inb = _abi.LikelihoodIn(int(n_worlds), int(memory), p(pose), p(alive), p(action),
+                                int(n_samples), int(n_buckets), float(lower), float(upper),
+                                int(seed), int(stream), 0)
+        self._check(self._lib.bmcts_likelihood_batch(self._h, C.byref(inb), p(prob)))

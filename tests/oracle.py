@@ -95,19 +95,22 @@ def philox(ctr, key):
 
 
 def rollout(cfg, scn, pose, alive, hyp_id=None, depth=None, seed=1000, stream=0,
-            first_rollout_id=0, n_threads=1):
+            first_rollout_id=0, n_threads=1, state_index=None):
     lib = load()
     A = scn.n_agents
-    n = np.asarray(pose).shape[1]
-    pose = _h(pose, np.float32, (A, n, 4), "pose")
-    alive = _h(alive, np.uint32, (n,), "alive")
+    ns = np.asarray(pose).shape[1]
+    n = ns if state_index is None else len(state_index)
+    pose = _h(pose, np.float32, (A, ns, 4), "pose")
+    alive = _h(alive, np.uint32, (ns,), "alive")
     hyp_id = _h(hyp_id if hyp_id is not None else np.zeros((A, n)), np.uint8, (A, n), "hyp_id")
-    depth = None if depth is None else _h(depth, np.uint16, (n,), "depth")
+    depth = None if depth is None else _h(depth, np.uint16, (ns,), "depth")
+    state_index = None if state_index is None else _h(state_index, np.uint32, (n,), "state_index")
     res = np.zeros(n, dtype=RESULT_DTYPE)
     ret_agents = np.zeros((A, n), np.float32)
     final_pose = np.zeros((A, n, 4), np.float32)
     inb = _abi.LeafBatch(n, _abi.MEM_HOST, _p(pose), _p(alive), _p(hyp_id), _p(depth), int(seed),
-                         int(stream), 0, int(first_rollout_id))
+                         int(stream), 0, int(first_rollout_id),
+                         0 if state_index is None else ns, 0, _p(state_index))
     out = _abi.RolloutOut(_p(res), _p(ret_agents), _p(final_pose))
     _check(lib.oracle_rollout_batch(C.byref(cfg), C.byref(scn), C.byref(inb), C.byref(out),
                                     int(n_threads)))

@@ -223,3 +223,19 @@ def test_idm_acceleration_kat_through_step():
     o = oracle.step(cfg, scn, pose, alive, np.zeros((2, 1), np.uint8),
                     np.array([[0], [0]], np.uint8), np.array([[5], [5]], np.uint64))
     assert o["last_action"][1, 0] == pytest.approx(-2.25, rel=1e-5)
+
+
+def test_unique_state_form_of_a_leaf_batch_equals_the_expanded_batch():
+    """bmcts_leaf_batch.state_index: a table of distinct states + one
+    index per rollout is the same batch as the states written out per rollout"""
+    from planner_mcts_b200 import scenarios
+    cfg, scn, meta = scenarios.workload("c3_merge_risk", horizon=8)
+    rng = np.random.default_rng(3)
+    pose, alive, _ = scenarios.sample_leaves(scn, 9, meta["lane_of"], meta["s_of"], rng, dead_prob=0.1)
+    depth = rng.integers(1, 4, size=9).astype(np.uint16)
+    index = rng.integers(0, 9, size=150).astype(np.uint32)
+    hyp = rng.integers(0, scn.n_hypotheses, size=(scn.n_agents, 150)).astype(np.uint8)
+    a = oracle.rollout(cfg, scn, pose, alive, hyp, depth=depth, state_index=index, n_threads=3)
+    b = oracle.rollout(cfg, scn, pose[:, index], alive[index], hyp, depth=depth[index])
+    for k in a:
+        assert a[k].tobytes() == b[k].tobytes(), k

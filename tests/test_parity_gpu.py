@@ -75,6 +75,48 @@ def test_host_batch_pipeline_parity(name, monkeypatch):
     assert eng.launch_count() == 7
 
 
+@pytest.mark.parametrize("name", ["c2_merge_sbg", "c4_coop", "c5_rsbg"])
+def test_unique_state_form_parity(name, monkeypatch):
+    """bmcts_leaf_batch.state_index: n rollouts over a table of distinct states (the waves of a
+    search revisit few states under fresh hypothesis samples).  Every host path (packed,
+    chunked, streamed) and the device path give the results of the expanded batch."""
+    cfg, scn, meta = scenarios.workload(name, horizon=12)
+    ns, n = 37, 400
+    rng = np.random.default_rng(5)
+    pose, alive, _ = scenarios.sample_leaves(scn, ns, meta["lane_of"], meta["s_of"], rng,
+                                             dead_prob=0.05)
+    depth = rng.integers(1, 4, size=ns).astype(np.uint16)
+    index = rng.integers(0, ns, size=n).astype(np.uint32)
+    hyp = rng.integers(0, max(1, scn.n_hypotheses), size=(scn.n_agents, n)).astype(np.uint8)
+    kw = dict(seed=8, stream=1, first_rollout_id=77)
+    want = oracle.rollout(cfg, scn, pose[:, index], alive[index], hyp, depth=depth[index],
+                          n_threads=8, **kw)
+    c = oracle.rollout(cfg, scn, pose, alive, hyp, depth=depth, state_index=index, n_threads=8, **kw)
+    parity.assert_results_match(c, want)          # the oracle's own two forms agree
+    eng = RolloutEngine(cfg, scn)
+    for env in ({}, {"BMCTS_PIPE_CHUNK": "64"}, {"BMCTS_STREAM_CHUNK": "32"}):
+        for k in ("BMCTS_PIPE_CHUNK", "BMCTS_STREAM_CHUNK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g = eng.rollout(pose, alive, hyp, depth=depth, state_index=index, want_agents=True,
+                        want_final=True, **kw)
+        parity.assert_results_match(g, want)
+    # device-resident buffers
+    import torch
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_pose, d_alive, d_hyp = t(pose), t(alive.view(np.int32)), t(hyp)
+    d_depth, d_index = t(depth.view(np.int16)), t(index.view(np.int32))
+    d_res = torch.zeros(n, 8, dtype=torch.float32, device=dev)
+    eng.rollout_raw(n, _abi.MEM_DEVICE, d_pose, d_alive, d_hyp, d_depth, d_res, n_states=ns,
+                    state_index=d_index, **kw)
+    eng.sync()
+    from planner_mcts_b200 import RESULT_DTYPE
+    got = d_res.cpu().numpy().view(RESULT_DTYPE).reshape(-1)
+    assert got.tobytes() == want["result"].tobytes()
+
+
 @pytest.mark.parametrize("name", GEOMETRIES)
 def test_rollout_parity(name):
     cfg, scn, meta = scenarios.workload(name, horizon=20)
