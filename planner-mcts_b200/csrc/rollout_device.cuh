@@ -231,7 +231,7 @@ __device__ __forceinline__ bool safe_dist_longitudinal(float v_f, float v_r, flo
   if (dist < 0.0f) return false;
   float t_stop_f = bm_div(-v_f, a_f);
   float v_f_star = (delta <= t_stop_f) ? bm_fma(a_f, delta, v_f) : 0.0f;
-  float t_stop_f_star = bm_div(-v_f_star, a_r);
+  float t_stop_f_star = bm_div(-v_f_star, a_f);  // the front vehicle's own stopping time
   float t_stop_r = bm_div(-v_r, a_r);
   float sd0 = v_r * delta - bm_div(v_r * v_r, 2.0f * a_r);
   float sd1 = sd0 + bm_div(v_f * v_f, 2.0f * a_f);

@@ -33,6 +33,13 @@ inline double Uniform01(std::mt19937& gen) {
   return ((double)hi * 67108864.0 + (double)lo) * (1.0 / 9007199254740992.0);
 }
 
+// uniform index in [0, n) by multiply-shift on one 32-bit draw.  (std::uniform_int_distribution is
+// implementation defined: the same seed would give different searches under another standard
+// library; this mapping is part of the search's definition and tests/tiny_mcts.py mirrors it.)
+inline size_t UniformIndex(std::mt19937& gen, size_t n) {
+  return (size_t)(((uint64_t)gen() * (uint64_t)n) >> 32);
+}
+
 // sqrt(2 ln N) of the UCB exploration term for small N (one table for the process)
 inline double SqrtTwoLog(double n) {
   constexpr int kN = 4096;
@@ -103,8 +110,7 @@ class UctStatistic {
   int ChooseNextAction(std::mt19937& gen) {
     int a;
     if (WideningAllowed()) {
-      std::uniform_int_distribution<size_t> d(0, unexpanded_.size() - 1);
-      size_t i = d(gen);
+      size_t i = UniformIndex(gen, unexpanded_.size());
       a = unexpanded_[i];
       unexpanded_.erase(unexpanded_.begin() + i);
       pairs_[a].expanded = true;
@@ -503,8 +509,7 @@ class CostConstrainedStatistic {
     if (!policy_is_ready() && !unexpanded_.empty()) {
       size_t i;
       if (explore_policy_.empty()) {
-        std::uniform_int_distribution<size_t> d(0, unexpanded_.size() - 1);
-        i = d(gen);
+        i = UniformIndex(gen, unexpanded_.size());
       } else {
         // NeuralCostConstrainedStatistic::choose_next_action: sample_policy(exploration policy),
         // restricted to the actions not tried yet
@@ -519,7 +524,7 @@ class CostConstrainedStatistic {
             break;
           }
         }
-        if (!(tot > 0.0)) i = std::uniform_int_distribution<size_t>(0, unexpanded_.size() - 1)(gen);
+        if (!(tot > 0.0)) i = UniformIndex(gen, unexpanded_.size());
       }
       a = unexpanded_[i];
       unexpanded_.erase(unexpanded_.begin() + i);
@@ -573,7 +578,7 @@ class CostConstrainedStatistic {
     }
     Greedy g;
     if (a_star < 0) {  // nothing visited yet: uniform
-      g.action = std::uniform_int_distribution<int>(0, n - 1)(gen);
+      g.action = (int)UniformIndex(gen, (size_t)n);
       return g;
     }
     g.a_star = g.action = a_star;

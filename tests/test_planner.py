@@ -134,6 +134,28 @@ def test_risk_constraint_planner_accelerates_on_free_road(make):
 
 
 @pytest.mark.parametrize("make", BACKENDS)
+def test_risk_constraint_planner_free_road_as_the_reference_writes_it(make):
+    """behavior_uct_risk_constraint_test.cc:218-276 AS WRITTEN: ego alone at 2 m/s, goal polygon
+    150 m ahead, 500 iterations, 10-step rollouts of 0.2 s, actions {0, 1, -1, -2}, rewards only at
+    the goal and at collisions.  Nothing within 10 x 0.2 s of a 2 m/s car is rewarded or costs
+    anything, so every root action has the same value (0) and the same cost (0): the reference's
+    `GetLastMacroAction() == 1` is decided by which of four equally optimal vertices OR-tools
+    returns for mamcts' greedy-policy LP and by sampling from that policy -- not by the search.
+    What the search itself guarantees is asserted here; this repo breaks the tie towards the lowest
+    action index (observed: 0 = keep velocity, on every seed)."""
+    world = W.observed_world(0, 7.0, 2.0, 0.0, goal_center=(150.0, -1.75), goal_half=3.0)
+    pl = make(P.BehaviorUCTRiskConstraint, risk_params(), W.hypotheses())
+    pl.Plan(0.5, world)
+    assert pl.last_num_iterations == 500
+    assert pl.last_return_values == {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0}
+    assert all(v == {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0} for v in pl.last_cost_values.values())
+    assert pl.last_visit_counts.tolist() == [125.0] * 4      # UCB over equal values: round robin
+    assert pl.last_expected_risk == [0.0, 0.0]
+    assert pl.last_macro_action == 0                          # the documented tie-break
+    assert pl.last_action[0] == 0.0
+
+
+@pytest.mark.parametrize("make", BACKENDS)
 def test_cooperative_planner(make):
     """behavior_uct_cooperative_test.cc:147-188: accelerate on a free road, brake behind a
     slow agent"""
