@@ -543,14 +543,20 @@ class CostConstrainedStatistic {
     if (total_pending_) total_pending_--;
   }
 
-  // greedy_policy(kappa, action_filter_factor): near-optimal action set under the
-  // Lagrangian value, then the stochastic mix that meets the first cost constraint
-  // (closed form of the two-action LP the reference solves with OR-tools).
-  // The result as numbers: the sampled action and the (at most two-point) policy behind it.
+  // greedy_policy(kappa, action_filter_factor) (behavior_uct_risk_constraint.hpp:145-153): the
+  // near-optimal action set under the Lagrangian value, then the stochastic policy over it that
+  // the reference finds with an OR-tools LP (CC-MCP, Lee et al. 2018, eq. 8):
+  //     min_{pi, xi >= 0}  sum_i lambda_i xi_i   s.t.  sum_a pi_a Q_Ci(a) <= c_i + xi_i  for EVERY
+  //     cost constraint i,  sum_a pi_a = 1,  pi >= 0,
+  // ties broken towards the higher Lagrangian value.  A vertex of this LP mixes at most
+  // 1 + (number of tight constraints) actions, so with two constraints the optimum is among: one
+  // action; two actions with one constraint tight; three actions with both tight -- enumerated
+  // exactly, no solver.
   struct Greedy {
     int action = 0;
-    int a_star = -1, a_min = -1;  // policy: p_min on a_min, the rest on a_star; a_star < 0: uniform
-    double p_min = 0.0;
+    int n = 0;  // size of the policy's support; 0: uniform over all actions
+    int a[3] = {-1, -1, -1};
+    double p[3] = {0.0, 0.0, 0.0};
   };
   Greedy GreedyCore(double kappa, double filter, const std::vector<double>& lambdas,
                     std::mt19937& gen) const {
@@ -581,30 +587,100 @@ class CostConstrainedStatistic {
       g.action = (int)UniformIndex(gen, (size_t)n);
       return g;
     }
-    g.a_star = g.action = a_star;
+    auto single = [&](int a) {
+      g.n = 1;
+      g.a[0] = g.action = a;
+      g.p[0] = 1.0;
+    };
+    single(a_star);
     if (reward_.pairs()[a_star].count == 0) return g;
+    const int nc = n_costs_;
+    double lim[2] = {0.0, 0.0}, w[2] = {0.0, 0.0};
+    for (int i = 0; i < nc; ++i) {
+      lim[i] = i < (int)constraints_.size() ? constraints_[i] : 0.0;
+      w[i] = std::max(1e-6, i < (int)lambdas.size() ? lambdas[i] : 0.0);
+    }
+    auto qc = [&](int i, int a) { return costs_[i].pairs()[a].value; };
+    auto violation = [&](const double* c) {
+      double v = 0.0;
+      for (int i = 0; i < nc; ++i) v += w[i] * std::max(0.0, c[i] - lim[i]);
+      return v;
+    };
+    {  // the maximising action meets every constraint: nothing to mix (the common case)
+      const double c[2] = {nc > 0 ? qc(0, a_star) : 0.0, nc > 1 ? qc(1, a_star) : 0.0};
+      if (nc == 0 || violation(c) <= 0.0) return g;
+    }
+    // near-optimal actions (ACTION_FILTER_FACTOR), the maximising one first
     auto conf = [&](int a) { return std::sqrt(std::log(std::max(2.0, cnt[a])) / std::max(1.0, cnt[a])); };
-    const double c0 = constraints_.empty() ? 0.0 : constraints_[0];
-    auto qc = [&](int a) { return n_costs_ == 0 ? 0.0 : costs_[0].pairs()[a].value; };
-    if (n_costs_ == 0 || qc(a_star) <= c0) return g;
-    // cheapest action (first cost channel) among the near-optimal ones
     const double conf_star = conf(a_star);
-    int n_near = 0, a_min = -1;
+    int near[BMCTS_MAX_EGO_ACTIONS], n_near = 0;
+    near[n_near++] = a_star;
     for (int a = 0; a < n; ++a) {
-      if (reward_.pairs()[a].count == 0) continue;
-      if (std::fabs(ucb[a] - ucb[a_star]) <= filter * (conf(a) + conf_star)) {
-        n_near++;
-        if (a_min < 0 || qc(a) < qc(a_min)) a_min = a;
-      }
+      if (a == a_star || reward_.pairs()[a].count == 0) continue;
+      if (std::fabs(ucb[a] - ucb[a_star]) <= filter * (conf(a) + conf_star)) near[n_near++] = a;
     }
     if (n_near < 2) return g;
-    if (a_min == a_star || qc(a_min) >= c0) {
-      g.a_star = g.action = a_min;
-      return g;
+    double best_v = std::numeric_limits<double>::infinity(), best_val = ninf;
+    auto consider = [&](int k, const int* acts, const double* probs) {
+      double c[2] = {0.0, 0.0}, val = 0.0;
+      for (int j = 0; j < k; ++j) {
+        for (int i = 0; i < nc; ++i) c[i] += probs[j] * qc(i, acts[j]);
+        val += probs[j] * ucb[acts[j]];
+      }
+      const double v = violation(c);
+      if (v < best_v - 1e-12 || (v <= best_v + 1e-12 && val > best_val + 1e-12)) {
+        best_v = v;
+        best_val = val;
+        g.n = k;
+        for (int j = 0; j < 3; ++j) {
+          g.a[j] = j < k ? acts[j] : -1;
+          g.p[j] = j < k ? probs[j] : 0.0;
+        }
+      }
+    };
+    for (int x = 0; x < n_near; ++x) {
+      const double one = 1.0;
+      consider(1, &near[x], &one);
     }
-    g.a_min = a_min;
-    g.p_min = (qc(a_star) - c0) / (qc(a_star) - qc(a_min));
-    g.action = Uniform01(gen) < g.p_min ? a_min : a_star;
+    for (int x = 0; x < n_near; ++x)
+      for (int y = x + 1; y < n_near; ++y)
+        for (int i = 0; i < nc; ++i) {  // two actions, constraint i tight
+          const double cx = qc(i, near[x]), cy = qc(i, near[y]);
+          if (cx == cy) continue;
+          const double px = (lim[i] - cy) / (cx - cy);
+          if (!(px > 0.0 && px < 1.0)) continue;
+          const int acts[2] = {near[x], near[y]};
+          const double probs[2] = {px, 1.0 - px};
+          consider(2, acts, probs);
+        }
+    if (nc > 1)
+      for (int x = 0; x < n_near; ++x)
+        for (int y = x + 1; y < n_near; ++y)
+          for (int z = y + 1; z < n_near; ++z) {  // three actions, both constraints tight
+            const double a00 = qc(0, near[x]) - qc(0, near[z]), a01 = qc(0, near[y]) - qc(0, near[z]);
+            const double a10 = qc(1, near[x]) - qc(1, near[z]), a11 = qc(1, near[y]) - qc(1, near[z]);
+            const double det = a00 * a11 - a01 * a10;
+            if (std::fabs(det) < 1e-300) continue;
+            const double b0 = lim[0] - qc(0, near[z]), b1 = lim[1] - qc(1, near[z]);
+            const double px = (b0 * a11 - a01 * b1) / det, py = (a00 * b1 - b0 * a10) / det;
+            const double pz = 1.0 - px - py;
+            if (!(px > 0.0 && py > 0.0 && pz > 0.0)) continue;
+            const int acts[3] = {near[x], near[y], near[z]};
+            const double probs[3] = {px, py, pz};
+            consider(3, acts, probs);
+          }
+    g.action = g.a[0];
+    if (g.n > 1) {  // sample_policy
+      double u = Uniform01(gen);
+      g.action = g.a[g.n - 1];
+      for (int j = 0; j < g.n; ++j) {
+        u -= g.p[j];
+        if (u < 0.0) {
+          g.action = g.a[j];
+          break;
+        }
+      }
+    }
     return g;
   }
   int GreedyAction(double kappa, double filter, const std::vector<double>& lambdas,
@@ -615,13 +691,10 @@ class CostConstrainedStatistic {
                                       const std::vector<double>& lambdas, std::mt19937& gen) const {
     const Greedy g = GreedyCore(kappa, filter, lambdas, gen);
     Policy pol;
-    if (g.a_star < 0) {
+    if (g.n == 0) {
       for (int a = 0; a < num_actions(); ++a) pol[(unsigned)a] = 1.0 / num_actions();
-    } else if (g.a_min < 0) {
-      pol[(unsigned)g.a_star] = 1.0;
     } else {
-      pol[(unsigned)g.a_min] = g.p_min;
-      pol[(unsigned)g.a_star] = 1.0 - g.p_min;
+      for (int j = 0; j < g.n; ++j) pol[(unsigned)g.a[j]] = g.p[j];
     }
     return {g.action, pol};
   }

@@ -18,6 +18,16 @@ def test_cpp_planner_api():
     assert res.stdout.strip().endswith("ok")
 
 
+def test_cpp_statistics():
+    """tests/cpp/test_statistics.cpp: the two-constraint greedy policy (exact LP vertices) and the
+    progressive widening of the UCT statistic"""
+    oracle.build()
+    exe = os.path.join(oracle.ORACLE_DIR, "_build", "test_statistics")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.strip().endswith("ok")
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not has_gpu(), reason="needs a CUDA device")
 def test_example_scripts_run():
