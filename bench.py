@@ -497,29 +497,44 @@ def run_ours(args):
     # ---- Plan() arm: one BehaviorUCT*::Plan() of --plan-iterations MCTS iterations in total,
     # root-parallel over the ranks (tree indices are disjoint), root statistics merged with one
     # NCCL all-reduce (BASELINE.json configs[4]: 10^6 rollouts per Plan())
-    plan = None
+    plan, plan_all = None, None
     if not args.no_plan:
-        threads = max(1, min(16, (os.cpu_count() or 1) // world))
-        trees = args.plan_trees if args.plan_trees > 0 else 2 * threads
-        per_tree = max(1, args.plan_iterations // (world * trees))
-        g = plan_benchmark(args.workload, args.horizon, per_tree, args.plan_wave, "gpu",
-                           device=local_rank, tree_index=rank, trees=trees, threads=threads)
         from planner_mcts_b200 import root_parallel
-        ms = torch.tensor([g["plan_ms"]], dtype=torch.float64, device=dev)
-        torch.cuda.synchronize()
-        t_merge = time.perf_counter()
-        st = root_parallel.merge_root_stats(g.pop("root_stats"), device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        torch.cuda.synchronize()
-        merge_ms = (time.perf_counter() - t_merge) * 1e3
-        n_act = (len(st) - 2) // 4
-        cnt, ret = st[:n_act], st[n_act:2 * n_act]
-        mean = np.where(cnt > 0, ret / np.maximum(cnt, 1), -np.inf)
-        plan = dict(g, iterations=int(st[-2]), plan_ms=float(ms[0]), merge_ms=merge_ms,
-                    iterations_per_s=float(st[-2]) / (float(ms[0]) * 1e-3),
-                    merged_best_action=int(np.argmax(mean)), trees=world * trees,
-                    workload=args.workload, host_cores=os.cpu_count())
+        cores = os.cpu_count() or 1
+        comm = root_parallel.RootComm(local_rank)   # ncclAllReduce behind the C ABI
+
+        def plan_arm(threads):
+            trees = args.plan_trees if args.plan_trees > 0 else 2 * threads
+            per_tree = max(1, args.plan_iterations // (world * trees))
+            g = plan_benchmark(args.workload, args.horizon, per_tree, args.plan_wave, "gpu",
+                               device=local_rank, tree_index=rank, trees=trees, threads=threads)
+            ms = torch.tensor([g["plan_ms"]], dtype=torch.float64, device=dev)
+            torch.cuda.synchronize()
+            t_merge = time.perf_counter()
+            st = comm.allreduce(g.pop("root_stats"))
+            merge_ms = (time.perf_counter() - t_merge) * 1e3
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            n_act = (len(st) - 2) // 4
+            cnt, ret = st[:n_act], st[n_act:2 * n_act]
+            mean = np.where(cnt > 0, ret / np.maximum(cnt, 1), -np.inf)
+            return dict(g, iterations=int(st[-2]), plan_ms=float(ms[0]), merge_ms=merge_ms,
+                        iterations_per_s=float(st[-2]) / (float(ms[0]) * 1e-3),
+                        merged_best_action=int(np.argmax(mean)), trees=world * trees,
+                        workload=args.workload, host_cores=cores, host_threads_per_rank=threads,
+                        merge="bmcts_allreduce_root (ncclAllReduce behind the C ABI)")
+
+        # The scaling series: every rank searches with ITS SHARE of the host -- cores / 8 threads,
+        # the share of one GPU on an 8-GPU box -- whatever N is, so that N ranks add N shares and
+        # the series shows whether the path itself scales.  (Plan() is bound by the host tree
+        # search: with cores / N threads per rank the N = 1 run would already use every core and
+        # more GPUs could add nothing.)
+        share = max(1, cores // 8)
+        plan = plan_arm(share)
+        plan["threads_note"] = "host threads per rank = cores / 8 at every N (per-GPU share of the host)"
+        if world == 1:
+            plan_all = plan_arm(max(1, min(16, cores)))   # one rank with (up to 16 of) all cores
+        comm.close()
 
     # ---- reduce over ranks: time = max, work = sum
     t = torch.tensor([m["elapsed_ms"], m["e2e_s"] * 1e3], dtype=torch.float64, device=dev)
@@ -575,6 +590,8 @@ def run_ours(args):
         line["likelihood"] = lik
     if plan is not None:
         line["plan"] = plan
+    if plan_all is not None:
+        line["plan_all_host_threads"] = plan_all
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cfg, scn, meta)
         if plan is not None:

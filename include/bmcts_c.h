@@ -390,6 +390,24 @@ int bmcts_expand_rollout_batch_end(bmcts_engine* e);
  * prob[(a*H + h)*n_worlds + w] */
 int bmcts_likelihood_batch(bmcts_engine* e, const bmcts_likelihood_in* in, float* prob);
 
+/* ---- multi-GPU: the one collective of the path -------------------------- */
+/* Root-parallel search (Mcts::NumParallelMcts): every rank searches its own
+ * trees under its own Philox stream and the root statistics are summed at the end of a Plan().
+ * These calls replace mamcts merge_node_statistics across processes
+ * (mcts_statistics/mcts_neural_cost_constrained_statistic.hpp:157-163,219-222) with one
+ * ncclAllReduce(sum, float64) over NVLink; NCCL is loaded at run time (libnccl.so.2). */
+#define BMCTS_COMM_ID_BYTES 128
+typedef struct bmcts_comm bmcts_comm; /* opaque, one per rank */
+/* rank 0 makes the id (ncclGetUniqueId) and hands it to the other ranks by its own means */
+int bmcts_comm_unique_id(void* id /* [BMCTS_COMM_ID_BYTES] */);
+/* collective over all ranks (ncclCommInitRank): one rank per GPU */
+int bmcts_comm_create(int device, int nranks, int rank, const void* id, bmcts_comm** out);
+void bmcts_comm_destroy(bmcts_comm* c);
+int bmcts_comm_nranks(const bmcts_comm* c);
+/* in-place sum over the ranks of n host doubles (SURVEY.md Appendix E bmcts_allreduce_root) */
+int bmcts_allreduce_root(bmcts_comm* c, double* stats, size_t n);
+const char* bmcts_comm_last_error(const bmcts_comm* c);
+
 /* ---- self test ---------------------------------------------------------- */
 /* Evaluates one elementary function of include/bmcts_math.h on the device for n host inputs:
  * out[i] = f(a[i], b[i]).  The flags of the path are threshold tests on FP32 geometry, so the

@@ -106,6 +106,10 @@ int bmcts_planner_root_stats(bmcts_planner* p, double* stats, int max_n);
 /* re-decide the action from merged statistics (after the NCCL all-reduce) */
 int bmcts_planner_decide_from_root_stats(bmcts_planner* p, const double* stats, int n,
                                          bmcts_plan_result* out);
+/* the two calls above with the all-reduce in between: sums the root statistics of the last search
+ * over the ranks of `comm` (bmcts_allreduce_root) and re-decides from the merged statistics, so
+ * that every rank of a root-parallel Plan() returns the same action */
+int bmcts_planner_allreduce_root_stats(bmcts_planner* p, bmcts_comm* comm, bmcts_plan_result* out);
 /* model of the neural warm start (kind BMCTS_PLANNER_NHEURISTIC_RISK_CONSTRAINT); must be set
  * before the first bmcts_planner_plan.  `user` is passed back to every call. */
 int bmcts_planner_set_node_prior(bmcts_planner* p, bmcts_node_prior_fn fn, void* user);

@@ -159,7 +159,10 @@ EXPORTED_SYMBOLS = [
     "bmcts_expand_rollout_batch_begin", "bmcts_expand_rollout_batch_end",
     "bmcts_likelihood_batch", "bmcts_sync", "bmcts_last_kernel_ms", "bmcts_launch_count",
     "bmcts_stream", "bmcts_last_error", "bmcts_status_string", "bmcts_math_probe",
+    "bmcts_comm_unique_id", "bmcts_comm_create", "bmcts_comm_destroy", "bmcts_comm_nranks",
+    "bmcts_allreduce_root", "bmcts_comm_last_error",
 ]
+COMM_ID_BYTES = 128
 MATH_OPS = ["sin", "cos", "atan2", "tan_small", "div", "sqrt", "min", "max", "norm_angle", "fma_aab",
             "pow4"]
 
@@ -220,6 +223,14 @@ def load_library(path=None):
     lib.bmcts_last_error.restype = C.c_char_p
     lib.bmcts_status_string.argtypes = [C.c_int]
     lib.bmcts_status_string.restype = C.c_char_p
+    lib.bmcts_comm_unique_id.argtypes = [C.c_void_p]
+    lib.bmcts_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, P(C.c_void_p)]
+    lib.bmcts_comm_destroy.argtypes = [C.c_void_p]
+    lib.bmcts_comm_destroy.restype = None
+    lib.bmcts_comm_nranks.argtypes = [C.c_void_p]
+    lib.bmcts_allreduce_root.argtypes = [C.c_void_p, P(C.c_double), C.c_size_t]
+    lib.bmcts_comm_last_error.argtypes = [C.c_void_p]
+    lib.bmcts_comm_last_error.restype = C.c_char_p
     if path == LIB_PATH:
         _lib = lib
     return lib

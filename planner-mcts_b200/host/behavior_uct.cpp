@@ -71,7 +71,10 @@ int CurrentCorridor(const bmcts_scenario& scn, float x, float y) {
 
 BehaviorUCTBase::BehaviorUCTBase(const ParamsPtr& params, int state_kind, int device)
     : BehaviorUCTBase(params, state_kind, std::shared_ptr<LeafEvaluator>(MakeDefaultEvaluator(device))) {
-  evaluator_factory_ = [device]() { return std::shared_ptr<LeafEvaluator>(MakeDefaultEvaluator(device)); };
+  const std::vector<int> devices = EngineDevices(device);
+  evaluator_factory_ = [devices](int i) {
+    return std::shared_ptr<LeafEvaluator>(MakeDefaultEvaluator(devices[(size_t)i % devices.size()]));
+  };
 }
 
 BehaviorUCTBase::BehaviorUCTBase(const ParamsPtr& params, int state_kind,
@@ -216,6 +219,13 @@ Trajectory BehaviorUCTBase::MacroActionTrajectory(const SearchWorld& sw, unsigne
 void BehaviorUCTBase::FinishPlan(const SearchWorld& sw, const ObservedWorld& observed_world,
                                  unsigned best_action, double min_planning_time) {
   last_motion_idx_ = best_action;
+  if (&sw != &last_sw_) {
+    last_sw_ = sw;
+    last_plan_world_.ego_id = observed_world.ego_id;
+    last_plan_world_.world_time = observed_world.world_time;
+    last_plan_time_ = min_planning_time;
+    has_last_plan_ = true;
+  }
   const unsigned applied = constant_action_idx_ >= 0 ? (unsigned)constant_action_idx_ : best_action;
   last_trajectory_ = MacroActionTrajectory(sw, applied, min_planning_time, observed_world.world_time,
                                            &last_action_);
@@ -271,7 +281,8 @@ RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees, const Sta
   const bool own_engines = evaluator_factory_ && (n_threads > 1 || lanes > 1);
   if (own_engines) {
     // engines are kept between Plan() calls
-    while ((long)tree_evaluators_.size() < n_threads * lanes) tree_evaluators_.push_back(evaluator_factory_());
+    while ((long)tree_evaluators_.size() < n_threads * lanes)
+      tree_evaluators_.push_back(evaluator_factory_((int)tree_evaluators_.size()));
     for (long i = 0; i < n_threads * lanes; ++i) {
       int st = tree_evaluators_[i]->Configure(engine_config_, sw.scenario);
       if (st != BMCTS_OK)

@@ -82,6 +82,11 @@ class BehaviorUCTBase : public UctBaseDebugInfos {
   RootStats GetLastRootStats() const { return last_root_stats_; }
   // re-decide from externally merged statistics (NCCL all-reduce over ranks)
   virtual void DecideFromRootStats(const RootStats& merged);
+  // after DecideFromRootStats on merged statistics: the trajectory / action of the (possibly
+  // different) chosen macro action, from the world of the last Plan()
+  void RefreshTrajectory() {
+    if (has_last_plan_) FinishPlan(last_sw_, last_plan_world_, last_motion_idx_, last_plan_time_);
+  }
   uint64_t EngineLaunchCount() const {
     uint64_t n = evaluator_ ? evaluator_->LaunchCount() : 0;
     for (const auto& ev : tree_evaluators_) n += ev->LaunchCount();
@@ -92,7 +97,21 @@ class BehaviorUCTBase : public UctBaseDebugInfos {
   // how further rollout engines are made for Mcts::UseMultiThreading (one engine, i.e. one
   // CUDA stream, per tree thread); without a factory the trees run one after the other
   void set_evaluator_factory(std::function<std::shared_ptr<LeafEvaluator>()> f) {
+    evaluator_factory_ = [f](int) { return f(); };
+  }
+  // ... with the index of the engine (engines are numbered thread by thread): the product factory
+  // spreads them over the GPUs of Mcts::Engine::Devices, so that ONE Plan() in ONE process uses
+  // several GPUs; the root statistics of all trees are merged in this process, no collective
+  void set_indexed_evaluator_factory(std::function<std::shared_ptr<LeafEvaluator>(int)> f) {
     evaluator_factory_ = std::move(f);
+  }
+  // Mcts::Engine::Devices (this engine's key): CUDA device ordinals of the rollout engines of a
+  // root-parallel search; empty = the device the planner was constructed with
+  std::vector<int> EngineDevices(int default_device) const {
+    std::vector<int> d;
+    for (double x : params_->GetListFloat("BehaviorUctBase::Mcts::Engine::Devices", {})) d.push_back((int)x);
+    if (d.empty()) d.push_back(default_device);
+    return d;
   }
 
  protected:
@@ -131,8 +150,12 @@ class BehaviorUCTBase : public UctBaseDebugInfos {
 
   ParamsPtr params_;
   int state_kind_;
+  SearchWorld last_sw_;             // inputs of the last FinishPlan (RefreshTrajectory)
+  ObservedWorld last_plan_world_;
+  double last_plan_time_ = 0.0;
+  bool has_last_plan_ = false;
   std::shared_ptr<LeafEvaluator> evaluator_;
-  std::function<std::shared_ptr<LeafEvaluator>()> evaluator_factory_;
+  std::function<std::shared_ptr<LeafEvaluator>(int)> evaluator_factory_;
   std::vector<std::shared_ptr<LeafEvaluator>> tree_evaluators_;  // engines of the tree threads
   MctsParameters mcts_parameters_;
   bmcts_config engine_config_;

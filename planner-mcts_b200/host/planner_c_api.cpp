@@ -69,9 +69,11 @@ void EnsurePlanner(bmcts_planner* p) {
   if (p->evaluator_factory) {
     p->planner->set_evaluator_factory(p->evaluator_factory);
   } else {
-    const int device = p->device;
-    p->planner->set_evaluator_factory(
-        [device]() { return std::shared_ptr<LeafEvaluator>(MakeDefaultEvaluator(device)); });
+    // one engine per tree in flight, spread over the GPUs of Mcts::Engine::Devices
+    const std::vector<int> devices = p->planner->EngineDevices(p->device);
+    p->planner->set_indexed_evaluator_factory([devices](int i) {
+      return std::shared_ptr<LeafEvaluator>(MakeDefaultEvaluator(devices[(size_t)i % devices.size()]));
+    });
   }
 }
 
@@ -271,6 +273,7 @@ int bmcts_planner_decide_from_root_stats(bmcts_planner* p, const double* stats, 
   rs.Unflatten(std::vector<double>(stats, stats + n));
   try {
     p->planner->DecideFromRootStats(rs);
+    p->planner->RefreshTrajectory();  // of the action chosen from the merged statistics
     FillResult(p, out);
   } catch (const std::exception& e) {
     return Fail(p, BMCTS_ERR_CUDA, e.what());

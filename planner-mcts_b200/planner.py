@@ -48,7 +48,7 @@ PLANNER_SYMBOLS = [
     "bmcts_planner_decide_from_root_stats", "bmcts_planner_parameter_sampling_probability",
     "bmcts_planner_last_error", "bmcts_planner_set_node_prior", "bmcts_planner_observation_size",
     "bmcts_planner_observe", "bmcts_planner_node_prior_stats", "bmcts_planner_update_beliefs",
-    "bmcts_planner_reset_beliefs",
+    "bmcts_planner_reset_beliefs", "bmcts_planner_allreduce_root_stats",
 ]
 
 
@@ -76,6 +76,8 @@ def declare_planner_api(lib):
     lib.bmcts_planner_parameter_sampling_probability.restype = C.c_double
     lib.bmcts_planner_last_error.argtypes = [C.c_void_p]
     lib.bmcts_planner_last_error.restype = C.c_char_p
+    if hasattr(lib, "bmcts_planner_allreduce_root_stats"):   # libbmcts.so only (needs a GPU)
+        lib.bmcts_planner_allreduce_root_stats.argtypes = [C.c_void_p, C.c_void_p, P(PlanResult)]
     return lib
 
 
@@ -273,6 +275,16 @@ class _BehaviorUCT:
         res = PlanResult()
         self._check(self._lib.bmcts_planner_decide_from_root_stats(
             self._h, stats.ctypes.data_as(C.POINTER(C.c_double)), len(stats), C.byref(res)))
+        self.last = res
+        return int(res.best_action)
+
+
+    def allreduce_root_stats(self, comm):
+        """sum the root statistics of the last Plan() over the ranks of `comm`
+        (root_parallel.RootComm: one ncclAllReduce behind the C ABI) and decide from the merged
+        statistics; returns the action every rank agrees on"""
+        res = PlanResult()
+        self._check(self._lib.bmcts_planner_allreduce_root_stats(self._h, comm.handle, C.byref(res)))
         self.last = res
         return int(res.best_action)
 
