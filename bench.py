@@ -501,7 +501,8 @@ def run_ours(args):
     if not args.no_plan:
         from planner_mcts_b200 import root_parallel
         cores = os.cpu_count() or 1
-        comm = root_parallel.RootComm(local_rank)   # ncclAllReduce behind the C ABI
+        # ncclAllReduce behind the C ABI (one rank: nothing to merge, and NCCL stays unloaded)
+        comm = root_parallel.RootComm(local_rank) if world > 1 else None
 
         def plan_arm(threads):
             trees = args.plan_trees if args.plan_trees > 0 else 2 * threads
@@ -511,7 +512,9 @@ def run_ours(args):
             ms = torch.tensor([g["plan_ms"]], dtype=torch.float64, device=dev)
             torch.cuda.synchronize()
             t_merge = time.perf_counter()
-            st = comm.allreduce(g.pop("root_stats"))
+            st = np.asarray(g.pop("root_stats"), dtype=np.float64)
+            if comm is not None:
+                st = comm.allreduce(st)
             merge_ms = (time.perf_counter() - t_merge) * 1e3
             if world > 1:
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -534,7 +537,8 @@ def run_ours(args):
         plan["threads_note"] = "host threads per rank = cores / 8 at every N (per-GPU share of the host)"
         if world == 1:
             plan_all = plan_arm(max(1, min(16, cores)))   # one rank with (up to 16 of) all cores
-        comm.close()
+        if comm is not None:
+            comm.close()
 
     # ---- reduce over ranks: time = max, work = sum
     t = torch.tensor([m["elapsed_ms"], m["e2e_s"] * 1e3], dtype=torch.float64, device=dev)

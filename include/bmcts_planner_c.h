@@ -88,6 +88,12 @@ int bmcts_planner_set_scenario_risk(bmcts_planner* p, const double* integral_per
 int bmcts_planner_set_map(bmcts_planner* p, const bmcts_scenario* map);
 /* root-parallel tree index of this planner (rank): distinct Philox streams per rank */
 int bmcts_planner_set_tree_index(bmcts_planner* p, uint32_t tree_index);
+/* The behaviour model agent `agent_id` really follows (BARK Agent::GetBehaviorModel), as a
+ * BehaviorIDMStochastic parameter region; used when
+ * BehaviorUctHypothesis::PredictionSettings::UseTrueBehaviorsAsHypothesis is set
+ * (behavior_uct_hypothesis_base.hpp:80-90: the omniscient planner -- every other agent is predicted
+ * with its own model, no beliefs).  Kept until overwritten. */
+int bmcts_planner_set_true_behavior(bmcts_planner* p, uint32_t agent_id, const bmcts_hypothesis* model);
 /* BehaviorUCT*::Plan(delta_time, observed_world) */
 int bmcts_planner_plan(bmcts_planner* p, double delta_time, double world_time, uint32_t ego_id,
                        const bmcts_agent_state* agents, int n_agents, bmcts_plan_result* out);

@@ -434,6 +434,30 @@ void BehaviorUCTHypothesisBase::UpdateBeliefs(const ObservedWorld& observed_worl
   current_beliefs_ = belief_tracker_.get_beliefs();
 }
 
+void BehaviorUCTHypothesisBase::DefineTrueBehaviorsAsHypothesis(const ObservedWorld& observed_world) {
+  // behavior_uct_hypothesis_base.hpp:80-90; GetOtherAgents() iterates in ascending AgentId
+  std::vector<const Agent*> others;
+  for (const Agent& a : observed_world.agents)
+    if (a.id != observed_world.ego_id) others.push_back(&a);
+  std::sort(others.begin(), others.end(), [](const Agent* l, const Agent* r) { return l->id < r->id; });
+  const BehaviorHypothesisIDM settings =
+      behavior_hypotheses_.empty() ? BehaviorHypothesisIDM() : behavior_hypotheses_[0];
+  behavior_hypotheses_.clear();
+  std::map<AgentId, unsigned> fixed;
+  for (const Agent* a : others) {
+    if (!a->has_behavior_model)
+      throw std::runtime_error("UseTrueBehaviorsAsHypothesis: agent " + std::to_string(a->id) +
+                               " carries no behaviour model");
+    if (behavior_hypotheses_.size() >= BMCTS_MAX_HYPOTHESES)
+      throw std::runtime_error("UseTrueBehaviorsAsHypothesis: more agents than hypothesis slots");
+    fixed[a->id] = (unsigned)behavior_hypotheses_.size();
+    BehaviorHypothesisIDM h = settings;  // histogram settings are irrelevant: no belief update
+    h.region = a->behavior_model;
+    behavior_hypotheses_.push_back(h);
+  }
+  belief_tracker_.update_fixed_hypothesis_set(fixed);
+}
+
 Mcts::HypothesisSampler BehaviorUCTHypothesisBase::MakeSampler(const SearchWorld& sw,
                                                                unsigned tree_index) {
   auto sampler = std::make_shared<HypothesisBeliefTracker::SlotSampler>(
@@ -448,6 +472,7 @@ Trajectory BehaviorUCTHypothesis::Plan(double min_planning_time, const ObservedW
   ObservedWorld mcts_world = FilterAgents(observed_world);
   last_nearest_agents_.clear();
   for (const Agent& a : mcts_world.agents) last_nearest_agents_.push_back(a.id);
+  if (use_true_behaviors_as_hypothesis_) DefineTrueBehaviorsAsHypothesis(observed_world);  // :34-36
   UpdateBeliefs(observed_world);  // all agents, not only the filtered ones (:56)
   SearchWorld sw = BuildSearchWorld(mcts_world, behavior_hypotheses_);
   last_num_actions_ = sw.scenario.n_ego_actions;
@@ -516,6 +541,7 @@ Trajectory BehaviorUCTRiskConstraint::Plan(double min_planning_time, const Obser
   ObservedWorld mcts_world = FilterAgents(observed_world);
   last_nearest_agents_.clear();
   for (const Agent& a : mcts_world.agents) last_nearest_agents_.push_back(a.id);
+  if (use_true_behaviors_as_hypothesis_) DefineTrueBehaviorsAsHypothesis(observed_world);  // :107-109
   UpdateBeliefs(observed_world);
   if (estimate_scenario_risk_ && !initialized_available_risk_ && belief_tracker_.beliefs_initialized()) {
     current_scenario_risk_[0] = CalculateAvailableScenarioRisk();  // :136-142

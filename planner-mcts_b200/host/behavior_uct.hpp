@@ -180,6 +180,9 @@ class BehaviorUCTHypothesisBase : public BehaviorUCTBase, public UctHypothesisDe
   std::vector<BehaviorHypothesisIDM> GetBehaviorHypotheses() const { return behavior_hypotheses_; }
   // behavior_uct_hypothesis_base.hpp:92-114 (all agents, not only the filtered ones)
   void UpdateBeliefs(const ObservedWorld& observed_world);
+  // behavior_uct_hypothesis_base.hpp:80-90: the others' true behaviour models become the
+  // hypothesis set, one per agent, fixed (no belief tracking)
+  void DefineTrueBehaviorsAsHypothesis(const ObservedWorld& observed_world);
   // forget the observation history (BeliefCalculator::Reset)
   void ResetBeliefs() {
     belief_tracker_ = HypothesisBeliefTracker(mcts_parameters_);

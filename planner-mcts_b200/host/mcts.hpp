@@ -589,10 +589,39 @@ class Mcts {
       t_engine_ += ms(t2, clock::now());
     }
     const auto t3 = clock::now();
+    // As in SelectWave, the root level of the wave's back-ups is done agent by agent (the tables
+    // of one agent stay in the cache): first every newly planned action of a root expansion is
+    // resolved, then the iterations are backed up in order with the root's other-agent updates
+    // deferred, then those are applied per agent in iteration order.  Each statistic sees the
+    // calls of the sequential order; nothing is selected in between.
+    const bool by_agent = w > 1 && other_mode_ == OtherMode::kHypothesis && root_->stats_ready;
+    if (by_agent) {
+      for (int s = 1; s < A_; ++s)
+        for (int i = 0; i < w; ++i) {
+          Selection& sel = sels[i];
+          if (!sel.needs_engine || sel.rollout_only || sel.path.size() != 1) continue;
+          PathStep& st = sel.path[0];
+          if (st.other_idx[s] < 0 || !st.other_new[s]) continue;
+          const ActionKey key = KeyOfAcceleration(wave_.last_action[wave_.at(s, slot[i])]);
+          st.other_idx[s] = root_->other_hyp[s].Resolve(sel.hyp[s], st.other_idx[s], key);
+          st.other_new[s] = 0;
+        }
+      defer_cost_.assign(w, 0.0);
+      defer_latest_.assign(w, 0.0);
+    }
     for (int i = 0; i < w; ++i) {
-      Backup(sels[i], slot[i]);
+      Backup(sels[i], slot[i], by_agent ? i : -1);
       iterations_++;
       if (ego_mode_ == EgoMode::kCostConstrained) UpdateLambdas();
+    }
+    if (by_agent) {
+      for (int s = 1; s < A_; ++s)
+        for (int i = 0; i < w; ++i) {
+          const Selection& sel = sels[i];
+          if (sel.path.empty() || sel.path[0].other_idx[s] < 0) continue;
+          root_->other_hyp[s].BackupEntry(sel.hyp[s], sel.path[0].other_idx[s], defer_cost_[i],
+                                          defer_latest_[i]);
+        }
     }
     t_backup_ += ms(t3, clock::now());
     EvaluatePriors();
@@ -636,7 +665,9 @@ class Mcts {
     }
   }
 
-  void Backup(Selection& sel, int k) {
+  // defer >= 0: the other agents' updates at the ROOT are left to the caller (EndWave applies them
+  // agent by agent); what they need is stored under this index
+  void Backup(Selection& sel, int k, int defer = -1) {
     Node* leaf = sel.reached;
     if (sel.rollout_only) {
       // RandomHeuristic on the depth-capped node itself (node->update_statistics(heuristic))
@@ -731,9 +762,14 @@ class Mcts {
         n->ego_cc->UpdateStatistic(st.ego_action, child->edge_reward_ego, child->edge_cost,
                                    child->LatestReturn(), child_cost);
       }
+      if (defer >= 0 && i == 0) {  // the root step (path[0].node is the root)
+        defer_cost_[defer] = child->edge_cost[0];
+        defer_latest_[defer] = child->latest_cost_other;
+      }
       for (int s = 1; s < A_; ++s) {
         if (st.other_idx[s] < 0) continue;
         if (other_mode_ == OtherMode::kHypothesis) {
+          if (defer >= 0 && i == 0) break;
           const int h = sel.hyp[s];
           n->other_hyp[s].BackupEntry(h, st.other_idx[s], child->edge_cost[0],
                                       child->latest_cost_other);
@@ -803,6 +839,7 @@ class Mcts {
   WaveBuffers wave_;
   std::vector<Selection> sels_;
   std::vector<int> slot_;
+  std::vector<double> defer_cost_, defer_latest_;  // root-level back-ups deferred within a wave
   HypothesisSampler sampler_;
   std::chrono::steady_clock::time_point t_start_;
   long wave_size_ = 1;

@@ -144,6 +144,11 @@ ObservedWorld WorldOf(const bmcts_planner* p, double world_time, uint32_t ego_id
     a.width = agents[i].width;
     a.rear = agents[i].rear;
     a.last_action.acc = agents[i].last_acc;
+    auto tb = p->true_behaviors.find(agents[i].id);
+    if (tb != p->true_behaviors.end()) {
+      a.has_behavior_model = true;
+      a.behavior_model = tb->second;
+    }
     w.agents.push_back(a);
   }
   return w;
@@ -242,6 +247,12 @@ int bmcts_planner_plan(bmcts_planner* p, double delta_time, double world_time, u
   } catch (const std::exception& e) {
     return Fail(p, BMCTS_ERR_CUDA, e.what());
   }
+  return BMCTS_OK;
+}
+
+int bmcts_planner_set_true_behavior(bmcts_planner* p, uint32_t agent_id, const bmcts_hypothesis* model) {
+  if (!p || !model) return BMCTS_ERR_INVALID_ARG;
+  p->true_behaviors[agent_id] = *model;
   return BMCTS_OK;
 }
 

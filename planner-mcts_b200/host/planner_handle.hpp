@@ -2,6 +2,7 @@
 #pragma once
 
 #include <functional>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -15,6 +16,7 @@ struct bmcts_planner {
   unsigned tree_index = 0;
   std::shared_ptr<bark_mcts_b200::Params> params = std::make_shared<bark_mcts_b200::Params>();
   std::vector<bark_mcts_b200::BehaviorHypothesisIDM> hypotheses;
+  std::map<uint32_t, bmcts_hypothesis> true_behaviors;  // agent id -> its own behaviour model
   std::vector<double> risk_integrals;  // scenario-risk integral per hypothesis (may be empty)
   std::shared_ptr<bark_mcts_b200::MapGeometry> map;
   // how the leaf evaluator is made; the product default is the CUDA engine

@@ -452,7 +452,15 @@ class HypothesisStatistic {
   static void SetN(Hot& t, uint32_t n) {
     t.n = n;
     // a live entry nobody has tried or is trying comes first, as in UCB1
-    t.inv_sqrt_n = n ? 1.0f / std::sqrt((float)n) : 1.0e30f;
+    // (1 / sqrt(n) from a table for the counts that occur: a division and a square root per
+    // selection otherwise)
+    constexpr uint32_t kN = 2048;
+    static const std::vector<float> table = [] {
+      std::vector<float> t(kN, 1.0e30f);
+      for (uint32_t i = 1; i < kN; ++i) t[i] = 1.0f / std::sqrt((float)i);
+      return t;
+    }();
+    t.inv_sqrt_n = n < kN ? table[n] : 1.0f / std::sqrt((float)n);
   }
 
   std::vector<Table> tables_;
@@ -564,7 +572,7 @@ class CostConstrainedStatistic {
     const double n_total = std::max(2.0, (double)(reward_.total_visits() + total_pending_));
     const double ninf = -std::numeric_limits<double>::infinity();
     double ucb[BMCTS_MAX_EGO_ACTIONS], cnt[BMCTS_MAX_EGO_ACTIONS];
-    const double log_total = std::log(n_total);
+    const double log_total = kappa > 0 ? std::log(n_total) : 0.0;  // kappa = 0: pure greedy
     int a_star = -1;
     for (int a = 0; a < n; ++a) {
       ucb[a] = ninf;
@@ -579,7 +587,7 @@ class CostConstrainedStatistic {
       double v = reward_.Normalized(a);
       for (int i = 0; i < num_costs(); ++i)
         v -= (i < (int)lambdas.size() ? lambdas[i] : 0.0) * costs_[i].Normalized(a);
-      ucb[a] = v + kappa * std::sqrt(log_total / std::max(1.0, cnt[a]));
+      ucb[a] = kappa > 0 ? v + kappa * std::sqrt(log_total / std::max(1.0, cnt[a])) : v;
       if (a_star < 0 || ucb[a] > ucb[a_star]) a_star = a;
     }
     Greedy g;
@@ -885,10 +893,12 @@ class HypothesisBeliefTracker {
           (*hyp)[s] = (uint8_t)sl.fixed;
           continue;
         }
-        // alias method: one uniform draw picks a column and a side of it
-        const double u = Uniform01(gen_) * (double)sl.prob.size();
-        const size_t col = std::min((size_t)u, sl.prob.size() - 1);
-        (*hyp)[s] = (u - (double)col) < sl.prob[col] ? (uint8_t)col : sl.alias[col];
+        // alias method: ONE 32-bit draw picks a column (multiply-shift) and, with the low half
+        // of the product as the fraction, a side of it
+        const uint64_t m = (uint64_t)gen_() * (uint64_t)sl.prob.size();
+        const size_t col = (size_t)(m >> 32);
+        const double frac = (double)(uint32_t)m * (1.0 / 4294967296.0);
+        (*hyp)[s] = frac < sl.prob[col] ? (uint8_t)col : sl.alias[col];
       }
     }
 

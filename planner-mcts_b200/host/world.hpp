@@ -39,6 +39,12 @@ struct Agent {
   State state;
   float length = 4.0f, width = 2.0f, rear = 1.25f;  // CarRectangle
   Action last_action;  // GetStateInputHistory().back().second
+  // the agent's own behaviour model (BARK Agent::GetBehaviorModel) as a BehaviorIDMStochastic
+  // parameter region, if the simulation knows it: what the omniscient planners use as this agent's
+  // one hypothesis (BehaviorUctHypothesis::PredictionSettings::UseTrueBehaviorsAsHypothesis,
+  // behavior_uct_hypothesis_base.hpp:80-90)
+  bool has_behavior_model = false;
+  bmcts_hypothesis behavior_model{};
 };
 
 // Map reduced to the path's inputs: only corridors, road polygon and goal of this

@@ -49,6 +49,7 @@ PLANNER_SYMBOLS = [
     "bmcts_planner_last_error", "bmcts_planner_set_node_prior", "bmcts_planner_observation_size",
     "bmcts_planner_observe", "bmcts_planner_node_prior_stats", "bmcts_planner_update_beliefs",
     "bmcts_planner_reset_beliefs", "bmcts_planner_allreduce_root_stats",
+    "bmcts_planner_set_true_behavior",
 ]
 
 
@@ -76,6 +77,7 @@ def declare_planner_api(lib):
     lib.bmcts_planner_parameter_sampling_probability.restype = C.c_double
     lib.bmcts_planner_last_error.argtypes = [C.c_void_p]
     lib.bmcts_planner_last_error.restype = C.c_char_p
+    lib.bmcts_planner_set_true_behavior.argtypes = [C.c_void_p, C.c_uint32, P(_abi.Hypothesis)]
     if hasattr(lib, "bmcts_planner_allreduce_root_stats"):   # libbmcts.so only (needs a GPU)
         lib.bmcts_planner_allreduce_root_stats.argtypes = [C.c_void_p, C.c_void_p, P(PlanResult)]
     return lib
@@ -92,6 +94,9 @@ class Agent:
     width: float = 2.0
     rear: float = 1.25
     last_acc: float = 0.0
+    # the agent's own behaviour model (a HypothesisIDM / _abi.Hypothesis region), if known: the
+    # omniscient planners (UseTrueBehaviorsAsHypothesis) predict the agent with it
+    behavior_model: object = None
 
 
 @dataclass
@@ -205,6 +210,9 @@ class _BehaviorUCT:
         arr = (AgentState * n)()
         for i, a in enumerate(observed_world.agents):
             arr[i] = AgentState(a.id, a.x, a.y, a.theta, a.v, a.length, a.width, a.rear, a.last_acc)
+            if a.behavior_model is not None:
+                region = getattr(a.behavior_model, "region", a.behavior_model)
+                self._check(self._lib.bmcts_planner_set_true_behavior(self._h, int(a.id), C.byref(region)))
         res = PlanResult()
         self._check(self._lib.bmcts_planner_plan(self._h, float(delta_time),
                                                  float(observed_world.world_time),

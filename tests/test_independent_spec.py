@@ -251,7 +251,7 @@ def test_longitudinal_safe_distance_against_brute_force_simulation():
 # ------------------------------------------------------------------ host search vs a tiny sequential MCTS
 def _alias_sampler(beliefs, seed):
     """root-belief sampling per agent slot: Vose alias tables over the beliefs, one uniform double
-    per slot and iteration (HypothesisBeliefTracker::SlotSampler, DESIGN.md section 6)"""
+    draw per slot and iteration (HypothesisBeliefTracker::SlotSampler, DESIGN.md section 6)"""
     import tiny_mcts
     gen = tiny_mcts.Mt19937(seed)
     tables = []
@@ -274,9 +274,9 @@ def _alias_sampler(beliefs, seed):
     def sample():
         hyp = [0]
         for prob, alias in tables:
-            u = gen.uniform01() * len(prob)
-            col = min(int(u), len(prob) - 1)
-            hyp.append(col if (u - col) < prob[col] else alias[col])
+            m = gen.next() * len(prob)        # one 32-bit draw: column and fraction
+            col, frac = m >> 32, (m & 0xFFFFFFFF) / 4294967296.0
+            hyp.append(col if frac < prob[col] else alias[col])
         return hyp
     return sample
 

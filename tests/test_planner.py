@@ -205,6 +205,40 @@ def test_uct_progressive_widening_and_search_limits():
     assert all(v < -1.5 for v in pl.last_return_values.values())
 
 
+@pytest.mark.parametrize("make", BACKENDS)
+def test_omniscient_planner_uses_the_true_behaviors_as_hypotheses(make):
+    """BehaviorUctHypothesis::PredictionSettings::UseTrueBehaviorsAsHypothesis
+    (behavior_uct_hypothesis_base.hpp:80-90): every other agent is predicted with its own model,
+    one fixed hypothesis per agent, no belief tracking.  Two agents that follow the same model R
+    give exactly the search of a one-hypothesis planner over [R]; agents with different models are
+    told apart (a tailgater is predicted differently from a cautious driver)."""
+    import kat_worlds
+    world = W.observed_world(2, 4.0, 6.0, 3.0, goal_center=(150.0, -1.75))
+    R = kat_worlds.make_params_hypothesis(1.0, 3.0)
+    omni = dict(W.base_params(300))
+    omni["BehaviorUctHypothesis::PredictionSettings::UseTrueBehaviorsAsHypothesis"] = 1
+    for a in world.agents[1:]:
+        a.behavior_model = R
+    pl = make(P.BehaviorUCTHypothesis, omni, [])
+    pl.Plan(0.2, world)
+    one = make(P.BehaviorUCTHypothesis, W.base_params(300), [P.HypothesisIDM(R)])
+    one.Plan(0.2, world)
+    assert np.array_equal(pl.root_stats(), one.root_stats())
+    assert pl.last_macro_action == one.last_macro_action
+    assert pl.current_beliefs(2).size == 0            # no beliefs in omniscient mode
+    # different true models -> a different search
+    world.agents[1].behavior_model = kat_worlds.make_params_hypothesis(0.1, 0.1)   # tailgater
+    world.agents[2].behavior_model = kat_worlds.make_params_hypothesis(3.0, 3.0)   # cautious
+    pl2 = make(P.BehaviorUCTHypothesis, omni, [])
+    pl2.Plan(0.2, world)
+    assert not np.array_equal(pl2.root_stats(), one.root_stats())
+    # an agent without a model cannot be predicted omnisciently: an error, not a guess
+    world.agents[2].behavior_model = None
+    pl3 = make(P.BehaviorUCTHypothesis, omni, [])
+    with pytest.raises(Exception, match="behaviour model"):
+        pl3.Plan(0.2, world)
+
+
 def test_root_parallel_merge_of_two_trees():
     """root-parallel search (Mcts::NumParallelMcts; SURVEY.md 8e): two trees with distinct
     tree indices, statistics merged by summation, decision from the merged statistics"""
@@ -327,6 +361,67 @@ def test_wave_batched_search_agrees_with_sequential_search_within_monte_carlo_ci
     # acceleration inputs (0, 1, 4, -1, -8): full braking is chosen whatever the wave size
     for wave in best:
         assert set(best[wave]) == {4}, (wave, best[wave])
+
+
+def _root_estimates(pl, n_actions):
+    """per ego action: return value and (risk planner) the two cost estimates; NaN = not visited"""
+    rv = pl.last_return_values
+    cols = [[rv.get(a, np.nan) for a in range(n_actions)]]
+    if hasattr(pl, "last_cost_values"):
+        cv = pl.last_cost_values
+        for name in ("envelope", "collision"):
+            if name in cv:
+                cols.append([cv[name].get(a, np.nan) for a in range(n_actions)])
+    return np.concatenate(cols)
+
+
+WORLDS_MC = [dict(n_others=1, rel=3.0, v=6.0, dv=3.0), dict(n_others=2, rel=8.0, v=8.0, dv=2.0)]
+
+
+@pytest.mark.parametrize("world_kw", WORLDS_MC, ids=["close_slow_leader", "two_agents_ahead"])
+@pytest.mark.parametrize("kind", ["risk", "cooperative"])
+def test_wave_batched_risk_and_cooperative_searches_within_monte_carlo_ci(kind, world_kw):
+    """north_star bullet 3 for the other two planners: root action values AND risk (cost)
+    estimates of the wave-batched search (default wave) against the sequential search (wave 1) at
+    equal iteration counts, 32 seeds: every estimate's seed-average differs by at most 4 pooled
+    standard errors (+ 0.5 % of the value range for estimates without seed-to-seed variance), and
+    the expected risk of the returned policy agrees the same way."""
+    world = W.observed_world(world_kw["n_others"], world_kw["rel"], world_kw["v"], world_kw["dv"],
+                             goal_center=(150.0, -1.75))
+    seeds, n_actions = range(32), 5
+    est, risk = {}, {}
+    for wave in (1, 0):
+        est[wave], risk[wave] = [], []
+        for seed in seeds:
+            params = W.base_params(768, seed=1000 + seed)
+            params[P0 + "Mcts::Engine::WaveSize"] = wave
+            params[P0 + "Mcts::RandomHeuristic::MaxNumIterations"] = 20
+            if kind == "risk":
+                params.update({P0 + "Mcts::State::SplitSafeDistCollision": 1,
+                               P0 + "Mcts::State::EvaluationParameters::AddSafeDist": 1,
+                               P0 + "Mcts::State::CollisionCost": 1.0, P0 + "Mcts::State::GoalCost": 0.0,
+                               "BehaviorUctRiskConstraint::DefaultAvailableRisk": [0.1, 0.0]})
+                pl = cpu(P.BehaviorUCTRiskConstraint, params, W.hypotheses())
+            else:
+                params[P0 + "Mcts::UctStatistic::ProgressiveWidening::K"] = 4.0
+                pl = cpu(P.BehaviorUCTCooperative, params)
+            pl.Plan(0.2, world)
+            est[wave].append(_root_estimates(pl, n_actions))
+            if kind == "risk":
+                risk[wave].append(pl.last_expected_risk)
+        est[wave] = np.array(est[wave])
+    seq, bat = est[1], est[0]
+    visited = ~(np.isnan(seq).any(0) | np.isnan(bat).any(0))
+    assert visited.sum() >= n_actions          # at least every return value is compared
+    diff = np.abs(seq.mean(0) - bat.mean(0))[visited]
+    sem = np.sqrt(seq.var(0, ddof=1) / len(seeds) + bat.var(0, ddof=1) / len(seeds))[visited]
+    scale = np.maximum(np.abs(seq.mean(0)), np.abs(bat.mean(0)))[visited]
+    assert (diff <= 4.0 * sem + 0.005 * scale + 1e-9).all(), (kind, diff, sem)
+    if kind == "risk":
+        a, b = np.array(risk[1]), np.array(risk[0])
+        d = np.abs(a.mean(0) - b.mean(0))
+        se = np.sqrt(a.var(0, ddof=1) / len(seeds) + b.var(0, ddof=1) / len(seeds))
+        assert (d <= 4.0 * se + 1e-3).all(), (d, se)
 
 
 def test_belief_calculator_tracks_the_planners_beliefs():
