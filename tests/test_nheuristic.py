@@ -132,7 +132,9 @@ def test_value_prior_initialises_the_action_statistics():
     # one virtual visit (the default) is washed out by the search: values move off the prior
     pl = _cpu(BehaviorUCTNHeuristicRiskConstraint, _params(256, wave=8), _Prior(values=values))
     pl.Plan(0.2, _world())
-    assert abs(pl.last_return_values[0] + 500.0) > 50.0
+    # (every action the search actually visits: here all but the first, which the prior rules out)
+    moved = [abs(pl.last_return_values[a] - values["Return"][a]) for a in range(4)]
+    assert sorted(moved)[1] > 20.0 and max(moved) > 400.0
 
 
 def test_root_parallel_trees_share_the_model():
