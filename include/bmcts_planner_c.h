@@ -70,6 +70,16 @@ typedef struct bmcts_plan_result {
   uint64_t engine_launches;                     /* kernels launched so far by this planner */
 } bmcts_plan_result;
 
+/* mamcts MctsEdgeInfo of the last search tree (behavior_uct_base.hpp:26,32: one record per node,
+ * agent and expanded action, down to BehaviorUctBase::MaxExtractionDepth) */
+typedef struct bmcts_edge_info {
+  uint32_t agent_id;
+  uint32_t depth;   /* depth of the node the action leaves from (root = 0) */
+  uint32_t action;  /* ego / cooperative agents: macro-action index; agents under hypotheses: the bit
+                       pattern of the sampled acceleration (the reference hashes the action value) */
+  float weight;     /* share of the node's visits of this agent that took the action */
+} bmcts_edge_info;
+
 typedef struct bmcts_planner bmcts_planner;
 
 int bmcts_planner_create(int kind, int device, bmcts_planner** out);
@@ -116,6 +126,14 @@ int bmcts_planner_decide_from_root_stats(bmcts_planner* p, const double* stats, 
  * over the ranks of `comm` (bmcts_allreduce_root) and re-decides from the merged statistics, so
  * that every rank of a root-parallel Plan() returns the same action */
 int bmcts_planner_allreduce_root_stats(bmcts_planner* p, bmcts_comm* comm, bmcts_plan_result* out);
+/* GetLastMctsEdgeInfo(): writes up to max_n records, returns how many the last search holds
+ * (BehaviorUctBase::ExtractEdgeInfo, default true) */
+int bmcts_planner_last_edges(bmcts_planner* p, bmcts_edge_info* edges, int max_n);
+/* GetLastMctsStateInfo() (BehaviorUctBase::ExtractStateInfo, default false): per extracted node its
+ * depth, alive mask over the search's agent slots and poses [A][4]; returns the number of nodes
+ * held, writes up to max_n; *n_agents receives A */
+int bmcts_planner_last_states(bmcts_planner* p, uint32_t* depth, uint32_t* agent_ids, float* pose,
+                              int max_n, int* n_agents);
 /* model of the neural warm start (kind BMCTS_PLANNER_NHEURISTIC_RISK_CONSTRAINT); must be set
  * before the first bmcts_planner_plan.  `user` is passed back to every call. */
 int bmcts_planner_set_node_prior(bmcts_planner* p, bmcts_node_prior_fn fn, void* user);

@@ -85,7 +85,10 @@ BehaviorUCTBase::BehaviorUCTBase(const ParamsPtr& params, int state_kind,
       mcts_parameters_(MctsParametersFromParamServer(*params_, kBase)),
       engine_config_(EngineConfigFromParamServer(*params_, kBase, state_kind, mcts_parameters_)),
       max_nearest_agents_((unsigned)params_->GetInt(std::string(kBase) + "MaxNearestAgents", 5)),
-      constant_action_idx_((int)params_->GetInt(std::string(kBase) + "ConstantActionIndex", -1)) {
+      constant_action_idx_((int)params_->GetInt(std::string(kBase) + "ConstantActionIndex", -1)),
+      extract_edge_info_(params_->GetBool(std::string(kBase) + "ExtractEdgeInfo", true)),
+      extract_state_info_(params_->GetBool(std::string(kBase) + "ExtractStateInfo", false)),
+      max_extraction_depth_((unsigned)params_->GetInt(std::string(kBase) + "MaxExtractionDepth", 10)) {
   if (!evaluator_) throw std::runtime_error("BehaviorUCT*: no rollout engine (no CPU fallback)");
 }
 
@@ -296,6 +299,15 @@ RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees, const Sta
     LeafEvaluator* evaluator = nullptr;
   };
   // runs trees from the shared counter on this thread's engines until none is left
+  // the tree infos are taken from the last tree only (they describe ONE tree)
+  auto collect_tree = [&](long t, Mcts& mcts) {
+    TreeResult r = collect(mcts);
+    if (t == trees - 1) {
+      if (extract_edge_info_) r.edges = mcts.ExtractEdges(max_extraction_depth_);
+      if (extract_state_info_) r.states = mcts.ExtractStates(max_extraction_depth_);
+    }
+    return r;
+  };
   auto worker = [&](long thread_index) {
     std::vector<Slot> slots((size_t)lanes);
     for (long k = 0; k < lanes; ++k)
@@ -316,7 +328,7 @@ RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees, const Sta
           return true;
         }
         s.mcts->FinishSearch();  // nothing to do (zero budget)
-        results[t] = collect(*s.mcts);
+        results[t] = collect_tree(t, *s.mcts);
       }
     };
     long active = 0;
@@ -331,7 +343,7 @@ RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees, const Sta
             continue;
           }
           s.mcts->FinishSearch();
-          results[s.tree] = collect(*s.mcts);
+          results[s.tree] = collect_tree(s.tree, *s.mcts);
           if (!refill(s)) active--;
         }
       }
@@ -376,6 +388,21 @@ RootStats BehaviorUCTBase::RunTrees(const SearchWorld& sw, long trees, const Sta
   last_solution_time_ = time_ms;
   last_max_tree_depth_ = results[trees - 1].max_depth;
   last_root_expanded_actions_ = results[trees - 1].root_expanded;
+  // ExtractMctsEdgeInfo / ExtractMctsStateInfo of the last tree (behavior_uct_hypothesis.cpp:69-79)
+  mcts_edge_infos_.clear();
+  for (const Mcts::EdgeInfo& e : results[trees - 1].edges)
+    mcts_edge_infos_.push_back({sw.slot_ids[(size_t)e.slot], e.depth, e.action, e.weight});
+  mcts_state_infos_.clear();
+  for (const Mcts::StateInfo& st : results[trees - 1].states) {
+    MctsStateInfo info;
+    info.depth = st.depth;
+    for (size_t a = 0; a < sw.slot_ids.size(); ++a) {
+      if (!((st.alive >> a) & 1u)) continue;
+      info.agent_ids.push_back(sw.slot_ids[a]);
+      info.states.push_back({0.0, st.pose[a * 4], st.pose[a * 4 + 1], st.pose[a * 4 + 2], st.pose[a * 4 + 3]});
+    }
+    mcts_state_infos_.push_back(std::move(info));
+  }
   return merged;
 }
 

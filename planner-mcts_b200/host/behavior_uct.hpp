@@ -30,6 +30,23 @@ struct UctBaseDebugInfos {  // behavior_uct_base.hpp:29-55
   // tree shape (what the reference's tests derive from GetLastMctsEdgeInfo)
   int GetLastMaxTreeDepth() const { return last_max_tree_depth_; }
   std::vector<int> GetLastRootExpandedActions() const { return last_root_expanded_actions_; }
+  // behavior_uct_base.hpp:32-37 (BarkMctsEdgeInfo / BarkMctsStateInfo of the last tree; filled
+  // when ExtractEdgeInfo / ExtractStateInfo are set, down to MaxExtractionDepth)
+  struct MctsEdgeInfo {
+    AgentId agent_id = 0;
+    unsigned depth = 0;
+    uint32_t action = 0;   // ego / cooperative: macro-action index; hypothesis agents: acceleration bits
+    double action_weight = 0.0;
+  };
+  struct MctsStateInfo {
+    unsigned depth = 0;
+    std::vector<AgentId> agent_ids;
+    std::vector<State> states;
+  };
+  std::vector<MctsEdgeInfo> GetLastMctsEdgeInfo() const { return mcts_edge_infos_; }
+  std::vector<MctsStateInfo> GetLastMctsStateInfo() const { return mcts_state_infos_; }
+  std::vector<MctsEdgeInfo> mcts_edge_infos_;
+  std::vector<MctsStateInfo> mcts_state_infos_;
   Policy last_return_values_;
   std::vector<AgentId> last_nearest_agents_;
   unsigned last_num_iterations_ = 0, last_num_nodes_ = 0;
@@ -136,6 +153,8 @@ class BehaviorUCTBase : public UctBaseDebugInfos {
     int max_depth = 0;
     std::vector<int> root_expanded;
     std::vector<double> lambdas;
+    std::vector<Mcts::EdgeInfo> edges;
+    std::vector<Mcts::StateInfo> states;
   };
   // runs `trees` independent searches (Mcts::NumParallelMcts) -- on threads with one engine
   // each when Mcts::UseMultiThreading is set, and with the waves of several trees in flight per
@@ -161,6 +180,8 @@ class BehaviorUCTBase : public UctBaseDebugInfos {
   bmcts_config engine_config_;
   unsigned max_nearest_agents_;
   int constant_action_idx_;
+  bool extract_edge_info_ = true, extract_state_info_ = false;  // behavior_uct_base.cpp:19-39
+  unsigned max_extraction_depth_ = 10;
   unsigned last_motion_idx_ = 0;
   unsigned tree_index_ = 0;
   Action last_action_;

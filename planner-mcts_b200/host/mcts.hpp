@@ -289,6 +289,65 @@ class Mcts {
     observer_ = observer;
     prior_visits_ = prior_visits;
   }
+  // mamcts MctsEdgeInfo / MctsStateInfo (behavior_uct_base.hpp:26-27,63-67: what the reference
+  // extracts for its tree viewer and its tree-shape tests): one record per (node, agent slot,
+  // expanded action) up to max_depth -- depth of the node, action (ego: macro-action index;
+  // others under hypotheses: bit pattern of the sampled acceleration), share of the node's visits
+  struct EdgeInfo {
+    int slot = 0;
+    unsigned depth = 0;
+    uint32_t action = 0;
+    double weight = 0.0;
+  };
+  std::vector<EdgeInfo> ExtractEdges(unsigned max_depth) const {
+    std::vector<EdgeInfo> out;
+    ForEachNode([&](const Node& n) {
+      if (!n.stats_ready || (unsigned)n.tree_depth > max_depth) return;
+      const UctStatistic* ego = n.ego_uct ? n.ego_uct.get() : n.ego_cc ? &n.ego_cc->reward_statistic() : nullptr;
+      if (ego) {
+        double tot = 0.0;
+        for (const auto& pr : ego->pairs()) tot += pr.count;
+        for (int a = 0; a < (int)ego->pairs().size(); ++a)
+          if (ego->pairs()[a].count > 0)
+            out.push_back({0, (unsigned)n.tree_depth, (uint32_t)a, ego->pairs()[a].count / std::max(1.0, tot)});
+      }
+      for (int s = 1; s < A_; ++s) {
+        if (other_mode_ == OtherMode::kHypothesis) {
+          if (n.other_hyp.empty()) continue;
+          std::map<ActionKey, double> by_key;
+          double tot = 0.0;
+          for (int h = 0; h < n.other_hyp[s].num_hypotheses(); ++h)
+            for (const auto& e : n.other_hyp[s].table(h))
+              if (e.resolved && e.count > 0) {
+                by_key[e.key] += e.count;
+                tot += e.count;
+              }
+          for (const auto& kv : by_key) out.push_back({s, (unsigned)n.tree_depth, kv.first, kv.second / std::max(1.0, tot)});
+        } else if (!n.other_uct.empty()) {
+          double tot = 0.0;
+          for (const auto& pr : n.other_uct[s].pairs()) tot += pr.count;
+          for (int a = 0; a < (int)n.other_uct[s].pairs().size(); ++a)
+            if (n.other_uct[s].pairs()[a].count > 0)
+              out.push_back({s, (unsigned)n.tree_depth, (uint32_t)a, n.other_uct[s].pairs()[a].count / std::max(1.0, tot)});
+        }
+      }
+    });
+    return out;
+  }
+  struct StateInfo {
+    unsigned depth = 0;
+    uint32_t alive = 0;
+    std::vector<float> pose;  // [A][4]
+  };
+  std::vector<StateInfo> ExtractStates(unsigned max_depth) const {
+    std::vector<StateInfo> out;
+    ForEachNode([&](const Node& n) {
+      if ((unsigned)n.tree_depth > max_depth) return;
+      out.push_back({(unsigned)n.tree_depth, n.alive, std::vector<float>(n.pose, n.pose + (size_t)A_ * 4)});
+    });
+    return out;
+  }
+
   // number of distinct actions expanded at the root per agent slot (tree-shape tests)
   std::vector<int> RootExpandedActions() const {
     std::vector<int> n(A_, 0);
@@ -819,6 +878,11 @@ class Mcts {
       const double limit = i < (int)constraints_.size() ? constraints_[i] : 0.0;
       lambdas_[i] = std::min(lam_max, std::max(0.0, lambdas_[i] + step * (q - limit) / range));
     }
+  }
+
+  template <class F>
+  void ForEachNode(const F& f) const {
+    for (size_t i = 0; i < n_nodes_; ++i) f(node_chunks_[i / kChunk][i % kChunk]);
   }
 
   MctsParameters p_, cc_params_;

@@ -250,6 +250,37 @@ int bmcts_planner_plan(bmcts_planner* p, double delta_time, double world_time, u
   return BMCTS_OK;
 }
 
+int bmcts_planner_last_edges(bmcts_planner* p, bmcts_edge_info* edges, int max_n) {
+  if (!p || !p->planner) return 0;
+  const auto infos = p->planner->GetLastMctsEdgeInfo();
+  for (int i = 0; edges && i < max_n && i < (int)infos.size(); ++i)
+    edges[i] = {infos[i].agent_id, infos[i].depth, infos[i].action, (float)infos[i].action_weight};
+  return (int)infos.size();
+}
+
+int bmcts_planner_last_states(bmcts_planner* p, uint32_t* depth, uint32_t* agent_ids, float* pose,
+                              int max_n, int* n_agents) {
+  if (!p || !p->planner) return 0;
+  const auto infos = p->planner->GetLastMctsStateInfo();
+  int A = 0;
+  for (const auto& s : infos) A = std::max(A, (int)s.agent_ids.size());
+  if (n_agents) *n_agents = A;
+  for (int i = 0; depth && agent_ids && pose && i < max_n && i < (int)infos.size(); ++i) {
+    depth[i] = infos[i].depth;
+    for (int a = 0; a < A; ++a) {
+      const bool have = a < (int)infos[i].agent_ids.size();
+      agent_ids[(size_t)i * A + a] = have ? infos[i].agent_ids[a] : 0xFFFFFFFFu;
+      const State st = have ? infos[i].states[a] : State();
+      float* q = pose + ((size_t)i * A + a) * 4;
+      q[0] = (float)st.x;
+      q[1] = (float)st.y;
+      q[2] = (float)st.theta;
+      q[3] = (float)st.v;
+    }
+  }
+  return (int)infos.size();
+}
+
 int bmcts_planner_set_true_behavior(bmcts_planner* p, uint32_t agent_id, const bmcts_hypothesis* model) {
   if (!p || !model) return BMCTS_ERR_INVALID_ARG;
   p->true_behaviors[agent_id] = *model;

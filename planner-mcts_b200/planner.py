@@ -25,6 +25,11 @@ class AgentState(C.Structure):
                 ("last_acc", C.c_float)]
 
 
+class EdgeInfo(C.Structure):
+    _fields_ = [("agent_id", C.c_uint32), ("depth", C.c_uint32), ("action", C.c_uint32),
+                ("weight", C.c_float)]
+
+
 class PlanResult(C.Structure):
     _fields_ = [
         ("best_action", C.c_uint32), ("num_iterations", C.c_uint32), ("num_nodes", C.c_uint32),
@@ -49,7 +54,7 @@ PLANNER_SYMBOLS = [
     "bmcts_planner_last_error", "bmcts_planner_set_node_prior", "bmcts_planner_observation_size",
     "bmcts_planner_observe", "bmcts_planner_node_prior_stats", "bmcts_planner_update_beliefs",
     "bmcts_planner_reset_beliefs", "bmcts_planner_allreduce_root_stats",
-    "bmcts_planner_set_true_behavior",
+    "bmcts_planner_set_true_behavior", "bmcts_planner_last_edges", "bmcts_planner_last_states",
 ]
 
 
@@ -78,6 +83,9 @@ def declare_planner_api(lib):
     lib.bmcts_planner_last_error.argtypes = [C.c_void_p]
     lib.bmcts_planner_last_error.restype = C.c_char_p
     lib.bmcts_planner_set_true_behavior.argtypes = [C.c_void_p, C.c_uint32, P(_abi.Hypothesis)]
+    lib.bmcts_planner_last_edges.argtypes = [C.c_void_p, P(EdgeInfo), C.c_int]
+    lib.bmcts_planner_last_states.argtypes = [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_float),
+                                              C.c_int, P(C.c_int)]
     if hasattr(lib, "bmcts_planner_allreduce_root_stats"):   # libbmcts.so only (needs a GPU)
         lib.bmcts_planner_allreduce_root_stats.argtypes = [C.c_void_p, C.c_void_p, P(PlanResult)]
     return lib
@@ -272,6 +280,48 @@ class _BehaviorUCT:
     @property
     def engine_launches(self):
         return int(self.last.engine_launches)
+
+    @property
+    def last_extracted_mcts_edges(self):
+        """python_planner_uct.cpp:175,202,265: [(agent id, depth, action, action weight), ...] of
+        the last search tree down to MaxExtractionDepth (ExtractEdgeInfo, default true)"""
+        n = self._lib.bmcts_planner_last_edges(self._h, None, 0)
+        buf = (EdgeInfo * max(1, n))()
+        self._lib.bmcts_planner_last_edges(self._h, buf, n)
+        return [(int(e.agent_id), int(e.depth), int(e.action), float(e.weight)) for e in buf[:n]]
+
+    @property
+    def last_extracted_mcts_states(self):
+        """[(depth, {agent id: (x, y, theta, v)}), ...] of the extracted nodes (ExtractStateInfo)"""
+        A = C.c_int(0)
+        n = self._lib.bmcts_planner_last_states(self._h, None, None, None, 0, C.byref(A))
+        if n == 0:
+            return []
+        depth = (C.c_uint32 * n)()
+        ids = (C.c_uint32 * (n * A.value))()
+        pose = (C.c_float * (n * A.value * 4))()
+        self._lib.bmcts_planner_last_states(self._h, depth, ids, pose, n, C.byref(A))
+        out = []
+        for i in range(n):
+            agents = {}
+            for a in range(A.value):
+                aid = ids[i * A.value + a]
+                if aid != 0xFFFFFFFF:
+                    agents[int(aid)] = tuple(pose[(i * A.value + a) * 4:(i * A.value + a) * 4 + 4])
+            out.append((int(depth[i]), agents))
+        return out
+
+    @property
+    def ego_behavior(self):
+        """python_planner_uct.cpp (ego_behavior): the ego's macro-action model as the planner builds
+        it from BehaviorUctBase::EgoBehavior::* -- the motion primitives in action-index order"""
+        b = "BehaviorUctBase::EgoBehavior::"
+        acc = self.params.get(b + "AccelerationInputs", [0.0, 1.0, 4.0, -1.0, -8.0])
+        prims = [("PrimitiveConstAccStayLane", float(a)) for a in acc]
+        if self.params.get(b + "AddLaneChangeActions", 1):
+            prims += [("PrimitiveConstAccChangeToLeft", 0.0), ("PrimitiveConstAccChangeToRight", 0.0)]
+        return {"model": "BehaviorMPMacroActions", "motion_primitives": prims,
+                "valid_primitives_at_last_plan": int(self.last.num_actions)}
 
     def root_stats(self):
         buf = (C.c_double * 128)()

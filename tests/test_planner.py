@@ -71,6 +71,17 @@ def test_hypothesis_planner_brakes_behind_slow_agent_and_tree_shape(make):
     # the second agent follows the first at its desired speed whatever the hypothesis says:
     # every planned action is the same value, i.e. one expanded action (:304-305)
     assert exp[2] == 1
+    # ... and the same facts the way the reference derives them, from the extracted edges
+    # (behavior_uct_hypothesis_test.cc:282-305: tuples (agent, depth, action, weight))
+    edges = pl.last_extracted_mcts_edges
+    assert 6 <= max(e[1] for e in edges) <= 10               # MaxExtractionDepth = 10
+    root_actions = {aid: {e[2] for e in edges if e[0] == aid and e[1] == 0} for aid in (1, 2, 3)}
+    assert 4 <= len(root_actions[1]) <= 10 and 3 <= len(root_actions[2]) <= 10
+    assert len(root_actions[3]) == 1
+    for aid in (1, 2, 3):    # weights are visit shares
+        assert sum(e[3] for e in edges if e[0] == aid and e[1] == 0) == pytest.approx(1.0)
+    assert pl.ego_behavior["motion_primitives"][2] == ("PrimitiveConstAccStayLane", 4.0)
+    assert pl.last_extracted_mcts_states == []                # ExtractStateInfo is off by default
     b = pl.current_beliefs(2)                 # one value per hypothesis, normalised
     assert b.shape == (2,) and b.sum() == pytest.approx(1.0)
     assert pl.parameter_sampling_probability(0) == pytest.approx(1.0 / (1.5 - 1.0), abs=1e-4)
@@ -237,6 +248,24 @@ def test_omniscient_planner_uses_the_true_behaviors_as_hypotheses(make):
     pl3 = make(P.BehaviorUCTHypothesis, omni, [])
     with pytest.raises(Exception, match="behaviour model"):
         pl3.Plan(0.2, world)
+
+
+def test_extracted_states_of_the_search_tree():
+    """BehaviorUctBase::ExtractStateInfo (behavior_uct_base.cpp:19-39): the agents' states at the
+    nodes of the last tree down to MaxExtractionDepth"""
+    world = W.observed_world(1, 12.0, 5.0, 0.0, goal_center=(150.0, -1.75))
+    params = W.base_params(200)
+    params[P0 + "ExtractStateInfo"] = 1
+    params[P0 + "MaxExtractionDepth"] = 2
+    pl = cpu(P.BehaviorUCTHypothesis, params, W.hypotheses())
+    pl.Plan(0.2, world)
+    states = pl.last_extracted_mcts_states
+    assert {d for d, _ in states} == {0, 1, 2}
+    root = [s for d, s in states if d == 0]
+    assert len(root) == 1 and set(root[0]) == {1, 2}
+    assert root[0][1][:2] == pytest.approx((3.0, -1.75)) and root[0][1][3] == pytest.approx(5.0)
+    assert all(s[1][0] > 3.0 for d, s in states if d == 1)     # the ego moved forward
+    assert max(e[1] for e in pl.last_extracted_mcts_edges) <= 2
 
 
 def test_root_parallel_merge_of_two_trees():
