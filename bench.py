@@ -503,6 +503,8 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         # ncclAllReduce behind the C ABI (one rank: nothing to merge, and NCCL stays unloaded)
         comm = root_parallel.RootComm(local_rank) if world > 1 else None
+        if comm is not None:
+            comm.allreduce(np.zeros(8))   # connection set-up of the new communicator, once
 
         def plan_arm(threads):
             trees = args.plan_trees if args.plan_trees > 0 else 2 * threads
@@ -522,7 +524,8 @@ def run_ours(args):
             cnt, ret = st[:n_act], st[n_act:2 * n_act]
             mean = np.where(cnt > 0, ret / np.maximum(cnt, 1), -np.inf)
             return dict(g, iterations=int(st[-2]), plan_ms=float(ms[0]), merge_ms=merge_ms,
-                        iterations_per_s=float(st[-2]) / (float(ms[0]) * 1e-3),
+                        # one Plan() = the ranks' searches + the merge of their root statistics
+                        iterations_per_s=float(st[-2]) / ((float(ms[0]) + merge_ms) * 1e-3),
                         merged_best_action=int(np.argmax(mean)), trees=world * trees,
                         workload=args.workload, host_cores=cores, host_threads_per_rank=threads,
                         merge="bmcts_allreduce_root (ncclAllReduce behind the C ABI)")
