@@ -35,6 +35,7 @@ extern "C" {
 #define BMCTS_MAX_CORRIDOR_PTS 16
 #define BMCTS_MAX_ROAD_PTS 32
 #define BMCTS_MAX_GOAL_PTS 8
+#define BMCTS_MAX_EXTRA_GOALS 3
 #define BMCTS_MAX_HYPOTHESES 64
 #define BMCTS_MAX_EGO_ACTIONS 16
 #define BMCTS_NUM_IDM_PARAMS 6
@@ -241,9 +242,15 @@ typedef struct bmcts_scenario {
   float agent_length[BMCTS_MAX_AGENTS]; /* rectangle shapes; BARK CarRectangle = 4 x 2 */
   float agent_width[BMCTS_MAX_AGENTS];
   float agent_rear[BMCTS_MAX_AGENTS];   /* rear edge -> reference point, 1.25 */
+  /* Cooperative state: every agent is evaluated from its own perspective AGAINST ITS OWN GOAL
+   * (mcts_state_cooperative.cpp:76-84: ObservedWorld(predicted_world, agent)).  agent_goal[a] = 0:
+   * `goal` above; k > 0: extra_goals[k - 1].  Slot 0 (the ego) is always 0; the hypothesis /
+   * risk states only evaluate the ego and ignore the table. */
+  int32_t agent_goal[BMCTS_MAX_AGENTS];
+  bmcts_goal extra_goals[BMCTS_MAX_EXTRA_GOALS];
   bmcts_hypothesis hypotheses[BMCTS_MAX_HYPOTHESES];
   bmcts_ego_action ego_actions[BMCTS_MAX_EGO_ACTIONS];
-  int32_t pad2_[2]; /* sizeof % 16 == 0: the kernels stage this struct with 16-byte copies */
+  int32_t pad2_[4]; /* sizeof % 16 == 0: the kernels stage this struct with 16-byte copies */
 } bmcts_scenario;
 
 /* per-rollout scalar results, one 32-byte record */

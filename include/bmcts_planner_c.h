@@ -104,6 +104,11 @@ int bmcts_planner_set_tree_index(bmcts_planner* p, uint32_t tree_index);
  * (behavior_uct_hypothesis_base.hpp:80-90: the omniscient planner -- every other agent is predicted
  * with its own model, no beliefs).  Kept until overwritten. */
 int bmcts_planner_set_true_behavior(bmcts_planner* p, uint32_t agent_id, const bmcts_hypothesis* model);
+/* The goal definition of agent `agent_id` (BARK Agent::GetGoalDefinition); NULL forgets it.  The
+ * cooperative planner evaluates every agent against its own goal (mcts_state_cooperative.cpp:76-84);
+ * an agent without one shares the ego's (the map's).  At most BMCTS_MAX_EXTRA_GOALS distinct
+ * definitions besides the ego's. */
+int bmcts_planner_set_agent_goal(bmcts_planner* p, uint32_t agent_id, const bmcts_goal* goal);
 /* BehaviorUCT*::Plan(delta_time, observed_world) */
 int bmcts_planner_plan(bmcts_planner* p, double delta_time, double world_time, uint32_t ego_id,
                        const bmcts_agent_state* agents, int n_agents, bmcts_plan_result* out);

@@ -508,8 +508,9 @@ static uint32_t evaluate(const bmcts_config* cfg, const bmcts_scenario* scn, con
       box_t bj = agent_box(scn, j, w->a[j].x, w->a[j].y, w->a[j].c, w->a[j].s, 0.0f, 0.0f);
       if (boxes_overlap(&be, &bj)) f |= BMCTS_F_COLLISION_OTHER;
     }
-    /* :261-262 EvaluatorGoalReached */
-    const bmcts_goal* g = &scn->goal;
+    /* :261-262 EvaluatorGoalReached against the goal of the agent whose perspective this is
+     * (mcts_state_cooperative.cpp:76-84 builds ObservedWorld(predicted_world, agent)) */
+    const bmcts_goal* g = scn->agent_goal[e] > 0 ? &scn->extra_goals[scn->agent_goal[e] - 1] : &scn->goal;
     if (g->kind == BMCTS_GOAL_POLYGON) {
       if (box_within_polygon(&be, g->px, g->py, g->n_pts)) f |= BMCTS_F_GOAL_REACHED;
     } else if (g->kind == BMCTS_GOAL_FRENET_LIMITS) {

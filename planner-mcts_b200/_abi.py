@@ -11,6 +11,7 @@ MAX_CORRIDORS = 4
 MAX_CORRIDOR_PTS = 16
 MAX_ROAD_PTS = 32
 MAX_GOAL_PTS = 8
+MAX_EXTRA_GOALS = 3
 MAX_HYPOTHESES = 64
 MAX_EGO_ACTIONS = 16
 NUM_IDM_PARAMS = 6
@@ -98,8 +99,9 @@ class Scenario(C.Structure):
         ("goal", Goal),
         ("agent_length", f32 * MAX_AGENTS), ("agent_width", f32 * MAX_AGENTS),
         ("agent_rear", f32 * MAX_AGENTS),
+        ("agent_goal", i32 * MAX_AGENTS), ("extra_goals", Goal * MAX_EXTRA_GOALS),
         ("hypotheses", Hypothesis * MAX_HYPOTHESES),
-        ("ego_actions", EgoAction * MAX_EGO_ACTIONS), ("pad2_", i32 * 2),
+        ("ego_actions", EgoAction * MAX_EGO_ACTIONS), ("pad2_", i32 * 4),
     ]
 
 

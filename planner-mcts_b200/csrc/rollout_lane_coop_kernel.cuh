@@ -62,6 +62,7 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
   const float* reach = reinterpret_cast<const float*>(smem_raw + lay.off_rad);
   const float* goal_bb = reach + 2 * BMCTS_MAX_AGENTS;
   const float* rects = goal_bb + 4;
+  const float* goal_bb_extra = rects + 8 + 2 * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = lane % T;
@@ -75,8 +76,6 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
   const uint32_t gmask = T == 32 ? 0xffffffffu : (((1u << T) - 1u) << (lane & ~(T - 1)));
 
   const bool add_sd = cfg.add_safe_dist != 0;
-  const bool goal_poly = scn.goal.kind == BMCTS_GOAL_POLYGON;
-  const bool goal_frenet = scn.goal.kind == BMCTS_GOAL_FRENET_LIMITS;
   const int n_road = scn.n_road_pts;
   const bool want_final = p.final_pose != nullptr && p.do_rollout != 0;
 
@@ -230,6 +229,13 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
         ca[K_V * fstride] = v;
         ca[K_CS * fstride] = cs;
         ca[K_SN * fstride] = sn;
+        // the goal of THIS agent (mcts_state_cooperative.cpp:76-84: every agent is evaluated in
+        // its own ObservedWorld, i.e. against its own goal definition)
+        const int gk = scn.agent_goal[a];
+        const bmcts_goal& gl = gk > 0 ? scn.extra_goals[gk - 1] : scn.goal;
+        const float* gbb = gk > 0 ? goal_bb_extra + 4 * (gk - 1) : goal_bb;
+        const bool goal_poly = gl.kind == BMCTS_GOAL_POLYGON;
+        const bool goal_frenet = gl.kind == BMCTS_GOAL_FRENET_LIMITS;
         // Frenet projection on every lane corridor; current corridor = arg min |d|
         float best = kBig, goal_d = 0.0f, goal_ang = 0.0f;
         bool goal_in = false;
@@ -251,7 +257,7 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
           const bool better = m < best;
           best = better ? m : best;
           bc = better ? c : bc;
-          if (goal_frenet && c == scn.goal.corridor) {
+          if (goal_frenet && c == gl.corridor) {
             goal_d = pr.d;
             goal_in = pr.in;
             goal_ang = bm_norm_angle(th - cc.angle[pr.seg]);
@@ -272,18 +278,17 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
           float cx, cy;
           box_corner(road ? bd : be, q & 3, cx, cy);
           bool in;
-          if (!road && (cx < goal_bb[0] || cx > goal_bb[1] || cy < goal_bb[2] || cy > goal_bb[3]))
+          if (!road && (cx < gbb[0] || cx > gbb[1] || cy < gbb[2] || cy > gbb[3]))
             in = false;  // outside the goal's bounding box (1 cm margin)
           else if (road && in_rects(rects, cx, cy))
             in = true;  // inside an inner rectangle of the road polygon
           else
-            in = point_in_polygon(road ? scn.road_x : scn.goal.px, road ? scn.road_y : scn.goal.py,
-                                  road ? n_road : scn.goal.n_pts, cx, cy);
+            in = point_in_polygon(road ? scn.road_x : gl.px, road ? scn.road_y : gl.py,
+                                  road ? n_road : gl.n_pts, cx, cy);
           if (!in) f |= road ? (uint32_t)BMCTS_F_COLLISION_DRIVABLE : kGoalFailBit;
         }
         if (goal_poly && !(f & kGoalFailBit)) f |= BMCTS_F_GOAL_REACHED;
         if (goal_frenet) {
-          const bmcts_goal& gl = scn.goal;
           bool ok = goal_in && goal_d <= gl.max_lat_left && -goal_d <= gl.max_lat_right &&
                     goal_ang <= gl.max_angle_left && -goal_ang <= gl.max_angle_right &&
                     v >= gl.vel_lo && v <= gl.vel_hi;

@@ -61,8 +61,10 @@ __host__ __device__ inline LaneLayout lane_layout(int A, int C, int H, int T, in
   b += smem_align16(sizeof(uint32_t) * 4 * (size_t)(H > 0 ? H : 1));  // flags, 1/v0, 1/(2 sqrt(ab))
   l.off_rad = b;  // per agent: plain / static-inflated bounding radius; then the goal's AABB
   // + goal AABB + 2 inner rects + safe arc intervals [lo | hi][corridor][segment]
+  // (+ the AABBs of the other agents' goals, cooperative state)
   b += smem_align16(sizeof(float) * (2 * BMCTS_MAX_AGENTS + 4 + 8 +
-                                     2 * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS));
+                                     2 * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS +
+                                     4 * BMCTS_MAX_EXTRA_GOALS));
   l.off_state = b;
   l.warp_bytes = sizeof(float) * (size_t)(L_PROJ + C) * A * (32 / T);
   l.total = b + l.warp_bytes * warps;
@@ -103,18 +105,23 @@ __device__ __forceinline__ void stage_reach(const bmcts_scenario* scn, const bmc
                                     : 0.0f);
   }
   if (tid == 0) {  // goal polygon AABB, grown by 1 cm: a point outside it is outside the goal
-    float x0 = kBig, x1 = -kBig, y0 = kBig, y1 = -kBig;
-    for (int i = 0; i < scn->goal.n_pts && i < BMCTS_MAX_GOAL_PTS; ++i) {
-      x0 = bm_min(x0, scn->goal.px[i]);
-      x1 = bm_max(x1, scn->goal.px[i]);
-      y0 = bm_min(y0, scn->goal.py[i]);
-      y1 = bm_max(y1, scn->goal.py[i]);
-    }
     float* bb = rad + 2 * BMCTS_MAX_AGENTS;
-    bb[0] = x0 - 0.01f;
-    bb[1] = x1 + 0.01f;
-    bb[2] = y0 - 0.01f;
-    bb[3] = y1 + 0.01f;
+    float* bb_extra = bb + 12 + 2 * BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS;
+    for (int k = 0; k <= BMCTS_MAX_EXTRA_GOALS; ++k) {
+      const bmcts_goal& gl = k == 0 ? scn->goal : scn->extra_goals[k - 1];
+      float x0 = kBig, x1 = -kBig, y0 = kBig, y1 = -kBig;
+      for (int i = 0; i < gl.n_pts && i < BMCTS_MAX_GOAL_PTS; ++i) {
+        x0 = bm_min(x0, gl.px[i]);
+        x1 = bm_max(x1, gl.px[i]);
+        y0 = bm_min(y0, gl.py[i]);
+        y1 = bm_max(y1, gl.py[i]);
+      }
+      float* o = k == 0 ? bb : bb_extra + 4 * (k - 1);
+      o[0] = x0 - 0.01f;
+      o[1] = x1 + 0.01f;
+      o[2] = y0 - 0.01f;
+      o[3] = y1 + 0.01f;
+    }
     // inner rectangles of the road polygon (engine.cu stores them behind the scenario)
     const float* rc = reinterpret_cast<const float*>(scn + 1);
     for (int i = 0; i < 8; ++i) bb[4 + i] = rc[i];

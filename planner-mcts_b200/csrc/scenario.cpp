@@ -136,12 +136,17 @@ int bmcts_scenario_finalize(bmcts_scenario* s) {
     if (t < BMCTS_ACT_CONST_ACC_STAY_LANE || t > BMCTS_ACT_CHANGE_RIGHT)
       return BMCTS_ERR_INVALID_ARG;
   }
-  if (s->goal.kind == BMCTS_GOAL_POLYGON) {
-    if (s->goal.n_pts < 3 || s->goal.n_pts > BMCTS_MAX_GOAL_PTS) return BMCTS_ERR_INVALID_ARG;
-  } else if (s->goal.kind == BMCTS_GOAL_FRENET_LIMITS) {
-    if (s->goal.corridor < 0 || s->goal.corridor >= s->n_corridors) return BMCTS_ERR_INVALID_ARG;
-  } else if (s->goal.kind != BMCTS_GOAL_NONE) {
-    return BMCTS_ERR_INVALID_ARG;
+  auto goal_ok = [&](const bmcts_goal& g) {
+    if (g.kind == BMCTS_GOAL_POLYGON) return g.n_pts >= 3 && g.n_pts <= BMCTS_MAX_GOAL_PTS;
+    if (g.kind == BMCTS_GOAL_FRENET_LIMITS) return g.corridor >= 0 && g.corridor < s->n_corridors;
+    return g.kind == BMCTS_GOAL_NONE;
+  };
+  if (!goal_ok(s->goal)) return BMCTS_ERR_INVALID_ARG;
+  if (s->agent_goal[0] != 0) return BMCTS_ERR_INVALID_ARG;  // the ego's goal is `goal`
+  for (int a = 0; a < s->n_agents; ++a) {
+    const int k = s->agent_goal[a];
+    if (k < 0 || k > BMCTS_MAX_EXTRA_GOALS) return BMCTS_ERR_INVALID_ARG;
+    if (k > 0 && !goal_ok(s->extra_goals[k - 1])) return BMCTS_ERR_INVALID_ARG;
   }
   s->finalized = 1;
   return BMCTS_OK;

@@ -148,6 +148,22 @@ BehaviorUCTBase::SearchWorld BehaviorUCTBase::BuildSearchWorld(
     sw.pose[(size_t)i * 4 + 2] = (float)a->state.theta;
     sw.pose[(size_t)i * 4 + 3] = (float)a->state.v;
   }
+  // goals of the other agents (cooperative state): distinct definitions go to extra_goals
+  int n_extra = 0;
+  for (int i = 0; i < BMCTS_MAX_AGENTS; ++i) s.agent_goal[i] = 0;
+  for (int i = 1; i < s.n_agents; ++i) {
+    const Agent* a = order[i];
+    if (!a->has_goal || std::memcmp(&a->goal, &s.goal, sizeof(bmcts_goal)) == 0) continue;
+    int k = 0;
+    while (k < n_extra && std::memcmp(&a->goal, &s.extra_goals[k], sizeof(bmcts_goal)) != 0) ++k;
+    if (k == n_extra) {
+      if (n_extra == BMCTS_MAX_EXTRA_GOALS)
+        throw std::runtime_error("more distinct agent goals than the engine holds (1 + " +
+                                 std::to_string(BMCTS_MAX_EXTRA_GOALS) + ")");
+      s.extra_goals[n_extra++] = a->goal;
+    }
+    s.agent_goal[i] = k + 1;
+  }
   sw.alive = ego ? ((s.n_agents >= 32) ? 0xffffffffu : ((1u << s.n_agents) - 1u)) : 0u;
   s.n_hypotheses = (int)std::min<size_t>(hypotheses.size(), BMCTS_MAX_HYPOTHESES);
   for (int h = 0; h < s.n_hypotheses; ++h) s.hypotheses[h] = hypotheses[h].region;

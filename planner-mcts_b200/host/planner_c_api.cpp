@@ -149,6 +149,11 @@ ObservedWorld WorldOf(const bmcts_planner* p, double world_time, uint32_t ego_id
       a.has_behavior_model = true;
       a.behavior_model = tb->second;
     }
+    auto ag = p->agent_goals.find(agents[i].id);
+    if (ag != p->agent_goals.end()) {
+      a.has_goal = true;
+      a.goal = ag->second;
+    }
     w.agents.push_back(a);
   }
   return w;
@@ -279,6 +284,15 @@ int bmcts_planner_last_states(bmcts_planner* p, uint32_t* depth, uint32_t* agent
     }
   }
   return (int)infos.size();
+}
+
+int bmcts_planner_set_agent_goal(bmcts_planner* p, uint32_t agent_id, const bmcts_goal* goal) {
+  if (!p) return BMCTS_ERR_INVALID_ARG;
+  if (!goal)
+    p->agent_goals.erase(agent_id);
+  else
+    p->agent_goals[agent_id] = *goal;
+  return BMCTS_OK;
 }
 
 int bmcts_planner_set_true_behavior(bmcts_planner* p, uint32_t agent_id, const bmcts_hypothesis* model) {

@@ -16,6 +16,7 @@ struct bmcts_planner {
   unsigned tree_index = 0;
   std::shared_ptr<bark_mcts_b200::Params> params = std::make_shared<bark_mcts_b200::Params>();
   std::vector<bark_mcts_b200::BehaviorHypothesisIDM> hypotheses;
+  std::map<uint32_t, bmcts_goal> agent_goals;  // agent id -> its own goal definition
   std::map<uint32_t, bmcts_hypothesis> true_behaviors;  // agent id -> its own behaviour model
   std::vector<double> risk_integrals;  // scenario-risk integral per hypothesis (may be empty)
   std::shared_ptr<bark_mcts_b200::MapGeometry> map;

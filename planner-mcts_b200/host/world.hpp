@@ -45,6 +45,11 @@ struct Agent {
   // behavior_uct_hypothesis_base.hpp:80-90)
   bool has_behavior_model = false;
   bmcts_hypothesis behavior_model{};
+  // the agent's own goal definition (BARK Agent::GetGoalDefinition), if it has one: the
+  // cooperative planner evaluates every agent against its own goal
+  // (mcts_state_cooperative.cpp:76-84); without one the agent shares the ego's
+  bool has_goal = false;
+  bmcts_goal goal{};
 };
 
 // Map reduced to the path's inputs: only corridors, road polygon and goal of this

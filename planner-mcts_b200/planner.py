@@ -55,6 +55,7 @@ PLANNER_SYMBOLS = [
     "bmcts_planner_observe", "bmcts_planner_node_prior_stats", "bmcts_planner_update_beliefs",
     "bmcts_planner_reset_beliefs", "bmcts_planner_allreduce_root_stats",
     "bmcts_planner_set_true_behavior", "bmcts_planner_last_edges", "bmcts_planner_last_states",
+    "bmcts_planner_set_agent_goal",
 ]
 
 
@@ -83,6 +84,7 @@ def declare_planner_api(lib):
     lib.bmcts_planner_last_error.argtypes = [C.c_void_p]
     lib.bmcts_planner_last_error.restype = C.c_char_p
     lib.bmcts_planner_set_true_behavior.argtypes = [C.c_void_p, C.c_uint32, P(_abi.Hypothesis)]
+    lib.bmcts_planner_set_agent_goal.argtypes = [C.c_void_p, C.c_uint32, P(_abi.Goal)]
     lib.bmcts_planner_last_edges.argtypes = [C.c_void_p, P(EdgeInfo), C.c_int]
     lib.bmcts_planner_last_states.argtypes = [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_float),
                                               C.c_int, P(C.c_int)]
@@ -105,6 +107,9 @@ class Agent:
     # the agent's own behaviour model (a HypothesisIDM / _abi.Hypothesis region), if known: the
     # omniscient planners (UseTrueBehaviorsAsHypothesis) predict the agent with it
     behavior_model: object = None
+    # the agent's own goal definition (an _abi.Goal), if it has one: the cooperative planner
+    # evaluates every agent against its own goal
+    goal: object = None
 
 
 @dataclass
@@ -218,6 +223,8 @@ class _BehaviorUCT:
         arr = (AgentState * n)()
         for i, a in enumerate(observed_world.agents):
             arr[i] = AgentState(a.id, a.x, a.y, a.theta, a.v, a.length, a.width, a.rear, a.last_acc)
+            if a.goal is not None:
+                self._check(self._lib.bmcts_planner_set_agent_goal(self._h, int(a.id), C.byref(a.goal)))
             if a.behavior_model is not None:
                 region = getattr(a.behavior_model, "region", a.behavior_model)
                 self._check(self._lib.bmcts_planner_set_true_behavior(self._h, int(a.id), C.byref(region)))

@@ -68,7 +68,10 @@ def ego_actions(acc_inputs=(0.0, 1.0, 4.0, -1.0, -8.0), lane_changes=True):
     return acts
 
 
-def build_scenario(corridors, road, n_agents, hypotheses, actions, goal=None, shapes=None):
+def build_scenario(corridors, road, n_agents, hypotheses, actions, goal=None, shapes=None,
+                   agent_goals=None):
+    """agent_goals: {agent slot: _abi.Goal} for agents that do not share the ego's goal
+    (cooperative state; at most _abi.MAX_EXTRA_GOALS distinct definitions)"""
     lib = _abi.load_library()
     s = _abi.Scenario()
     s.n_corridors = len(corridors)
@@ -90,6 +93,13 @@ def build_scenario(corridors, road, n_agents, hypotheses, actions, goal=None, sh
         s.ego_actions[i].type, s.ego_actions[i].acceleration = t, acc
     if goal is not None:
         s.goal = goal
+    extra = []
+    for a, g in (agent_goals or {}).items():
+        key = bytes(g)
+        if key not in extra:
+            extra.append(key)
+            s.extra_goals[len(extra) - 1] = g
+        s.agent_goal[a] = 1 + extra.index(key)
     st = lib.bmcts_scenario_finalize(s)
     if st != _abi.OK:
         raise _abi.BmctsError(st, "bmcts_scenario_finalize: " +

@@ -67,10 +67,11 @@ class Scenario:
             self.corridors.append({"pts": pts, "half_width": float(k.half_width), "left": k.left,
                                    "right": k.right})
         self.road = np.array([[scn.road_x[i], scn.road_y[i]] for i in range(scn.n_road_pts)], np.float64)
-        g = scn.goal
-        self.goal_kind = g.kind
-        self.goal_poly = np.array([[g.px[i], g.py[i]] for i in range(g.n_pts)], np.float64)
-        self.goal = g
+        # goal per agent slot: the ego's, or (cooperative state) the agent's own
+        self.goals = []
+        for a in range(self.A):
+            g = scn.extra_goals[scn.agent_goal[a] - 1] if scn.agent_goal[a] > 0 else scn.goal
+            self.goals.append((g.kind, np.array([[g.px[i], g.py[i]] for i in range(g.n_pts)], np.float64), g))
         self.length = [float(scn.agent_length[a]) for a in range(self.A)]
         self.width = [float(scn.agent_width[a]) for a in range(self.A)]
         self.rear = [float(scn.agent_rear[a]) for a in range(self.A)]
@@ -355,13 +356,14 @@ def evaluate(w, e, margins):
         margins.append(abs(rect_gap(body, rects[j])))
         if clip_area(body, rects[j]) > 0.0:
             f |= F_COLLISION
-    if sc.goal_kind == 1:
+    goal_kind, goal_poly, goal = sc.goals[e]
+    if goal_kind == 1:
         for p in body:
-            margins.append(polygon_margin(sc.goal_poly, p[0], p[1]))
-        if all(winding_inside(sc.goal_poly, p[0], p[1]) for p in body):
+            margins.append(polygon_margin(goal_poly, p[0], p[1]))
+        if all(winding_inside(goal_poly, p[0], p[1]) for p in body):
             f |= F_GOAL
-    elif sc.goal_kind == 2:
-        g = sc.goal
+    elif goal_kind == 2:
+        g = goal
         c = g.corridor
         ang = wrap(w.th[e] - sc.corridors[c]["angle"][w.seg[e, c]])
         d = w.d[e, c]

@@ -91,7 +91,19 @@ def random_case(seed):
                                                              size=int(rng.integers(1, 6)),
                                                              replace=False).tolist()),
                                  lane_changes=bool(rng.integers(0, 2)))
-    scn = scenarios.build_scenario(cors, road, A, hyps, acts, goal, shapes=shapes)
+    # cooperative state: some agents pursue their own goal (mcts_state_cooperative.cpp:76-84)
+    agent_goals = {}
+    if coop and A > 1 and seed % 2 == 1:
+        pool = [scenarios.frenet_goal(int(rng.integers(0, len(cors))), max_lat=(0.4, 0.9),
+                                      max_angle=(0.1, 0.3), vel=(0.0, 25.0)),
+                scenarios.polygon_goal([(40.0, 10.0), (400.0, 10.0), (400.0, -12.0), (40.0, -12.0)]),
+                scenarios.polygon_goal([(0.0, 1.0), (90.0, 1.0), (90.0, -5.0), (0.0, -5.0)])]
+        for a in range(1, A):
+            k = int(rng.integers(0, 4))
+            if k:
+                agent_goals[a] = pool[k - 1]
+    scn = scenarios.build_scenario(cors, road, A, hyps, acts, goal, shapes=shapes,
+                                   agent_goals=agent_goals)
     lane_of, s_of = scenarios.place_agents(A, lanes, rng, ego_lane=ego_lane,
                                            ego_s=float(rng.uniform(20.0, 80.0)))
     return cfg, scn, lane_of, s_of, rng

@@ -239,3 +239,27 @@ def test_unique_state_form_of_a_leaf_batch_equals_the_expanded_batch():
     b = oracle.rollout(cfg, scn, pose[:, index], alive[index], hyp, depth=depth[index])
     for k in a:
         assert a[k].tobytes() == b[k].tobytes(), k
+
+
+def test_cooperative_agents_are_evaluated_against_their_own_goals():
+    """mcts_state_cooperative.cpp:76-84: r_j comes from ObservedWorld(predicted_world, j), i.e. from
+    agent j's OWN goal.  Ego goal far away, the other agent's goal around where it will be after the
+    step: r_ego = 0, r_1 = GoalReward = 100; with cf = 0.2 and n = 2 the mixed rewards are
+    (1/2)((1-cf) 0 + cf 100) = 10 for the ego and (1/2)((1-cf) 100 + cf 0) = 40 for the agent."""
+    from planner_mcts_b200 import scenarios
+    cors, road = scenarios.highway_geometry(300.0)
+    far = scenarios.polygon_goal([(250.0, 0.0), (300.0, 0.0), (300.0, -3.5), (250.0, -3.5)])
+    near = scenarios.polygon_goal([(20.0, -2.0), (60.0, -2.0), (60.0, -6.0), (20.0, -6.0)])
+    pose = np.zeros((2, 1, 4), np.float32)
+    pose[0, 0] = (30.0, -1.75, 0.0, 5.0)
+    pose[1, 0] = (40.0, -4.75, 0.0, 5.0)
+    cfg = _abi.default_config()
+    cfg.state_kind = _abi.STATE_COOPERATIVE
+    act = np.zeros((2, 1), np.uint8)
+    for goals, want in (({}, (0.0, 0.0)), ({1: near}, (10.0, 40.0))):
+        scn = scenarios.build_scenario(cors, road, 2, [], scenarios.ego_actions((0.0,), False), far,
+                                       agent_goals=goals)
+        out = oracle.step(cfg, scn, pose, np.array([3], np.uint32), np.zeros((2, 1), np.uint8), act)
+        assert int(out["flags"][0]) == 0                      # the EGO reached nothing
+        assert out["reward"][:, 0].tolist() == pytest.approx(list(want))
+        assert out["cost"][0, 0] == pytest.approx(-want[0])   # cost[0] = -reward_ego (:110-111)

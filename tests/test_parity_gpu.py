@@ -117,6 +117,33 @@ def test_unique_state_form_parity(name, monkeypatch):
     assert got.tobytes() == want["result"].tobytes()
 
 
+def test_cooperative_state_with_per_agent_goals():
+    """agents of the cooperative state pursuing their own goals (bmcts_scenario.agent_goal /
+    extra_goals; mcts_state_cooperative.cpp:76-84): rollouts and steps bit-exact against the oracle"""
+    cfg, scn0, meta = scenarios.workload("c4_coop", horizon=20)
+    cors, road = scenarios.highway_geometry(500.0)
+    goals = {a: [scenarios.polygon_goal([(100.0, 0.0), (200.0, 0.0), (200.0, -6.0), (100.0, -6.0)]),
+                 scenarios.frenet_goal(1, max_lat=(0.5, 0.5), max_angle=(0.2, 0.2), vel=(0.0, 9.0)),
+                 scenarios.polygon_goal([(60.0, -3.0), (500.0, -3.0), (500.0, -6.0), (60.0, -6.0)])][a % 3]
+             for a in range(1, 20, 2)}
+    scn = scenarios.build_scenario(cors, road, 20, [], scenarios.ego_actions(), scn0.goal,
+                                   agent_goals=goals)
+    pose, alive, hyp = scenarios.leaves_for(scn, meta, 96, seed=5)
+    eng = RolloutEngine(cfg, scn)
+    g = eng.rollout(pose, alive, hyp, seed=11, stream=1, first_rollout_id=3, want_agents=True,
+                    want_final=True)
+    c = oracle.rollout(cfg, scn, pose, alive, hyp, seed=11, stream=1, first_rollout_id=3, n_threads=8)
+    parity.assert_results_match(g, c)
+    plain = oracle.rollout(cfg, scn0, pose, alive, hyp, seed=11, stream=1, first_rollout_id=3,
+                           n_threads=8)
+    assert not np.array_equal(c["ret_agents"], plain["ret_agents"])   # the goals matter
+    rng = np.random.default_rng(2)
+    action = rng.integers(0, scn.n_ego_actions, size=(20, 96)).astype(np.uint8)
+    g = eng.step(pose, alive, hyp, action, seed=4)
+    c = oracle.step(cfg, scn, pose, alive, hyp, action, seed=4)
+    parity.assert_steps_match(g, c)
+
+
 @pytest.mark.parametrize("name", GEOMETRIES)
 def test_rollout_parity(name):
     cfg, scn, meta = scenarios.workload(name, horizon=20)

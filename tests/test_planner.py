@@ -268,6 +268,28 @@ def test_extracted_states_of_the_search_tree():
     assert max(e[1] for e in pl.last_extracted_mcts_edges) <= 2
 
 
+@pytest.mark.parametrize("make", BACKENDS)
+def test_cooperative_planner_with_an_agent_that_has_its_own_goal(make):
+    """Agent.goal: the cooperative search rewards the other agent for ITS goal
+    (mcts_state_cooperative.cpp:76-84) -- the statistics differ from the shared-goal search"""
+    from planner_mcts_b200 import scenarios
+    params = W.base_params(300)
+    params[P0 + "Mcts::UctStatistic::ProgressiveWidening::K"] = 4.0
+    stats = []
+    for own_goal in (False, True):
+        world = W.observed_world(1, 6.0, 5.0, 0.0, goal_center=(150.0, -1.75))
+        if own_goal:
+            world.agents[1].goal = scenarios.polygon_goal([(10.0, 1.0), (40.0, 1.0), (40.0, -5.0), (10.0, -5.0)])
+        pl = make(P.BehaviorUCTCooperative, params)
+        pl.Plan(0.2, world)
+        stats.append(pl.root_stats())
+    assert not np.array_equal(stats[0], stats[1])
+    n_act = 5
+    # the other agent collects its goal reward at once; the ego's share of it (cf = 0.2) shows
+    assert (stats[1][n_act:2 * n_act] / np.maximum(stats[1][:n_act], 1)).max() > \
+        (stats[0][n_act:2 * n_act] / np.maximum(stats[0][:n_act], 1)).max()
+
+
 def test_root_parallel_merge_of_two_trees():
     """root-parallel search (Mcts::NumParallelMcts; SURVEY.md 8e): two trees with distinct
     tree indices, statistics merged by summation, decision from the merged statistics"""
