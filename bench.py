@@ -206,8 +206,10 @@ def make_batch(scn, meta, n, share, seed):
     hyp = rng.integers(0, max(1, scn.n_hypotheses), size=(scn.n_agents, n), dtype=np.uint8)
     index = None
     if share > 1:
+        # the rollouts of one state are adjacent, the way a search emits them (node by node, each
+        # under its freshly sampled hypotheses); the C ABI takes the state table state-major
         index = np.repeat(np.arange(ns, dtype=np.uint32), share)
-        rng.shuffle(index)   # a wave does not come sorted by state
+        pose = np.ascontiguousarray(pose.transpose(1, 0, 2))
     return pose, alive, hyp, index
 
 
@@ -219,8 +221,8 @@ class Arm:
         from planner_mcts_b200 import _abi
         self.eng, self.n, self.rank, self._abi, self.torch = eng, n, rank, _abi, torch
         pose, alive, hyp, index = make_batch(scn, meta, n, share, seed)
-        self.ns = pose.shape[1]
         self.indexed = index is not None
+        self.ns = pose.shape[0] if self.indexed else pose.shape[1]
         t = lambda a: None if a is None else torch.from_numpy(a)
         host = [t(pose), t(alive.view(np.int32)), t(hyp), t(None if index is None else index.view(np.int32))]
         self.dev = [None if x is None else x.to(dev) for x in host]
@@ -354,6 +356,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     n = args.cpu_rollouts
     pose, alive, hyp, index = make_batch(scn, meta, n, args.share, seed=1)
+    if index is not None:
+        pose = np.ascontiguousarray(pose.transpose(1, 0, 2))   # tests/oracle.py takes [A, n_states, 4]
     oracle.load()
     kw = dict(state_index=index, n_threads=cores)
     w = max(64, n // 16)
@@ -630,6 +634,8 @@ def cpu_baseline(args, cfg, scn, meta):
     cores = os.cpu_count() or 1
     n = args.cpu_rollouts
     pose, alive, hyp, index = make_batch(scn, meta, n, args.share, seed=1)
+    if index is not None:
+        pose = np.ascontiguousarray(pose.transpose(1, 0, 2))   # tests/oracle.py takes [A, n_states, 4]
     oracle.load()
     w = max(64, n // 64)
     oracle.rollout(cfg, scn, pose, alive, hyp[:, :w], n_threads=cores,

@@ -282,7 +282,7 @@ typedef struct bmcts_rollout_result {
 typedef struct bmcts_leaf_batch {
   int32_t n_leaves;
   int32_t memory;            /* BMCTS_MEM_HOST / BMCTS_MEM_DEVICE for ALL pointers below */
-  const float* pose;         /* [A][n][4]  ([A][n_states][4] in the unique-state form) */
+  const float* pose;         /* [A][n][4]  ([n_states][A][4], STATE-major, in the unique-state form) */
   const uint32_t* alive;     /* [n] bit a = agent slot a present  ([n_states]) */
   const uint8_t* hyp_id;     /* [A][n] sampled hypothesis per agent (slot 0 ignored) */
   const uint16_t* depth;     /* [n] depth_ of the leaf state (root = 1), NULL = all 1  ([n_states]) */
@@ -292,7 +292,9 @@ typedef struct bmcts_leaf_batch {
   uint64_t first_rollout_id; /* rollout k uses Philox counter id first_rollout_id + k */
   /* Unique-state form (the waves of a search revisit few distinct states,
    * under freshly sampled hypotheses): pose / alive / depth hold n_states distinct states and
-   * rollout k starts from state state_index[k].  n_states == 0: one state per leaf. */
+   * rollout k starts from state state_index[k].  The state table is STATE-major -- record s is the
+   * A poses pose[(s*A + a)*4 ..], the way a search keeps the poses of a node -- so that a gather
+   * in any order reads whole records.  n_states == 0: one state per leaf, agent-major arrays. */
   int32_t n_states;
   int32_t pad2_;
   const uint32_t* state_index; /* [n], each < n_states; NULL when n_states == 0 */

@@ -829,7 +829,10 @@ static void* rollout_worker(void* arg) {
       unsigned depth = j->in->depth ? j->in->depth[row] : 1u;
       float pose[MAXA * 4], ra[MAXA], fp[MAXA * 4];
       uint8_t hyp[MAXA];
-      gather_f4(j->in->pose, A, ns, row, pose);
+      if (j->in->n_states > 0) /* the state table is state-major: record `row` is contiguous */
+        memcpy(pose, j->in->pose + (size_t)row * A * 4, sizeof(float) * 4 * (size_t)A);
+      else
+        gather_f4(j->in->pose, A, ns, row, pose);
       gather_u8(j->in->hyp_id, A, n, k, hyp);
       oracle_rollout(j->cfg, j->scn, pose, j->in->alive[row], hyp, depth, j->in->seed,
                      j->in->stream, j->in->first_rollout_id + (uint64_t)k, &j->out->result[k], ra,

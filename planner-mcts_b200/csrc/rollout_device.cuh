@@ -66,6 +66,13 @@ struct KernelArgs {
   int ns;
 };
 
+// start pose of agent a of rollout rid: row rid of the agent-major batch arrays, or -- unique-state
+// form -- record state_index[rid] of the STATE-MAJOR table [ns][A] (one state is 16 A contiguous
+// bytes: a gather in any order reads whole sectors)
+__device__ __forceinline__ float4 start_pose(const KernelArgs& p, int a, uint32_t rid) {
+  return p.state_index ? p.pose[(size_t)p.state_index[rid] * p.A + a] : p.pose[(size_t)a * p.n + rid];
+}
+
 __host__ __device__ inline size_t smem_align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {

@@ -141,7 +141,7 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
         const bool was_alive = (pre >> a) & 1u;
         float x, y, th, v, cs, sn, la = 0.0f;
         if (fresh) {
-          const float4 q = p.pose[(size_t)a * p.ns + (p.state_index ? p.state_index[rid] : rid)];
+          const float4 q = start_pose(p, a, rid);
           x = q.x;
           y = q.y;
           th = q.z;
@@ -154,7 +154,7 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
         } else {
           if (!was_alive) {
             if (expand) {
-              if (p.next_pose) p.next_pose[gi] = p.pose[(size_t)a * p.ns + (p.state_index ? p.state_index[rid] : rid)];
+              if (p.next_pose) p.next_pose[gi] = start_pose(p, a, rid);
               if (p.last_action) p.last_action[gi] = 0.0f;
             }
             continue;

@@ -322,7 +322,7 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         R = C0 = C1 = L = 0.0f;
         f_any = f_last = 0;
         inc0 = inc1 = inc2 = inc3 = 0;
-        const float4 q0 = p.pose[sid];  // ego pose (agent slot 0)
+        const float4 q0 = start_pose(p, 0, rid);  // ego pose (agent slot 0)
         ex = q0.x;
         ey = q0.y;
         eth = q0.z;
@@ -489,7 +489,7 @@ BM_UNROLL(BMCTS_EGO_UNROLL)
         int word = 0;
         bool on_safe_arc = false;  // centre-line point with a margin to the road boundary
         if (fresh) {
-          const float4 q = p.pose[(size_t)a * p.ns + (p.state_index ? p.state_index[rid] : rid)];
+          const float4 q = start_pose(p, a, rid);
           x = q.x;
           y = q.y;
           th = q.z;
@@ -499,7 +499,7 @@ BM_UNROLL(BMCTS_EGO_UNROLL)
           if (!was_alive) ca[L_CUR * fstride] = __int_as_float(word);
         } else if (!was_alive) {
           if (expand) {
-            if (p.next_pose) p.next_pose[gi] = p.pose[(size_t)a * p.ns + (p.state_index ? p.state_index[rid] : rid)];
+            if (p.next_pose) p.next_pose[gi] = start_pose(p, a, rid);
             if (p.reward && a > 0) p.reward[gi] = 0.0f;
             if (p.last_action && a > 0) p.last_action[gi] = 0.0f;
           }

@@ -108,12 +108,15 @@ class RolloutEngine:
                 first_rollout_id=0, want_agents=False, want_final=False, state_index=None):
         """Host-buffer rollout batch.  Returns a dict of numpy arrays.  With state_index[n],
         pose / alive / depth are tables of distinct states and rollout k starts from row
-        state_index[k] (hyp_id stays per rollout)."""
+        state_index[k] (hyp_id stays per rollout); pose is given agent-major [A, n_states, 4] like
+        every batch array and handed to the C ABI state-major, as its unique-state form asks."""
         A = self.A
         pose = _host(pose, np.float32, name="pose")
         ns = pose.shape[1]
         n = ns if state_index is None else len(state_index)
         pose = _host(pose, np.float32, (A, ns, 4), "pose")
+        if state_index is not None:
+            pose = np.ascontiguousarray(pose.transpose(1, 0, 2))   # [n_states, A, 4]
         alive = _host(alive, np.uint32, (ns,), "alive")
         hyp_id = _host(hyp_id if hyp_id is not None else np.zeros((A, n)), np.uint8, (A, n), "hyp_id")
         depth = _host(depth, np.uint16, (ns,), "depth")

@@ -101,6 +101,8 @@ def rollout(cfg, scn, pose, alive, hyp_id=None, depth=None, seed=1000, stream=0,
     ns = np.asarray(pose).shape[1]
     n = ns if state_index is None else len(state_index)
     pose = _h(pose, np.float32, (A, ns, 4), "pose")
+    if state_index is not None:   # the unique-state form takes the table state-major
+        pose = np.ascontiguousarray(pose.transpose(1, 0, 2))
     alive = _h(alive, np.uint32, (ns,), "alive")
     hyp_id = _h(hyp_id if hyp_id is not None else np.zeros((A, n)), np.uint8, (A, n), "hyp_id")
     depth = None if depth is None else _h(depth, np.uint16, (ns,), "depth")

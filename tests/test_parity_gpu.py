@@ -106,7 +106,7 @@ def test_unique_state_form_parity(name, monkeypatch):
     import torch
     dev = torch.device("cuda", 0)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    d_pose, d_alive, d_hyp = t(pose), t(alive.view(np.int32)), t(hyp)
+    d_pose, d_alive, d_hyp = t(pose.transpose(1, 0, 2)), t(alive.view(np.int32)), t(hyp)   # state-major table
     d_depth, d_index = t(depth.view(np.int16)), t(index.view(np.int32))
     d_res = torch.zeros(n, 8, dtype=torch.float32, device=dev)
     eng.rollout_raw(n, _abi.MEM_DEVICE, d_pose, d_alive, d_hyp, d_depth, d_res, n_states=ns,
