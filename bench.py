@@ -516,7 +516,7 @@ def run_ours(args):
             g = plan_benchmark(args.workload, args.horizon, per_tree, args.plan_wave, "gpu",
                                device=local_rank, tree_index=rank, trees=trees, threads=threads)
             ms = torch.tensor([g["plan_ms"]], dtype=torch.float64, device=dev)
-            torch.cuda.synchronize()
+            barrier()   # plan_ms is the MAX over ranks: waiting for the slowest rank is in it already
             t_merge = time.perf_counter()
             st = np.asarray(g.pop("root_stats"), dtype=np.float64)
             if comm is not None:
