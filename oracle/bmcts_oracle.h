@@ -16,7 +16,11 @@
  * time span, likelihood histogram) are restated line by line and pinned by the
  * reference's own known-answer tests (tests/test_oracle_kat.py); the BARK
  * internals (IDM, single-track, geometry, safe distance) restate the published
- * algorithms as fixed in DESIGN.md "Normative step spec".
+ * algorithms as fixed in DESIGN.md "Normative step spec".  Those are checked
+ * against sources outside this file (tests/test_independent_spec.py): a float64
+ * numpy restatement with different algorithms for every predicate, a brute-force
+ * simulation of the safe-distance rule, Treiber's IDM equilibrium, Random123's
+ * Philox vectors -- but not against BARK's own numbers, which do not exist here.
  */
 #ifndef BMCTS_ORACLE_H_
 #define BMCTS_ORACLE_H_
