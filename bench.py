@@ -422,8 +422,10 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
-OTHER_WORKLOADS = [("c1_highway_mdp", 1 << 20), ("c2_merge_sbg", 1 << 20), ("c3_merge_risk", 1 << 19),
-                   ("c4_coop", 1 << 19), ("c5_rsbg", 1 << 19)]
+# rollouts per step of the short runs: enough rollouts per lane (>= 35) that the tail of the
+# persistent grid is below 2 %
+OTHER_WORKLOADS = [("c1_highway_mdp", 1 << 22), ("c2_merge_sbg", 1 << 22), ("c3_merge_risk", 1 << 21),
+                   ("c4_coop", 1 << 21), ("c5_rsbg", 1 << 21)]
 
 
 def run_ours(args):

@@ -1111,7 +1111,12 @@ int bmcts_likelihood_batch(bmcts_engine* e, const bmcts_likelihood_in* in, float
     a.prob = (float*)e->b_prob.ptr;
   }
   CU(cudaEventRecord(e->ev_start, e->stream));
-  dim3 grid((unsigned)W, (unsigned)H, (unsigned)A);
+  // hypotheses per block: as many as leave at least ~6 blocks per SM (the belief update of one
+  // Plan() is a single world: few blocks, each must stay short)
+  int hb = bmcts::kLikelihoodHypsPerBlock;
+  while (hb > 1 && (long)W * A * ((H + hb - 1) / hb) < 6L * e->sm_count) hb /= 2;
+  a.hyps_per_block = hb;
+  dim3 grid((unsigned)W, (unsigned)((H + hb - 1) / hb), (unsigned)A);
   bmcts::likelihood_kernel<<<grid, 256, 0, e->stream>>>(a);
   CU(cudaGetLastError());
   e->launches++;

@@ -367,6 +367,8 @@ __device__ __forceinline__ float idm_acc(const IdmLimits& h, const IdmParams& p,
 // K4: BehaviorHypothesisIDM::GetProbability (hypothesis/idm/hypothesis_idm.cpp:40-126)
 // one block per (agent a, hypothesis h, world w); threads stride over the samples and
 // count those that fall into the bucket of the observed action.
+constexpr int kLikelihoodHypsPerBlock = 8;  // at most; LikelihoodArgs::hyps_per_block is what a launch uses
+
 struct LikelihoodArgs {
   const float4* pose;     // [A][n_worlds]
   const uint32_t* alive;  // [n_worlds]
@@ -377,20 +379,85 @@ struct LikelihoodArgs {
   int n_samples, n_buckets;
   float lower, upper;
   uint32_t key0, key1;
+  int hyps_per_block;  // 1 .. kLikelihoodHypsPerBlock (fewer when the grid would not fill the GPU)
 };
+
+// bucket of an acceleration exactly as the reference computes it
+// (hypothesis_idm.cpp:92-95,117-120: floor((a - lower) / bucket_size), clamped to the histogram)
+__device__ __forceinline__ int likelihood_bucket(float acc, float lower, float bucket_size, int nb) {
+  int b = (int)floorf(bm_div(acc - lower, bucket_size));
+  if (b > nb - 1) b = nb - 1;
+  if (b < 0) b = 0;
+  return b;
+}
+
+// floats as integers in their numeric order (and back): for a monotone function of a float the
+// set of arguments that map to one value is an interval of consecutive such integers
+__device__ __forceinline__ int ordered_of(float x) {
+  const int i = __float_as_int(x);
+  return i >= 0 ? i : (int)(0x80000000u - (unsigned)i);
+}
+__device__ __forceinline__ float float_of(int o) {
+  return __int_as_float(o >= 0 ? o : (int)(0x80000000u - (unsigned)o));
+}
+
+// [lo, hi]: the accelerations inside [lower, upper] whose bucket is `target` -- exactly the
+// samples the histogram of the reference counts in that bucket.  likelihood_bucket is monotone in
+// acc (subtraction, division by a positive size, floor and the clamps all are), so two binary
+// searches over the ordered floats find the interval; the per-sample test is then two
+// comparisons instead of a division.  Empty interval: lo > hi.
+__device__ void likelihood_interval(float lower, float upper, float bucket_size, int nb, int target,
+                                    float* lo_out, float* hi_out) {
+  const int o_lo = ordered_of(lower), o_hi = ordered_of(upper);
+  // The boundaries sit within a few ulps of lower + k * bucket_size: bracket each of them with a
+  // window of +-64 ordered floats around that estimate, check the bracket, and search inside it
+  // (6 probes instead of 32); a bracket that does not hold falls back to the whole range.
+  auto search = [&](int want_above, int k) {  // first x in [lower, upper] with bucket(x) > want_above
+    if (want_above >= nb - 1) return o_hi + 1;  // the last bucket has no upper neighbour
+    int a = o_lo, b = o_hi + 1;               // answer in [a, b]
+    const int est = ordered_of(bm_fma((float)k, bucket_size, lower));
+    const int wa = est - 64 > o_lo ? est - 64 : o_lo, wb = est + 64 < o_hi ? est + 64 : o_hi;
+    if (wa <= wb) {
+      const bool below_ok = wa == o_lo || likelihood_bucket(float_of(wa - 1), lower, bucket_size, nb) <= want_above;
+      const bool above_ok = likelihood_bucket(float_of(wb), lower, bucket_size, nb) > want_above;
+      if (below_ok && above_ok) {
+        a = wa;
+        b = wb;
+      }
+    }
+    while (a < b) {
+      const int m = a + (int)(((long long)b - a) / 2);
+      if (likelihood_bucket(float_of(m), lower, bucket_size, nb) > want_above) b = m; else a = m + 1;
+    }
+    return a;
+  };
+  const int first = search(target - 1, target);  // first x with bucket(x) >= target
+  int a = search(target, target + 1);            // first x with bucket(x) > target
+  const int last = a - 1;
+  if (first > o_hi || last < first) {
+    *lo_out = 1.0f;
+    *hi_out = 0.0f;
+  } else {
+    *lo_out = float_of(first);
+    *hi_out = float_of(last);
+  }
+}
 
 __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p) {
   __shared__ int s_cur;
   __shared__ float s_gap, s_vl, s_vown;
-  __shared__ int s_has_leader, s_skip, s_bucket;
-  __shared__ unsigned s_count;
+  __shared__ int s_has_leader, s_skip;
+  __shared__ float s_acc_lo, s_acc_hi;  // accelerations that fall into the observed action's bucket
+  __shared__ unsigned s_count[kLikelihoodHypsPerBlock];
   const bmcts_scenario& scn = *p.scn;  // read through L1/L2 (few KB, hot)
   const int w = blockIdx.x;
-  const int h = blockIdx.y;
+  // a block serves kLikelihoodHypsPerBlock hypotheses of one (world, agent): corridor, leader
+  // and the bucket interval do not depend on the hypothesis and are found once
+  const int h0 = blockIdx.y * p.hyps_per_block;
+  const int h1 = h0 + p.hyps_per_block < p.H ? h0 + p.hyps_per_block : p.H;
   const int a = blockIdx.z;
   const int t = threadIdx.x;
   const uint32_t am = p.alive[w];
-  const size_t out_idx = ((size_t)a * p.H + h) * p.n_worlds + w;
   // Prologue on warp 0 (one lane per corridor, then one lane per candidate leader, reduced with
   // shuffles); the other warps wait at two barriers instead of behind a serial thread.
   if (t < 32) {
@@ -411,8 +478,8 @@ __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p)
       m = take ? om : m;
       bc = take ? oc : bc;
     }
+    if (t < kLikelihoodHypsPerBlock) s_count[t] = 0;
     if (t == 0) {
-      s_count = 0;
       s_cur = m < kBig ? bc : 0;  // no corridor in range: corridor 0, as the serial scan
       s_vown = q.w;
       int skip = !((am >> a) & 1u);
@@ -420,15 +487,19 @@ __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p)
       if (act > p.upper || act < p.lower) skip = 1;
       s_skip = skip;
       const float bucket_size = bm_div(p.upper - p.lower, (float)p.n_buckets);
-      int b = (int)floorf(bm_div(act - p.lower, bucket_size));
-      if (b > p.n_buckets - 1) b = p.n_buckets - 1;
-      if (b < 0) b = 0;
-      s_bucket = b;
+      float lo = 1.0f, hi = 0.0f;
+      if (!skip) {
+        const int target = likelihood_bucket(act, p.lower, bucket_size, p.n_buckets);
+        likelihood_interval(p.lower, p.upper, bucket_size, p.n_buckets, target, &lo, &hi);
+      }
+      s_acc_lo = lo;
+      s_acc_hi = hi;
     }
   }
   __syncthreads();
   if (s_skip) {
-    if (t == 0) p.prob[out_idx] = 0.0f;
+    for (int h = h0 + t; h < h1; h += blockDim.x)
+      p.prob[((size_t)a * p.H + h) * p.n_worlds + w] = 0.0f;
     return;
   }
   const int cur = s_cur;
@@ -469,45 +540,46 @@ __global__ void __launch_bounds__(256) likelihood_kernel(const LikelihoodArgs p)
     }
   }
   __syncthreads();
-  const bmcts_hypothesis hy = scn.hypotheses[h];
-  const IdmLimits hl = idm_limits(hy);
   const bool has_leader = s_has_leader != 0;
   const float gap = s_gap, v_l = s_vl, v_own = s_vown;
-  const float bucket_size = bm_div(p.upper - p.lower, (float)p.n_buckets);
-  const int target = s_bucket;
-  // Exact skips, as in the rollout kernels: a Philox block none of whose words reaches a ranged
-  // parameter is not drawn (u * 0 + lo = lo whatever u), and the reciprocals of parameters that
-  // are FixedValues are the same for every sample.
-  const bool need0 = hy.hi[0] != hy.lo[0] || hy.hi[1] != hy.lo[1] || hy.hi[2] != hy.lo[2] ||
-                     hy.hi[3] != hy.lo[3];
-  const bool need1 = hy.hi[4] != hy.lo[4];
-  const bool fixed_v0 = hy.hi[3] == hy.lo[3];
-  const bool fixed_ab = hy.hi[2] == hy.lo[2] && hy.hi[4] == hy.lo[4];
-  const float inv_v0_fixed = bm_div(1.0f, bm_max(hy.lo[3], 1.0e-3f));
-  const float inv_2sab_fixed = bm_div(1.0f, 2.0f * bm_sqrt(bm_max(hy.lo[2] * hy.lo[4], 1.0e-6f)));
-  unsigned cnt = 0;
-  for (int smp = t; smp < p.n_samples; smp += blockDim.x) {
-    uint64_t id = (uint64_t)(uint32_t)smp | ((uint64_t)(uint32_t)w << 32);
-    uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-    if (need0) r0 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h);
-    if (need1)
-      r1 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h + 1u);
-    IdmParams ip = sample_idm_params(hy, r0, r1);
-    const float inv_v0 = fixed_v0 ? inv_v0_fixed : bm_div(1.0f, bm_max(ip.v0, 1.0e-3f));
-    const float inv_2sab =
-        fixed_ab ? inv_2sab_fixed
-                 : bm_div(1.0f, 2.0f * bm_sqrt(bm_max(ip.a_max * ip.b, 1.0e-6f)));
-    float acc = idm_acc(hl, ip, inv_v0, inv_2sab, has_leader, v_own, v_l, gap);
-    if (acc < p.lower || acc > p.upper) continue;
-    int b = (int)floorf(bm_div(acc - p.lower, bucket_size));
-    if (b > p.n_buckets - 1) b = p.n_buckets - 1;
-    if (b < 0) b = 0;
-    cnt += (b == target);
+  const float acc_lo = s_acc_lo, acc_hi = s_acc_hi;
+#pragma unroll 1
+  for (int h = h0; h < h1; ++h) {
+    const bmcts_hypothesis hy = scn.hypotheses[h];
+    const IdmLimits hl = idm_limits(hy);
+    // Exact skips, as in the rollout kernels: a Philox block none of whose words reaches a ranged
+    // parameter is not drawn (u * 0 + lo = lo whatever u), and the reciprocals of parameters that
+    // are FixedValues are the same for every sample.
+    const bool need0 = hy.hi[0] != hy.lo[0] || hy.hi[1] != hy.lo[1] || hy.hi[2] != hy.lo[2] ||
+                       hy.hi[3] != hy.lo[3];
+    const bool need1 = hy.hi[4] != hy.lo[4];
+    const bool fixed_v0 = hy.hi[3] == hy.lo[3];
+    const bool fixed_ab = hy.hi[2] == hy.lo[2] && hy.hi[4] == hy.lo[4];
+    const float inv_v0_fixed = bm_div(1.0f, bm_max(hy.lo[3], 1.0e-3f));
+    const float inv_2sab_fixed = bm_div(1.0f, 2.0f * bm_sqrt(bm_max(hy.lo[2] * hy.lo[4], 1.0e-6f)));
+    unsigned cnt = 0;
+#pragma unroll 1
+    for (int smp = t; smp < p.n_samples; smp += blockDim.x) {
+      uint64_t id = (uint64_t)(uint32_t)smp | ((uint64_t)(uint32_t)w << 32);
+      uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+      if (need0) r0 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h);
+      if (need1)
+        r1 = draw(p.key0, p.key1, id, (uint32_t)a, BMCTS_RNG_LIKELIHOOD, 2u * (uint32_t)h + 1u);
+      IdmParams ip = sample_idm_params(hy, r0, r1);
+      const float inv_v0 = fixed_v0 ? inv_v0_fixed : bm_div(1.0f, bm_max(ip.v0, 1.0e-3f));
+      const float inv_2sab =
+          fixed_ab ? inv_2sab_fixed
+                   : bm_div(1.0f, 2.0f * bm_sqrt(bm_max(ip.a_max * ip.b, 1.0e-6f)));
+      const float acc = idm_acc(hl, ip, inv_v0, inv_2sab, has_leader, v_own, v_l, gap);
+      // the observed action's bucket, as an interval of accelerations (likelihood_interval)
+      cnt += (acc >= acc_lo && acc <= acc_hi);
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((t & 31) == 0 && cnt) atomicAdd(&s_count[h - h0], cnt);
   }
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  if ((t & 31) == 0 && cnt) atomicAdd(&s_count, cnt);
   __syncthreads();
-  if (t == 0) p.prob[out_idx] = bm_div((float)s_count, (float)p.n_samples);
+  for (int h = h0 + t; h < h1; h += blockDim.x)
+    p.prob[((size_t)a * p.H + h) * p.n_worlds + w] = bm_div((float)s_count[h - h0], (float)p.n_samples);
 }
 
 // elementary-function probe (bmcts_math_probe): out[i] = f(a[i], b[i])
