@@ -375,7 +375,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args, meta, n, None),
+        "config": workload_config(args, meta),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -390,17 +390,19 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, meta, n, extra):
-    """`config` of the JSON line: identical keys on both arms (the reference arm's step is a
-    bounded sample, its size is in cpu_baseline.sample)"""
-    c = {"workload": args.workload, "agents": meta["A"], "hypotheses": meta["H"],
-         "horizon": args.horizon, "ego_substeps": 10,
-         "leaf_form": ("unique-state table: rollouts / %d distinct leaf states, each under %d sampled "
-                       "hypothesis assignments" % (args.share, args.share)) if args.share > 1
-         else "one state per rollout"}
-    if extra:
-        c.update(extra)
-    return c
+def workload_config(args, meta):
+    """`config` of the JSON line: the SAME on both arms for the same command line (the reference
+    arm's step is a bounded sample of this workload, its size is in cpu_baseline.sample; what a
+    run measured on top -- rollout lengths, rates, the timed region -- goes to `run`)"""
+    in_bytes = input_bytes_per_step(meta["A"], args.rollouts, args.share)
+    return {"workload": args.workload, "agents": meta["A"], "hypotheses": meta["H"],
+            "horizon": args.horizon, "ego_substeps": 10,
+            "leaf_form": ("unique-state table: rollouts / %d distinct leaf states, each under %d sampled "
+                          "hypothesis assignments" % (args.share, args.share)) if args.share > 1
+            else "one state per rollout",
+            "rollouts_per_step_per_gpu": args.rollouts,
+            "l2": "inputs larger than L2 (%.0f MB of leaf states, hypothesis ids and indices per "
+                  "step)" % (in_bytes / 1e6)}
 
 
 def bind_to_gpu_numa_node(index):
@@ -574,12 +576,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, meta, n, {
-            "rollouts_per_step_per_gpu": n, "mean_rollout_steps": m["mean_rollout_steps"],
-            "l2": "inputs larger than L2 (%.0f MB of leaf states, hypothesis ids and indices per "
-                  "step)" % (in_bytes / 1e6),
-            "rollouts_per_s": n * world / (elapsed_ms / args.steps * 1e-3),
-            "timed_region_s": elapsed_ms * 1e-3, "cpus_bound_per_rank": numa}),
+        "config": workload_config(args, meta),
+        "run": {"mean_rollout_steps": m["mean_rollout_steps"],
+                "rollouts_per_s": n * world / (elapsed_ms / args.steps * 1e-3),
+                "timed_region_s": elapsed_ms * 1e-3, "cpus_bound_per_rank": numa},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": int(n * 32)},

@@ -528,6 +528,7 @@ class Mcts {
   // the interleaving of the shared random generator differs.  A wave of one iteration is the
   // sequential search.
   void SelectWave(int w) {
+    root_w_ = 0;  // set when the root level goes through the per-agent arrays
     for (int i = 0; i < w; ++i) {
       Selection& sel = sels_[i];
       sel.path.clear();
@@ -553,9 +554,40 @@ class Mcts {
                                                  : root_->ego_cc->ChooseNextAction(lambdas_, gen_);
       sels_[i].path.push_back(st);
     }
-    for (int s = 1; s < A_; ++s) {
-      if (!((root_->alive >> s) & 1u)) continue;
-      for (int i = 0; i < w; ++i) ChooseOther(root_, s, sels_[i], sels_[i].path[0]);
+    if (other_mode_ == OtherMode::kHypothesis) {
+      // the wave's root-level choices as arrays per agent ([slot][iteration]): the inner loop
+      // streams through them instead of touching a Selection, its path and its hypothesis
+      // vector (three cache lines of three different heap blocks) per (agent, iteration)
+      root_w_ = w;
+      root_hyp_.resize((size_t)A_ * w);
+      root_idx_.assign((size_t)A_ * w, -1);
+      root_new_.assign((size_t)A_ * w, 0);
+      for (int i = 0; i < w; ++i)
+        for (int s = 1; s < A_; ++s) root_hyp_[(size_t)s * w + i] = sels_[i].hyp[s];
+      for (int s = 1; s < A_; ++s) {
+        if (!((root_->alive >> s) & 1u)) continue;
+        HypothesisStatistic& hs = root_->other_hyp[s];
+        const uint8_t* hyp = &root_hyp_[(size_t)s * w];
+        int* idx = &root_idx_[(size_t)s * w];
+        uint8_t* isnew = &root_new_[(size_t)s * w];
+        for (int i = 0; i < w; ++i) {
+          bool n = false;
+          idx[i] = hs.ChooseNextAction(hyp[i], gen_, next_draw_id_++, &n);
+          isnew[i] = n;
+        }
+      }
+      for (int i = 0; i < w; ++i) {
+        PathStep& st = sels_[i].path[0];
+        for (int s = 1; s < A_; ++s) {
+          st.other_idx[s] = root_idx_[(size_t)s * w + i];
+          st.other_new[s] = root_new_[(size_t)s * w + i];
+        }
+      }
+    } else {
+      for (int s = 1; s < A_; ++s) {
+        if (!((root_->alive >> s) & 1u)) continue;
+        for (int i = 0; i < w; ++i) ChooseOther(root_, s, sels_[i], sels_[i].path[0]);
+      }
     }
     for (int i = 0; i < w; ++i) {
       Selection& sel = sels_[i];
@@ -653,18 +685,32 @@ class Mcts {
     // resolved, then the iterations are backed up in order with the root's other-agent updates
     // deferred, then those are applied per agent in iteration order.  Each statistic sees the
     // calls of the sequential order; nothing is selected in between.
-    const bool by_agent = w > 1 && other_mode_ == OtherMode::kHypothesis && root_->stats_ready;
+    const bool by_agent = w > 1 && other_mode_ == OtherMode::kHypothesis && root_->stats_ready &&
+                          root_w_ == w;
     if (by_agent) {
-      for (int s = 1; s < A_; ++s)
+      root_expand_.resize(w);
+      for (int i = 0; i < w; ++i)
+        root_expand_[i] = sels[i].needs_engine && !sels[i].rollout_only && sels[i].path.size() == 1;
+      for (int s = 1; s < A_; ++s) {
+        HypothesisStatistic& hs = root_->other_hyp[s];
+        const uint8_t* hyp = &root_hyp_[(size_t)s * w];
+        int* idx = &root_idx_[(size_t)s * w];
+        uint8_t* isnew = &root_new_[(size_t)s * w];
+        const float* last = &wave_.last_action[wave_.n > 0 ? wave_.at(s, 0) : 0];
         for (int i = 0; i < w; ++i) {
-          Selection& sel = sels[i];
-          if (!sel.needs_engine || sel.rollout_only || sel.path.size() != 1) continue;
-          PathStep& st = sel.path[0];
-          if (st.other_idx[s] < 0 || !st.other_new[s]) continue;
-          const ActionKey key = KeyOfAcceleration(wave_.last_action[wave_.at(s, slot[i])]);
-          st.other_idx[s] = root_->other_hyp[s].Resolve(sel.hyp[s], st.other_idx[s], key);
-          st.other_new[s] = 0;
+          if (!root_expand_[i] || idx[i] < 0 || !isnew[i]) continue;
+          idx[i] = hs.Resolve(hyp[i], idx[i], KeyOfAcceleration(last[slot[i]]));
+          isnew[i] = 0;
         }
+      }
+      for (int i = 0; i < w; ++i) {
+        if (!root_expand_[i]) continue;
+        PathStep& st = sels[i].path[0];
+        for (int s = 1; s < A_; ++s) {
+          st.other_idx[s] = root_idx_[(size_t)s * w + i];
+          st.other_new[s] = root_new_[(size_t)s * w + i];
+        }
+      }
       defer_cost_.assign(w, 0.0);
       defer_latest_.assign(w, 0.0);
     }
@@ -674,13 +720,13 @@ class Mcts {
       if (ego_mode_ == EgoMode::kCostConstrained) UpdateLambdas();
     }
     if (by_agent) {
-      for (int s = 1; s < A_; ++s)
-        for (int i = 0; i < w; ++i) {
-          const Selection& sel = sels[i];
-          if (sel.path.empty() || sel.path[0].other_idx[s] < 0) continue;
-          root_->other_hyp[s].BackupEntry(sel.hyp[s], sel.path[0].other_idx[s], defer_cost_[i],
-                                          defer_latest_[i]);
-        }
+      for (int s = 1; s < A_; ++s) {
+        HypothesisStatistic& hs = root_->other_hyp[s];
+        const uint8_t* hyp = &root_hyp_[(size_t)s * w];
+        const int* idx = &root_idx_[(size_t)s * w];
+        for (int i = 0; i < w; ++i)
+          if (idx[i] >= 0) hs.BackupEntry(hyp[i], idx[i], defer_cost_[i], defer_latest_[i]);
+      }
     }
     t_backup_ += ms(t3, clock::now());
     EvaluatePriors();
@@ -904,6 +950,10 @@ class Mcts {
   std::vector<Selection> sels_;
   std::vector<int> slot_;
   std::vector<double> defer_cost_, defer_latest_;  // root-level back-ups deferred within a wave
+  // root-level choices of the wave in flight, [agent slot][iteration] (SelectWave / EndWave)
+  std::vector<uint8_t> root_hyp_, root_new_, root_expand_;
+  std::vector<int> root_idx_;
+  int root_w_ = 0;
   HypothesisSampler sampler_;
   std::chrono::steady_clock::time_point t_start_;
   long wave_size_ = 1;
