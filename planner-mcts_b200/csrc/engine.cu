@@ -139,13 +139,20 @@ int upload_dt_table(bmcts_engine* e) {
 // the batch fills the GPU, more when it does not (an MCTS wave of a few hundred leaves) or
 // when the per-rollout state of a large scenario would leave too few warps resident.
 // W warps per block share one staged scenario; the grid is persistent (blocks/SM x SMs).
-template <int T, bool COOP>
+// AHEAD (hypothesis / risk kernel only): the "ego ahead" variant for batches too small to fill
+// the GPU -- one warp of rollouts plus the ego warp per block (rollout_lane_kernel.cuh).
+template <int T, bool COOP, bool AHEAD>
 int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cudaStream_t stream,
                   unsigned int* counter) {
-  auto kern = COOP ? bmcts::rollout_lane_coop_kernel<T> : bmcts::rollout_lane_kernel<T>;
+  static_assert(!(COOP && AHEAD), "the cooperative kernel has no ego-ahead variant");
+  auto kern = COOP ? bmcts::rollout_lane_coop_kernel<T> : bmcts::rollout_lane_kernel<T, AHEAD>;
   auto layout = [&](int W) {
-    return COOP ? bmcts::lane_coop_layout(a.A, a.C, T, W) : bmcts::lane_layout(a.A, a.C, a.H, T, W);
+    bmcts::LaneLayout l =
+        COOP ? bmcts::lane_coop_layout(a.A, a.C, T, W) : bmcts::lane_layout(a.A, a.C, a.H, T, W);
+    if (AHEAD) l.total = bmcts::smem_align16(l.total) + sizeof(bmcts::EgoMail);
+    return l;
   };
+  if (AHEAD) force_W = 1;
   const int NC = 32 / T;
   const long need_warps = ((long)a.n + NC - 1) / NC;
   // the kernel may use all the shared memory the SM offers.  cudaFuncSetAttribute applies to the
@@ -168,7 +175,8 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cuda
     return cuda_fail(e, attr_err[e->device], "cudaFuncSetAttribute");
   // geometry per (variant, scenario size, batch class): occupancy queries are cached
   // (COOP has its own top bit: T = 16 is 1 << 60 in the T field)
-  const unsigned long long key = ((unsigned long long)COOP << 63) | ((unsigned long long)T << 56) |
+  const unsigned long long key = ((unsigned long long)COOP << 63) |
+                                 ((unsigned long long)AHEAD << 62) | ((unsigned long long)T << 56) |
                                  ((unsigned long long)a.A << 48) | ((unsigned long long)a.C << 44) |
                                  ((unsigned long long)a.H << 36) | ((unsigned long long)force_W << 28) |
                                  (unsigned long long)std::min<long>(need_warps, (1L << 28) - 1);
@@ -183,7 +191,8 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cuda
       const bmcts::LaneLayout lay = layout(W);
       if ((int)lay.total > e->max_smem_optin) continue;
       int blocks = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, W * 32, lay.total));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, (W + (AHEAD ? 1 : 0)) * 32,
+                                                       lay.total));
       if (blocks < 1) continue;
       // a small batch is spread over the SMs first: never more warps than it can fill
       long resident = (long)blocks * W * e->sm_count;
@@ -211,14 +220,15 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cuda
     if (cap > 0 && grid > cap) grid = cap;
   }
   CU(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
-  kern<<<(unsigned)grid, g.W * 32, g.smem, stream>>>(a, counter);
+  kern<<<(unsigned)grid, (g.W + (AHEAD ? 1 : 0)) * 32, g.smem, stream>>>(a, counter);
   CU(cudaGetLastError());
   e->launches++;
   e->lane_T = T;
   e->lane_W = g.W;
   if (std::getenv("BMCTS_DEBUG"))
-    std::fprintf(stderr, "[bmcts] lane kernel coop=%d T=%d W=%d blocks/SM=%d grid=%ld smem=%zu n=%d\n",
-                 (int)COOP, T, g.W, g.blocks, grid, g.smem, a.n);
+    std::fprintf(stderr,
+                 "[bmcts] lane kernel coop=%d ahead=%d T=%d W=%d blocks/SM=%d grid=%ld smem=%zu n=%d\n",
+                 (int)COOP, (int)AHEAD, T, g.W, g.blocks, grid, g.smem, a.n);
   return BMCTS_OK;
 }
 
@@ -246,12 +256,27 @@ int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream
     for (int t = 2; t <= 16; t *= 2)
       if (T < t && (long)a.n * t <= lanes_resident && a.A > t / 2) T = t;
   }
+  // the ego-ahead variant when the batch leaves most of the GPU idle (latency bound: an MCTS
+  // wave); BMCTS_LANE_AHEAD = 0 / 1 forces the choice (tests)
+  bool ahead = !COOP && (long)a.n * T * 4 <= (long)e->sm_count * 32 * 16;
+  if (const char* s = std::getenv("BMCTS_LANE_AHEAD")) ahead = !COOP && std::atoi(s) != 0;
+  if constexpr (!COOP) {
+    if (ahead) {
+      switch (T) {
+        case 16: return launch_lane_T<16, false, true>(e, a, W, stream, counter);
+        case 8: return launch_lane_T<8, false, true>(e, a, W, stream, counter);
+        case 4: return launch_lane_T<4, false, true>(e, a, W, stream, counter);
+        case 2: return launch_lane_T<2, false, true>(e, a, W, stream, counter);
+        default: return launch_lane_T<1, false, true>(e, a, W, stream, counter);
+      }
+    }
+  }
   switch (T) {
-    case 16: return launch_lane_T<16, COOP>(e, a, W, stream, counter);
-    case 8: return launch_lane_T<8, COOP>(e, a, W, stream, counter);
-    case 4: return launch_lane_T<4, COOP>(e, a, W, stream, counter);
-    case 2: return launch_lane_T<2, COOP>(e, a, W, stream, counter);
-    default: return launch_lane_T<1, COOP>(e, a, W, stream, counter);
+    case 16: return launch_lane_T<16, COOP, false>(e, a, W, stream, counter);
+    case 8: return launch_lane_T<8, COOP, false>(e, a, W, stream, counter);
+    case 4: return launch_lane_T<4, COOP, false>(e, a, W, stream, counter);
+    case 2: return launch_lane_T<2, COOP, false>(e, a, W, stream, counter);
+    default: return launch_lane_T<1, COOP, false>(e, a, W, stream, counter);
   }
 }
 

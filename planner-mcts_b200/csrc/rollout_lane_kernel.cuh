@@ -179,6 +179,85 @@ BM_UNROLL(BMCTS_IDM_UNROLL)
   return trav;
 }
 
+// The ego's macro action (BehaviorMPMacroActions primitive on the single-track model, spec
+// item 3): advances the pose (x, y, th, v) and the sine / cosine of the heading over Dt from
+// the corridor `cur` the ego is on; returns the clamped acceleration.
+__device__ __forceinline__ float ego_macro_step(const bmcts_scenario& scn,
+                                                const bmcts_ego_action* acts,
+                                                const bmcts_config& cfg, int action, int cur,
+                                                float Dt, float& ex, float& ey, float& eth,
+                                                float& ev, float& esn, float& ecs) {
+  const bmcts_ego_action act = acts[action];
+  const float acc = bm_clamp(act.acceleration, cfg.lon_acc_min, cfg.lon_acc_max);
+  int tgt = cur;
+  if (act.type == BMCTS_ACT_CHANGE_LEFT && scn.corridors[tgt].left >= 0)
+    tgt = scn.corridors[tgt].left;
+  else if (act.type == BMCTS_ACT_CHANGE_RIGHT && scn.corridors[tgt].right >= 0)
+    tgt = scn.corridors[tgt].right;
+  const bmcts_corridor& corr = scn.corridors[tgt];
+  const float wb = cfg.wheel_base, kct = cfg.crosstrack_gain, dmax = cfg.delta_max;
+  const float vmax = cfg.ego_max_velocity;
+  const float inv_wb = bm_div(1.0f, wb);
+  const int nsub_e = ego_substeps(cfg, Dt);
+  const float dt_e = bm_div(Dt, (float)nsub_e);
+  const bool limit = cfg.limit_steering_rate != 0;
+  const float lat_lo = cfg.lat_acc_min, lat_hi = cfg.lat_acc_max;
+  float nx = ex, ny = ey, nth = eth, nv = ev;
+  float sn = esn, cs = ecs;  // sin / cos of the current heading (published values)
+BM_UNROLL(BMCTS_EGO_UNROLL)
+  for (int q = 0; q < nsub_e; ++q) {
+    const float fx = bm_fma(wb, cs, nx);
+    const float fy = bm_fma(wb, sn, ny);
+    const Proj pr = project(corr, fx, fy);
+    const float th_err = bm_norm_angle(corr.angle[pr.seg] - nth);
+    float delta = th_err + bm_atan2(-(kct * pr.d), nv);
+    delta = bm_clamp(delta, -dmax, dmax);
+    float tn = bm_tan_small(delta);
+    if (limit) {  // lateral acceleration v^2 tan(delta) / L inside [LatAccMin, LatAccMax]
+      const float r = bm_div(wb, bm_max(nv * nv, 1.0e-6f));
+      tn = bm_clamp(tn, lat_lo * r, lat_hi * r);
+    }
+    const float dv = dt_e * nv;
+    nx = bm_fma(dv, cs, nx);
+    ny = bm_fma(dv, sn, ny);
+    nth = bm_fma(dv, tn * inv_wb, nth);
+    nv = bm_clamp(bm_fma(dt_e, acc, nv), 0.0f, vmax);
+    // heading for the next sub-step; after the last one: of the wrapped final heading
+    if (q + 1 == nsub_e) nth = bm_norm_angle(nth);
+    bm_sincos(nth, &sn, &cs);
+  }
+  ex = nx;
+  ey = ny;
+  eth = nth;
+  ev = nv;
+  esn = sn;
+  ecs = cs;
+  return acc;
+}
+
+// ---- "ego ahead" variant (AHEAD = true), for batches too small to fill the GPU ----------
+// The ego's motion does not depend on the other agents (its action is drawn from the
+// counter-based generator, its primitive tracks a lane), so the serial chain of its macro
+// action -- half of a step's latency when a rollout has a lane per agent -- is taken off the
+// step: the block gets a second warp whose lane c computes the ego of column c ONE PASS AHEAD
+// of the warp that carries the rollouts and hands it over through shared memory.  The two warps
+// meet at one named barrier per pass (no spinning).  Same arithmetic in the same order: results
+// are bit-identical to the plain variant.
+struct EgoAcq {      // the rollout a column works on, posted by the rollout warp every pass
+  uint32_t seq;      // changes with every acquisition
+  uint32_t rid;
+  int depth;
+  uint32_t flags;    // bit 0: expansion step first, bit 1: ego alive in the leaf state
+};
+struct EgoMail {     // everything is double-buffered by pass parity: the writer of pass i + 1
+                     // never touches what the other warp reads in pass i
+  uint32_t done[4];  // [parity]: all columns of the rollout warp are out of work
+  EgoAcq acq[2][32];
+  float slot[2][32][8];  // [parity][column]: x, y, th, v, cos, sin after the pass's ego step
+};
+
+__device__ __forceinline__ void ahead_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
 #ifndef BMCTS_LANE_MAX_THREADS
 #define BMCTS_LANE_MAX_THREADS 384
 #endif
@@ -186,13 +265,14 @@ BM_UNROLL(BMCTS_IDM_UNROLL)
 #define BMCTS_LANE_MIN_BLOCKS 2
 #endif
 
-template <int T>
-__global__ void __launch_bounds__(BMCTS_LANE_MAX_THREADS, BMCTS_LANE_MIN_BLOCKS)
+template <int T, bool AHEAD>
+__global__ void __launch_bounds__(AHEAD ? 64 : BMCTS_LANE_MAX_THREADS, AHEAD ? 1 : BMCTS_LANE_MIN_BLOCKS)
 rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = 32 / T;  // rollouts (columns) per warp
   const int A = p.A, C = p.C;
-  const int warps = blockDim.x >> 5;
+  // AHEAD: one warp of rollouts + the ego warp (launched with 64 threads)
+  const int warps = AHEAD ? 1 : blockDim.x >> 5;
   const LaneLayout lay = lane_layout(A, C, p.H, T, warps);
 
   // ---- stage scenario prefix + used hypotheses, macro actions, config, segment sin/cos,
@@ -260,6 +340,73 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
   const float* arc_hi = arc_lo + BMCTS_MAX_CORRIDORS * BMCTS_MAX_CORRIDOR_PTS;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  EgoMail* mail = reinterpret_cast<EgoMail*>(smem_raw + smem_align16(lay.total));
+  if (AHEAD && warp == 1) {
+    // ---------------------------------------------------------------- the ego warp
+    uint32_t seq = 0, rid = 0;
+    int n = 0, depth = 1;
+    bool expand = false, alive = false;
+    float ex = 0.0f, ey = 0.0f, eth = 0.0f, ev = 0.0f, ecs = 1.0f, esn = 0.0f;
+    for (uint32_t it = 0;; ++it) {
+      ahead_barrier();  // acquisitions of this pass posted, slots of this pass complete
+      if (mail->done[it & 1u]) break;
+      if (lane < NC) {
+        const EgoAcq q = mail->acq[it & 1u][lane];
+        if (q.seq != seq) {
+          seq = q.seq;
+          rid = q.rid;
+          depth = q.depth;
+          expand = (q.flags & 1u) != 0;
+          alive = (q.flags & 2u) != 0;
+          n = 0;
+          const float4 q0 = start_pose(p, 0, rid);
+          ex = q0.x;
+          ey = q0.y;
+          eth = q0.z;
+          ev = q0.w;
+          bm_sincos(eth, &esn, &ecs);
+        }
+        if (alive) {
+          // the corridor the publish phase finds for this pose: arg min |d| over the corridors
+          // the pose projects into (first one on ties, corridor 0 when there is none)
+          float best = kBig;
+          int cur = 0;
+#pragma unroll 1
+          for (int c = 0; c < C; ++c) {
+            const Proj pr = project(scn.corridors[c], ex, ey);
+            const float m = pr.in ? bm_abs(pr.d) : kBig;
+            const bool better = m < best;
+            best = better ? m : best;
+            cur = better ? c : cur;
+          }
+          const float Dt = p.dt_table
+                               ? p.dt_table[depth < BMCTS_MAX_DEPTH ? depth : BMCTS_MAX_DEPTH - 1]
+                               : cfg.prediction_k;
+          int action;
+          if (expand) {
+            action = p.action[rid];
+          } else {
+            uint4 rr = draw(p.key0, p.key1, p.first_rollout_id + (uint64_t)rid, 0u,
+                            BMCTS_RNG_ROLLOUT_ACTION, (uint32_t)n);
+            action = (int)bm_bounded(rr.x, (uint32_t)scn.n_ego_actions);
+          }
+          const float acc = ego_macro_step(scn, acts, cfg, action, cur, Dt, ex, ey, eth, ev, esn, ecs);
+          if (expand && p.last_action) p.last_action[rid] = acc;
+          if (expand) expand = false; else n++;
+          depth++;
+          float* s = mail->slot[(it + 1u) & 1u][lane];
+          s[0] = ex;
+          s[1] = ey;
+          s[2] = eth;
+          s[3] = ev;
+          s[4] = ecs;
+          s[5] = esn;
+        }
+      }
+    }
+    return;
+  }
+  uint32_t pass = 0, acq_seq = 0;  // AHEAD: pass counter (slot parity), acquisitions posted
   const int t = lane % T;  // lane inside the group
   const int g = lane / T;  // column
   float* col = reinterpret_cast<float*>(smem_raw + lay.off_state + lay.warp_bytes * warp) + g;
@@ -328,9 +475,25 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         eth = q0.z;
         ev = q0.w;
         bm_sincos(eth, &esn, &ecs);
+        acq_seq++;
       }
     }
-    if (__all_sync(0xffffffffu, done)) break;
+    {
+      const bool all_done = __all_sync(0xffffffffu, done);
+      if (AHEAD) {
+        if (t == 0) {
+          EgoAcq q;
+          q.seq = acq_seq;
+          q.rid = rid;
+          q.depth = depth;
+          q.flags = (expand ? 1u : 0u) | ((am & 1u) && active ? 2u : 0u);
+          mail->acq[pass & 1u][g] = q;
+        }
+        if (lane == 0) mail->done[pass & 1u] = all_done ? 1u : 0u;
+        ahead_barrier();  // the ego warp sees the acquisitions; its slots for this pass are written
+      }
+      if (all_done) break;
+    }
 
     const bool stepping = active && !fresh;
     const uint32_t pre = am;
@@ -403,71 +566,43 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
       }
     }
 
-    // ego: BehaviorMPMacroActions primitive on the single-track model (lane 0 of the group)
-    if (stepping && (pre & 1u) && t == 0) {
-      int action;
-      if (expand) {
-        action = p.action[rid];
-      } else {
-        uint4 rr = draw(p.key0, p.key1, rollout_id, 0u, BMCTS_RNG_ROLLOUT_ACTION, (uint32_t)n);
-        action = (int)bm_bounded(rr.x, (uint32_t)scn.n_ego_actions);
+    // ego: BehaviorMPMacroActions primitive on the single-track model (lane 0 of the group;
+    // AHEAD: computed one pass ago by the ego warp)
+    if (AHEAD) {
+      if (stepping && (pre & 1u)) {
+        const float* s = mail->slot[pass & 1u][g];
+        ex = s[0];
+        ey = s[1];
+        eth = s[2];
+        ev = s[3];
+        ecs = s[4];
+        esn = s[5];
+      } else if (stepping && expand && t == 0 && p.last_action) {
+        p.last_action[rid] = 0.0f;
       }
-      const bmcts_ego_action act = acts[action];
-      const float acc = bm_clamp(act.acceleration, cfg.lon_acc_min, cfg.lon_acc_max);
-      int tgt = STI(L_CUR, 0) & 0xf;
-      if (act.type == BMCTS_ACT_CHANGE_LEFT && scn.corridors[tgt].left >= 0)
-        tgt = scn.corridors[tgt].left;
-      else if (act.type == BMCTS_ACT_CHANGE_RIGHT && scn.corridors[tgt].right >= 0)
-        tgt = scn.corridors[tgt].right;
-      const bmcts_corridor& corr = scn.corridors[tgt];
-      const float wb = cfg.wheel_base, kct = cfg.crosstrack_gain, dmax = cfg.delta_max;
-      const float vmax = cfg.ego_max_velocity;
-      const float inv_wb = bm_div(1.0f, wb);
-      const int nsub_e = ego_substeps(cfg, Dt);
-      const float dt_e = bm_div(Dt, (float)nsub_e);
-      const bool limit = cfg.limit_steering_rate != 0;
-      const float lat_lo = cfg.lat_acc_min, lat_hi = cfg.lat_acc_max;
-      float nx = ex, ny = ey, nth = eth, nv = ev;
-      float sn = esn, cs = ecs;  // sin / cos of the current heading (published values)
-BM_UNROLL(BMCTS_EGO_UNROLL)
-      for (int q = 0; q < nsub_e; ++q) {
-        const float fx = bm_fma(wb, cs, nx);
-        const float fy = bm_fma(wb, sn, ny);
-        const Proj pr = project(corr, fx, fy);
-        const float th_err = bm_norm_angle(corr.angle[pr.seg] - nth);
-        float delta = th_err + bm_atan2(-(kct * pr.d), nv);
-        delta = bm_clamp(delta, -dmax, dmax);
-        float tn = bm_tan_small(delta);
-        if (limit) {  // lateral acceleration v^2 tan(delta) / L inside [LatAccMin, LatAccMax]
-          const float r = bm_div(wb, bm_max(nv * nv, 1.0e-6f));
-          tn = bm_clamp(tn, lat_lo * r, lat_hi * r);
+    } else {
+      if (stepping && (pre & 1u) && t == 0) {
+        int action;
+        if (expand) {
+          action = p.action[rid];
+        } else {
+          uint4 rr = draw(p.key0, p.key1, rollout_id, 0u, BMCTS_RNG_ROLLOUT_ACTION, (uint32_t)n);
+          action = (int)bm_bounded(rr.x, (uint32_t)scn.n_ego_actions);
         }
-        const float dv = dt_e * nv;
-        nx = bm_fma(dv, cs, nx);
-        ny = bm_fma(dv, sn, ny);
-        nth = bm_fma(dv, tn * inv_wb, nth);
-        nv = bm_clamp(bm_fma(dt_e, acc, nv), 0.0f, vmax);
-        // heading for the next sub-step; after the last one: of the wrapped final heading
-        if (q + 1 == nsub_e) nth = bm_norm_angle(nth);
-        bm_sincos(nth, &sn, &cs);
+        const float acc =
+            ego_macro_step(scn, acts, cfg, action, STI(L_CUR, 0) & 0xf, Dt, ex, ey, eth, ev, esn, ecs);
+        if (expand && p.last_action) p.last_action[rid] = acc;
+      } else if (stepping && expand && t == 0 && p.last_action) {
+        p.last_action[rid] = 0.0f;
       }
-      ex = nx;
-      ey = ny;
-      eth = nth;
-      ev = nv;
-      esn = sn;
-      ecs = cs;
-      if (expand && p.last_action) p.last_action[rid] = acc;
-    } else if (stepping && expand && t == 0 && p.last_action) {
-      p.last_action[rid] = 0.0f;
-    }
-    if (T > 1) {
-      ex = group_lead<T>(ex, lane);
-      ey = group_lead<T>(ey, lane);
-      eth = group_lead<T>(eth, lane);
-      ev = group_lead<T>(ev, lane);
-      ecs = group_lead<T>(ecs, lane);
-      esn = group_lead<T>(esn, lane);
+      if (T > 1) {
+        ex = group_lead<T>(ex, lane);
+        ey = group_lead<T>(ey, lane);
+        eth = group_lead<T>(eth, lane);
+        ev = group_lead<T>(ev, lane);
+        ecs = group_lead<T>(ecs, lane);
+        esn = group_lead<T>(esn, lane);
+      }
     }
     group_sync<T>();  // every read of the pre-step Frenet table is done
 
@@ -753,6 +888,7 @@ BM_UNROLL(BMCTS_EGO_UNROLL)
       }
     }
     fresh = false;
+    pass++;
   }
 #undef ST
 #undef STI

@@ -109,14 +109,18 @@ def random_case(seed):
     return cfg, scn, lane_of, s_of, rng
 
 
-# BMCTS_FUZZ_SEEDS=N widens the sweep (the round's one-off run: 1000 seeds, all bit-exact)
+# BMCTS_FUZZ_SEEDS=N widens the sweep (the round's one-off runs: 1500 seeds + 300 planner worlds, all bit-exact)
 @pytest.mark.parametrize("seed", range(int(os.environ.get("BMCTS_FUZZ_SEEDS", "40"))))
 def test_random_scenario_parity(seed, monkeypatch):
     # lanes per rollout: the engine's choice, or a forced value on every third seed
+    # (then also the kernel variant: plain / ego ahead; the engine's own choice for batches
+    # this small is the ego-ahead variant)
     if seed % 3 == 2:
         monkeypatch.setenv("BMCTS_LANE_T", str([1, 2, 4, 8, 16][(seed // 3) % 5]))
+        monkeypatch.setenv("BMCTS_LANE_AHEAD", str((seed // 15) % 2))
     else:
         monkeypatch.delenv("BMCTS_LANE_T", raising=False)
+        monkeypatch.delenv("BMCTS_LANE_AHEAD", raising=False)
     cfg, scn, lane_of, s_of, rng = random_case(seed)
     n = int(rng.choice([1, 33, 200]))
     pose, alive, hyp = scenarios.sample_leaves(scn, n, lane_of, s_of, rng, s_jitter=6.0,

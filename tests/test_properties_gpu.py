@@ -32,6 +32,13 @@ def test_full_size_batch_properties(name, n, monkeypatch):
     for t in ("1", "2", "4", "16"):
         monkeypatch.setenv("BMCTS_LANE_T", t)
         assert np.array_equal(a, _run(eng, pose, alive, hyp)["result"]), f"T={t}"
+    # the "ego ahead" variant (engine.cu: chosen for small batches) on a full-size one: every
+    # column refills many times
+    monkeypatch.setenv("BMCTS_LANE_AHEAD", "1")
+    for t in ("1", "16"):
+        monkeypatch.setenv("BMCTS_LANE_T", t)
+        assert np.array_equal(a, _run(eng, pose, alive, hyp)["result"]), f"ego ahead, T={t}"
+    monkeypatch.delenv("BMCTS_LANE_AHEAD", raising=False)
     monkeypatch.delenv("BMCTS_LANE_T", raising=False)
     monkeypatch.setenv("BMCTS_PIPE_CHUNK", "100000")
     assert np.array_equal(a, _run(eng, pose, alive, hyp)["result"]), "chunked host batch"
