@@ -174,7 +174,7 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cuda
   if (attr_err[e->device] != cudaSuccess)
     return cuda_fail(e, attr_err[e->device], "cudaFuncSetAttribute");
   // geometry per (variant, scenario size, batch class): occupancy queries are cached
-  // (COOP has its own top bit: T = 16 is 1 << 60 in the T field)
+  // (COOP and AHEAD have the two top bits: T = 32 is 1 << 61 in the T field)
   const unsigned long long key = ((unsigned long long)COOP << 63) |
                                  ((unsigned long long)AHEAD << 62) | ((unsigned long long)T << 56) |
                                  ((unsigned long long)a.A << 48) | ((unsigned long long)a.C << 44) |
@@ -241,7 +241,7 @@ int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream
   int T = 0, W = 0;
   if (const char* s = std::getenv("BMCTS_LANE_T")) T = std::atoi(s);
   if (const char* s = std::getenv("BMCTS_LANE_W")) W = std::atoi(s);
-  if (T != 1 && T != 2 && T != 4 && T != 8 && T != 16) {
+  if (T != 1 && T != 2 && T != 4 && T != 8 && T != 16 && T != 32) {
     const size_t budget = 11 * 1024 + 512;
     auto warp_bytes = [&](int t) {
       return COOP ? bmcts::lane_coop_layout(a.A, a.C, t, 1).warp_bytes
@@ -253,16 +253,18 @@ int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream
     // a batch too small to fill the GPU (an MCTS wave) is latency bound: more lanes per
     // rollout shorten the serial chain of a step (up to one agent per lane)
     const long lanes_resident = (long)e->sm_count * 32 * 16;
-    for (int t = 2; t <= 16; t *= 2)
+    for (int t = 2; t <= 32; t *= 2)
       if (T < t && (long)a.n * t <= lanes_resident && a.A > t / 2) T = t;
   }
   // the ego-ahead variant when the batch leaves most of the GPU idle (latency bound: an MCTS
-  // wave); BMCTS_LANE_AHEAD = 0 / 1 forces the choice (tests)
-  bool ahead = !COOP && (long)a.n * T * 4 <= (long)e->sm_count * 32 * 16;
+  // wave; measured on c2 / c5: faster up to about a quarter of the lanes the GPU can hold,
+  // slower from half of them); BMCTS_LANE_AHEAD = 0 / 1 forces the choice (tests)
+  bool ahead = !COOP && (long)a.n * T * 2 <= (long)e->sm_count * 32 * 16;
   if (const char* s = std::getenv("BMCTS_LANE_AHEAD")) ahead = !COOP && std::atoi(s) != 0;
   if constexpr (!COOP) {
     if (ahead) {
       switch (T) {
+        case 32: return launch_lane_T<32, false, true>(e, a, W, stream, counter);
         case 16: return launch_lane_T<16, false, true>(e, a, W, stream, counter);
         case 8: return launch_lane_T<8, false, true>(e, a, W, stream, counter);
         case 4: return launch_lane_T<4, false, true>(e, a, W, stream, counter);
@@ -272,6 +274,7 @@ int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream
     }
   }
   switch (T) {
+    case 32: return launch_lane_T<32, COOP, false>(e, a, W, stream, counter);
     case 16: return launch_lane_T<16, COOP, false>(e, a, W, stream, counter);
     case 8: return launch_lane_T<8, COOP, false>(e, a, W, stream, counter);
     case 4: return launch_lane_T<4, COOP, false>(e, a, W, stream, counter);

@@ -8,7 +8,7 @@
 // (paths relative to /root/reference/bark_mcts/models/behavior/).  The cooperative state
 // has its own kernel with the same mapping (rollout_lane_coop_kernel.cuh).
 //
-// Mapping: T consecutive lanes (T = 1, 2, 4, 8 or 16) own one rollout; a warp carries 32/T
+// Mapping: T consecutive lanes (T = 1, 2, 4, 8, 16 or 32) own one rollout; a warp carries 32/T
 // rollouts and never talks to another warp, so there is no block barrier in the step
 // loop.  Within a group the others' IDM hypothesis models are split over the T lanes and
 // the ego's single-track macro action runs on lane 0 of the group: every lane of a warp is

@@ -116,8 +116,8 @@ def test_random_scenario_parity(seed, monkeypatch):
     # (then also the kernel variant: plain / ego ahead; the engine's own choice for batches
     # this small is the ego-ahead variant)
     if seed % 3 == 2:
-        monkeypatch.setenv("BMCTS_LANE_T", str([1, 2, 4, 8, 16][(seed // 3) % 5]))
-        monkeypatch.setenv("BMCTS_LANE_AHEAD", str((seed // 15) % 2))
+        monkeypatch.setenv("BMCTS_LANE_T", str([1, 2, 4, 8, 16, 32][(seed // 3) % 6]))
+        monkeypatch.setenv("BMCTS_LANE_AHEAD", str((seed // 18) % 2))
     else:
         monkeypatch.delenv("BMCTS_LANE_T", raising=False)
         monkeypatch.delenv("BMCTS_LANE_AHEAD", raising=False)

@@ -18,12 +18,12 @@ WORKLOADS = ["c1_highway_mdp", "c2_merge_sbg", "c3_merge_risk", "c4_coop", "c5_r
 GEOMETRIES = WORKLOADS + ["x_curved_max"]
 
 
-@pytest.fixture(params=["auto", "1", "2", "4", "8", "16", "1+ahead", "4+ahead", "16+ahead"],
+@pytest.fixture(params=["auto", "1", "2", "4", "8", "16", "32", "1+ahead", "4+ahead", "16+ahead", "32+ahead"],
                 autouse=True)
 def lanes_per_rollout(request, monkeypatch):
     """every test runs with the engine's own choice of kernel variant (for these small batches:
     the "ego ahead" variant, engine.cu launch_lane), with each forced number of lanes per
-    rollout on the plain variant, and with the ego-ahead variant at 1 / 4 / 16 lanes
+    rollout on the plain variant, and with the ego-ahead variant at 1 / 4 / 16 / 32 lanes
     (BMCTS_LANE_T / BMCTS_LANE_AHEAD are read at every launch)"""
     if request.param == "auto":
         monkeypatch.delenv("BMCTS_LANE_T", raising=False)

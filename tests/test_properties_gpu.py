@@ -29,7 +29,7 @@ def test_full_size_batch_properties(name, n, monkeypatch):
     # 1. determinism: the same call again
     assert np.array_equal(a, _run(eng, pose, alive, hyp)["result"])
     # 2. launch geometry does not matter: other lanes-per-rollout, tiny grid, chunked upload
-    for t in ("1", "2", "4", "16"):
+    for t in ("1", "2", "4", "16", "32"):
         monkeypatch.setenv("BMCTS_LANE_T", t)
         assert np.array_equal(a, _run(eng, pose, alive, hyp)["result"]), f"T={t}"
     # the "ego ahead" variant (engine.cu: chosen for small batches) on a full-size one: every
