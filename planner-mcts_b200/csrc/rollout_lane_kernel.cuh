@@ -521,13 +521,40 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         // BaseIDM::CalcRelativeValues: nearest alive agent ahead inside the corridor
         int jf = -1;
         float ds_f = kBig;
+        if (AHEAD) {
+          // latency-bound variant: four candidates per trip, their loads in flight together
+          // (a short tail repeats the first candidate, which changes nothing: the test is strict)
+          for (uint32_t m = pre & INC(cur) & ~(1u << i); m;) {
+            const uint32_t m1 = m & (m - 1u), m2 = m1 & (m1 - 1u), m3 = m2 & (m2 - 1u);
+            const int j0 = __ffs(m) - 1;
+            const int j1 = m1 ? __ffs(m1) - 1 : j0;
+            const int j2 = m2 ? __ffs(m2) - 1 : j0;
+            const int j3 = m3 ? __ffs(m3) - 1 : j0;
+            m = m3 & (m3 - 1u);
+            const float d0 = tab_s[j0 * NC] - s_cur, d1 = tab_s[j1 * NC] - s_cur;
+            const float d2 = tab_s[j2 * NC] - s_cur, d3 = tab_s[j3 * NC] - s_cur;
+            bool b = d0 > 0.0f && d0 < ds_f;
+            ds_f = b ? d0 : ds_f;
+            jf = b ? j0 : jf;
+            b = d1 > 0.0f && d1 < ds_f;
+            ds_f = b ? d1 : ds_f;
+            jf = b ? j1 : jf;
+            b = d2 > 0.0f && d2 < ds_f;
+            ds_f = b ? d2 : ds_f;
+            jf = b ? j2 : jf;
+            b = d3 > 0.0f && d3 < ds_f;
+            ds_f = b ? d3 : ds_f;
+            jf = b ? j3 : jf;
+          }
+        } else {
 #pragma unroll 1
-        for (uint32_t m = pre & INC(cur) & ~(1u << i); m; m &= m - 1u) {
-          const int j = __ffs(m) - 1;
-          const float ds = tab_s[j * NC] - s_cur;
-          const bool better = ds > 0.0f && ds < ds_f;
-          ds_f = better ? ds : ds_f;
-          jf = better ? j : jf;
+          for (uint32_t m = pre & INC(cur) & ~(1u << i); m; m &= m - 1u) {
+            const int j = __ffs(m) - 1;
+            const float ds = tab_s[j * NC] - s_cur;
+            const bool better = ds > 0.0f && ds < ds_f;
+            ds_f = better ? ds : ds_f;
+            jf = better ? j : jf;
+          }
         }
         const bool has_leader = jf >= 0;
         float gap = 0.0f, v_l = 0.0f;
@@ -801,17 +828,38 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
           const float s_e = tab_s[0];
           int jf = -1, jr = -1;
           float ds_f = kBig, ds_r = kBig;
+          if (AHEAD) {  // (two candidates per trip, as in the leader search above)
+            for (uint32_t m = am & INC(cur) & ~1u; m;) {
+              const uint32_t m1 = m & (m - 1u);
+              const int j0 = __ffs(m) - 1;
+              const int j1 = m1 ? __ffs(m1) - 1 : j0;
+              m = m1 & (m1 - 1u);
+              const float d0 = tab_s[j0 * NC] - s_e, d1 = tab_s[j1 * NC] - s_e;
+              bool bf = d0 > 0.0f && d0 < ds_f, br = -d0 > 0.0f && -d0 < ds_r;
+              ds_f = bf ? d0 : ds_f;
+              jf = bf ? j0 : jf;
+              ds_r = br ? -d0 : ds_r;
+              jr = br ? j0 : jr;
+              bf = d1 > 0.0f && d1 < ds_f;
+              br = -d1 > 0.0f && -d1 < ds_r;
+              ds_f = bf ? d1 : ds_f;
+              jf = bf ? j1 : jf;
+              ds_r = br ? -d1 : ds_r;
+              jr = br ? j1 : jr;
+            }
+          } else {
 #pragma unroll 1
-          for (uint32_t m = am & INC(cur) & ~1u; m; m &= m - 1u) {
-            const int j = __ffs(m) - 1;
-            const float ds = tab_s[j * NC] - s_e;
-            const float dr = -ds;
-            const bool bf = ds > 0.0f && ds < ds_f;
-            const bool br = dr > 0.0f && dr < ds_r;
-            ds_f = bf ? ds : ds_f;
-            jf = bf ? j : jf;
-            ds_r = br ? dr : ds_r;
-            jr = br ? j : jr;
+            for (uint32_t m = am & INC(cur) & ~1u; m; m &= m - 1u) {
+              const int j = __ffs(m) - 1;
+              const float ds = tab_s[j * NC] - s_e;
+              const float dr = -ds;
+              const bool bf = ds > 0.0f && ds < ds_f;
+              const bool br = dr > 0.0f && dr < ds_r;
+              ds_f = bf ? ds : ds_f;
+              jf = bf ? j : jf;
+              ds_r = br ? dr : ds_r;
+              jr = br ? j : jr;
+            }
           }
           bool safe = true;
           if (jf >= 0) {
