@@ -505,7 +505,7 @@ def run_ours(args):
     # ---- Plan() arm: one BehaviorUCT*::Plan() of --plan-iterations MCTS iterations in total,
     # root-parallel over the ranks (tree indices are disjoint), root statistics merged with one
     # NCCL all-reduce (BASELINE.json configs[4]: 10^6 rollouts per Plan())
-    plan, plan_all = None, None
+    plan, plan_all, plan_w16 = None, None, None
     if not args.no_plan:
         from planner_mcts_b200 import root_parallel
         cores = os.cpu_count() or 1
@@ -514,10 +514,11 @@ def run_ours(args):
         if comm is not None:
             comm.allreduce(np.zeros(8))   # connection set-up of the new communicator, once
 
-        def plan_arm(threads):
-            trees = args.plan_trees if args.plan_trees > 0 else 2 * threads
+        def plan_arm(threads, wave=None, trees_per_thread=2):
+            trees = args.plan_trees if args.plan_trees > 0 else trees_per_thread * threads
             per_tree = max(1, args.plan_iterations // (world * trees))
-            g = plan_benchmark(args.workload, args.horizon, per_tree, args.plan_wave, "gpu",
+            g = plan_benchmark(args.workload, args.horizon, per_tree,
+                               args.plan_wave if wave is None else wave, "gpu",
                                device=local_rank, tree_index=rank, trees=trees, threads=threads)
             ms = torch.tensor([g["plan_ms"]], dtype=torch.float64, device=dev)
             barrier()   # plan_ms is the MAX over ranks: waiting for the slowest rank is in it already
@@ -548,6 +549,10 @@ def run_ours(args):
         plan["threads_note"] = "host threads per rank = cores / 8 at every N (per-GPU share of the host)"
         if world == 1:
             plan_all = plan_arm(max(1, min(16, cores)))   # one rank with (up to 16 of) all cores
+            # the same budget in waves of 16 leaves -- the largest wave whose root estimates stay
+            # within Monte-Carlo noise of the sequential search -- with four
+            # trees per thread in flight to cover the latency of such a wave
+            plan_w16 = plan_arm(max(1, min(16, cores)), wave=16, trees_per_thread=4)
         if comm is not None:
             comm.close()
 
@@ -605,6 +610,8 @@ def run_ours(args):
         line["plan"] = plan
     if plan_all is not None:
         line["plan_all_host_threads"] = plan_all
+    if plan_w16 is not None:
+        line["plan_wave16"] = plan_w16
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cfg, scn, meta)
         if plan is not None:

@@ -434,6 +434,10 @@ int bmcts_math_probe(bmcts_engine* e, int op, const float* a, const float* b, in
 int bmcts_sync(bmcts_engine* e);
 /* device time of the last batch call's kernel(s) in milliseconds (CUDA events on the engine stream) */
 int bmcts_last_kernel_ms(bmcts_engine* e, float* ms);
+/* the two event records around every launch are on by default; a caller that never asks for
+ * bmcts_last_kernel_ms (the planner's tree search: one launch per MCTS wave, many host threads
+ * sharing the driver) switches them off.  bmcts_last_kernel_ms then fails with INVALID_ARG. */
+int bmcts_set_kernel_timing(bmcts_engine* e, int on);
 /* number of kernels this engine has launched since creation */
 uint64_t bmcts_launch_count(const bmcts_engine* e);
 /* the engine's CUDA stream as an opaque pointer (cudaStream_t) */

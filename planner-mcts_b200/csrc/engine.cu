@@ -8,6 +8,7 @@
 // fallback: without a CUDA device bmcts_create fails with BMCTS_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -41,6 +42,11 @@ struct bmcts_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  bool timing = true;  // record the events around every launch (bmcts_set_kernel_timing)
+  // completion flag of zero-copy waves (pinned; written by the kernel's last warp)
+  unsigned int* h_done_flag = nullptr;
+  unsigned int done_seq = 0;
+  bool flag_pending = false;  // the launch in flight raises the flag
   bool timed = false;
   bmcts_config cfg;
   bmcts_scenario scn;
@@ -219,7 +225,7 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cuda
     const long cap = std::atol(s);
     if (cap > 0 && grid > cap) grid = cap;
   }
-  CU(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+  // (no memset of the work counter: the kernel's last warp clears it, retire_warp)
   kern<<<(unsigned)grid, (g.W + (AHEAD ? 1 : 0)) * 32, g.smem, stream>>>(a, counter);
   CU(cudaGetLastError());
   e->launches++;
@@ -291,6 +297,10 @@ int launch_on(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream,
 
 int launch(bmcts_engine* e, const bmcts::KernelArgs& a) {
   if (a.n <= 0) return BMCTS_OK;
+  if (!e->timing) {  // bmcts_set_kernel_timing(e, 0): two driver calls per launch less
+    e->timed = false;
+    return launch_on(e, a, e->stream, e->d_counter);
+  }
   CU(cudaEventRecord(e->ev_start, e->stream));
   int st = launch_on(e, a, e->stream, e->d_counter);
   if (st) return st;
@@ -628,6 +638,40 @@ bool pack_zero_copy(const Pack& pin, const Pack& pout) {
          !std::getenv("BMCTS_NO_ZERO_COPY");
 }
 
+// Waits for the wave in flight.  A zero-copy wave raises a flag in pinned memory when its last
+// warp is done (retire_warp): the host reads that word instead of calling the driver, whose lock
+// the host threads of a multi-tree search share; the stream is only queried now and then, so that
+// a failed launch ends in an error and not in a spin.
+int wait_wave(bmcts_engine* e) {
+  if (!e->flag_pending) {
+    CU(cudaStreamSynchronize(e->stream));
+    return BMCTS_OK;
+  }
+  e->flag_pending = false;
+  volatile unsigned int* f = e->h_done_flag;
+  const unsigned int want = e->done_seq;
+  for (unsigned int spins = 1; *f != want; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 2047u) == 0) {
+      const cudaError_t ce = cudaStreamQuery(e->stream);
+      if (ce == cudaSuccess) break;  // finished: the results are in place whatever the flag says
+      if (ce != cudaErrorNotReady) return cuda_fail(e, ce, "cudaStreamQuery");
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return BMCTS_OK;
+}
+
+// arms the completion flag for a launch that works on the pinned blocks directly
+void arm_flag(bmcts_engine* e, bmcts::KernelArgs& a, const Pack& pin, const Pack& pout) {
+  if (!pack_zero_copy(pin, pout) || !e->h_done_flag || std::getenv("BMCTS_NO_DONE_FLAG")) return;
+  a.done_flag = e->h_done_flag;
+  a.done_value = ++e->done_seq;
+  e->flag_pending = true;
+}
+
 // stages the packed inputs (and uploads them unless the wave is small enough for zero copy);
 // returns the base pointers of the input and output blocks as the kernel sees them
 int pack_upload(bmcts_engine* e, const Pack& pin, const Pack& pout, char** d_in, char** d_out) {
@@ -660,7 +704,8 @@ int pack_download(bmcts_engine* e, const Pack& pin, const Pack& pout, bool async
     e->async_pending = true;
     return BMCTS_OK;
   }
-  CU(cudaStreamSynchronize(e->stream));
+  int st = wait_wave(e);
+  if (st) return st;
   for (const Pack::Item& it : pout.items)
     std::memcpy(it.dst, (char*)e->h_pack_out + it.off, it.bytes);
   return BMCTS_OK;
@@ -669,7 +714,8 @@ int pack_download(bmcts_engine* e, const Pack& pin, const Pack& pout, bool async
 int pack_collect(bmcts_engine* e) {
   e->async_pending = false;
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  int st = wait_wave(e);
+  if (st) return st;
   for (const bmcts_engine::PendingItem& it : e->async_items)
     std::memcpy(it.dst, (char*)e->h_pack_out + it.off, it.bytes);
   return BMCTS_OK;
@@ -729,14 +775,19 @@ int bmcts_create(int device, const bmcts_config* cfg, bmcts_engine** out) {
     return bail(ce);
   cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if ((ce = cudaMalloc(&e->d_counter, sizeof(unsigned int))) != cudaSuccess) return bail(ce);
+  if ((ce = cudaHostAlloc((void**)&e->h_done_flag, 64, cudaHostAllocDefault)) != cudaSuccess)
+    return bail(ce);
+  *e->h_done_flag = 0;
+  if ((ce = cudaMalloc(&e->d_counter, 2 * sizeof(unsigned int))) != cudaSuccess) return bail(ce);
+  if ((ce = cudaMemset(e->d_counter, 0, 2 * sizeof(unsigned int))) != cudaSuccess) return bail(ce);
   if ((ce = cudaEventCreateWithFlags(&e->ev_pipe, cudaEventDisableTiming)) != cudaSuccess)
     return bail(ce);
   if ((ce = cudaMalloc(&e->d_ready, 2 * sizeof(unsigned int))) != cudaSuccess) return bail(ce);
   for (auto& sl : e->pipe) {
     if ((ce = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) != cudaSuccess)
       return bail(ce);
-    if ((ce = cudaMalloc(&sl.d_counter, sizeof(unsigned int))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMalloc(&sl.d_counter, 2 * sizeof(unsigned int))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMemset(sl.d_counter, 0, 2 * sizeof(unsigned int))) != cudaSuccess) return bail(ce);
   }
   if ((ce = cudaMemcpy(e->d_cfg, &e->cfg, sizeof(bmcts_config), cudaMemcpyHostToDevice)) !=
       cudaSuccess)
@@ -763,6 +814,7 @@ void bmcts_destroy(bmcts_engine* e) {
   if (e->d_scn) cudaFree(e->d_scn);
   if (e->d_dt_table) cudaFree(e->d_dt_table);
   if (e->d_counter) cudaFree(e->d_counter);
+  if (e->h_done_flag) cudaFreeHost(e->h_done_flag);
   for (auto& sl : e->pipe) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
     DevBuf* sb[] = {&sl.pose, &sl.alive, &sl.hyp, &sl.depth, &sl.index, &sl.result, &sl.ret_agents, &sl.final_pose};
@@ -896,6 +948,7 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
       a.result = (bmcts_rollout_result*)op(o_res);
       a.ret_agents = (float*)op(o_ra);
       a.final_pose = (float4*)op(o_fp);
+      arm_flag(e, a, pin, pout);
       if ((st = launch(e, a))) return st;
       return pack_download(e, pin, pout);
     }
@@ -1009,6 +1062,7 @@ static int step_common(bmcts_engine* e, const bmcts_step_in* in, const bmcts_ste
       a.result = (bmcts_rollout_result*)op(o_res);
       a.ret_agents = (float*)op(o_ra);
       a.final_pose = (float4*)op(o_fp);
+      arm_flag(e, a, pin, pout);
       if ((st = launch(e, a))) return st;
       return pack_download(e, pin, pout, async);
     }
@@ -1201,10 +1255,20 @@ int bmcts_sync(bmcts_engine* e) {
 
 int bmcts_last_kernel_ms(bmcts_engine* e, float* ms) {
   if (!e || !ms) return BMCTS_ERR_INVALID_ARG;
-  if (!e->timed) return fail(e, BMCTS_ERR_INVALID_ARG, "no batch call has been timed yet");
+  if (!e->timed)
+    return fail(e, BMCTS_ERR_INVALID_ARG,
+                e->timing ? "no batch call has been timed yet"
+                          : "kernel timing is off (bmcts_set_kernel_timing)");
   CU(cudaSetDevice(e->device));
   CU(cudaEventSynchronize(e->ev_stop));
   CU(cudaEventElapsedTime(ms, e->ev_start, e->ev_stop));
+  return BMCTS_OK;
+}
+
+int bmcts_set_kernel_timing(bmcts_engine* e, int on) {
+  if (!e) return BMCTS_ERR_INVALID_ARG;
+  e->timing = on != 0;
+  if (!e->timing) e->timed = false;
   return BMCTS_OK;
 }
 

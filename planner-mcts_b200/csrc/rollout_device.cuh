@@ -64,6 +64,11 @@ struct KernelArgs {
   // tables of ns states and rollout k starts from state state_index[k]; null: ns == n, state k
   const uint32_t* state_index;
   int ns;
+  // completion flag of a wave that runs on pinned host memory (engine.cu pack_zero_copy): the
+  // last warp of the grid stores done_value there after its results, and the host waits on the
+  // flag instead of making a driver call.  Null for every other call.
+  unsigned int* done_flag;
+  unsigned int done_value;
 };
 
 // start pose of agent a of rollout rid: row rid of the agent-major batch arrays, or -- unique-state

@@ -119,7 +119,10 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
         inc0 = inc1 = inc2 = inc3 = 0;
       }
     }
-    if (__all_sync(0xffffffffu, done)) break;
+    if (__all_sync(0xffffffffu, done)) {
+      retire_warp(p, counter, gridDim.x * (uint32_t)warps, lane);
+      break;
+    }
 
     const bool stepping = active && !fresh;
     const uint32_t pre = am;

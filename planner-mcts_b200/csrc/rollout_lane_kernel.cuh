@@ -83,6 +83,27 @@ __device__ __forceinline__ float group_lead(float x, int lane) {
   return T == 1 ? x : __shfl_sync(0xffffffffu, x, lane & ~(T - 1));
 }
 
+// The work counter resets itself: counter[0] hands out rollouts, counter[1] counts the warps
+// that are out of work; the last one of the grid clears both, so the next launch on the stream
+// finds them zero and no memset travels with a launch (a driver call per MCTS wave less).  That
+// last warp also raises the wave's completion flag in host memory, when there is one: every
+// warp's results are ordered before its count (fence), the count before the flag.
+__device__ __forceinline__ void retire_warp(const KernelArgs& p, unsigned int* counter,
+                                            unsigned int warps_in_grid, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    if (p.done_flag) __threadfence_system(); else __threadfence();
+    if (atomicAdd(counter + 1, 1u) == warps_in_grid - 1u) {
+      counter[0] = 0u;
+      counter[1] = 0u;
+      if (p.done_flag) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(p.done_flag) = p.done_value;
+      }
+    }
+  }
+}
+
 template <int T>
 __device__ __forceinline__ void group_sync() {
   if (T > 1) __syncwarp();
@@ -492,7 +513,10 @@ rollout_lane_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
         if (lane == 0) mail->done[pass & 1u] = all_done ? 1u : 0u;
         ahead_barrier();  // the ego warp sees the acquisitions; its slots for this pass are written
       }
-      if (all_done) break;
+      if (all_done) {
+        retire_warp(p, counter, gridDim.x * (uint32_t)warps, lane);
+        break;
+      }
     }
 
     const bool stepping = active && !fresh;

@@ -21,6 +21,8 @@ class GpuLeafEvaluator : public LeafEvaluator {
         err_ = std::string("bmcts_create: ") + bmcts_status_string(st);
         return st;
       }
+      // one launch per MCTS wave and nobody reads the kernel time: no event records
+      bmcts_set_kernel_timing(engine_, 0);
     } else {
       int st = bmcts_set_config(engine_, &cfg);
       if (st != BMCTS_OK) return st;
