@@ -97,6 +97,10 @@ class RolloutEngine:
         self._check(self._lib.bmcts_last_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def set_kernel_timing(self, on):
+        """event records around every launch on / off (on by default; off: last_kernel_ms raises)"""
+        self._check(self._lib.bmcts_set_kernel_timing(self._h, 1 if on else 0))
+
     def launch_count(self):
         return int(self._lib.bmcts_launch_count(self._h))
 

@@ -365,3 +365,31 @@ def test_elementary_math_is_bit_identical_on_device_and_host():
         bad = np.nonzero(~same)[0]
         assert bad.size == 0, f"{op}: {bad.size} mismatches, e.g. a={a[bad[:3]]} b={b[bad[:3]]} " \
                               f"gpu={g[bad[:3]]} cpu={c[bad[:3]]}"
+
+
+def test_wave_paths_without_driver_calls_change_nothing(monkeypatch):
+    """a small wave from host memory (the planner's case) runs on the pinned blocks directly and
+    reports completion through a flag in host memory (engine.cu wait_wave); with the flag off the
+    host synchronizes the stream instead; with kernel timing off there are no event records.
+    Same results every way, many waves in a row (the flag's sequence number advances, the work
+    counter resets itself between launches), and bmcts_last_kernel_ms says when it has nothing."""
+    cfg, scn, meta = scenarios.workload("c3_merge_risk", horizon=20)
+    rng = np.random.default_rng(5)
+    eng = RolloutEngine(cfg, scn)
+    ref = None
+    for it in range(12):
+        n = [7, 40, 130][it % 3]
+        pose, alive, hyp = scenarios.sample_leaves(scn, n, meta["lane_of"], meta["s_of"], rng)
+        c = oracle.rollout(cfg, scn, pose, alive, hyp, seed=3, stream=it)
+        monkeypatch.delenv("BMCTS_NO_DONE_FLAG", raising=False)
+        eng.set_kernel_timing(it % 2 == 0)
+        g = eng.rollout(pose, alive, hyp, seed=3, stream=it)
+        parity.assert_results_match(g, c)
+        if it % 2 == 0:
+            assert eng.last_kernel_ms() > 0.0
+        else:
+            with pytest.raises(Exception, match="timing is off"):
+                eng.last_kernel_ms()
+        monkeypatch.setenv("BMCTS_NO_DONE_FLAG", "1")
+        g2 = eng.rollout(pose, alive, hyp, seed=3, stream=it)
+        assert np.array_equal(g["result"], g2["result"])
