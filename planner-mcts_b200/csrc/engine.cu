@@ -949,7 +949,10 @@ int bmcts_rollout_batch(bmcts_engine* e, const bmcts_leaf_batch* in, const bmcts
       a.ret_agents = (float*)op(o_ra);
       a.final_pose = (float4*)op(o_fp);
       arm_flag(e, a, pin, pout);
-      if ((st = launch(e, a))) return st;
+      if ((st = launch(e, a))) {
+        e->flag_pending = false;
+        return st;
+      }
       return pack_download(e, pin, pout);
     }
   }
@@ -1063,7 +1066,10 @@ static int step_common(bmcts_engine* e, const bmcts_step_in* in, const bmcts_ste
       a.ret_agents = (float*)op(o_ra);
       a.final_pose = (float4*)op(o_fp);
       arm_flag(e, a, pin, pout);
-      if ((st = launch(e, a))) return st;
+      if ((st = launch(e, a))) {
+        e->flag_pending = false;
+        return st;
+      }
       return pack_download(e, pin, pout, async);
     }
   }
