@@ -1,6 +1,14 @@
-"""bias of the wave-batched search against the sequential search by wave size (CPU oracle backend)"""
+"""Bias of the wave-batched search against the sequential search by wave size (CPU oracle
+backend; test infrastructure, like everything that imports tests/oracle.py).
+
+    python tools/wave_bias.py [seeds]      # profiles/r2_wave_bias_64seeds.txt was made with 64
+
+Three planners x two worlds x 1500 / 2000 / 4000 iterations; per case the waves iterations / 128
+(the default), a candidate of up to iterations / 64, and twice that.  Per line: the extreme
+z-scores (pooled standard errors of the seed means) and the extreme bias in seed-to-seed standard
+deviations over the root estimates, and the set of decisions taken."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import oracle, planner_worlds as W
