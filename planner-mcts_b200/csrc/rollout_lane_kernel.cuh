@@ -14,7 +14,9 @@
 // the ego's single-track macro action runs on lane 0 of the group: every lane of a warp is
 // in the same role at the same time (no ego-vs-IDM divergence), and a group that finishes
 // its rollout pulls the next one from a global counter, so lanes stay busy until the batch
-// is drained (rollouts end at different steps).
+// is drained (rollouts end at different steps).  Batches too small to fill the GPU run the
+// "ego ahead" variant (AHEAD = true, below): a block is one warp of rollouts plus one warp that
+// computes the egos' macro actions a pass ahead.
 //
 // Per-rollout state in shared memory, [field][agent][column] with column = group index in
 // the warp (bank = column: conflict free): velocity, arc length s on every lane corridor,
