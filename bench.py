@@ -631,6 +631,16 @@ def run_ours(args):
             "workload": "c2_merge_sbg", "iterations": 2000, "trees": 1, "wave": "default",
             "gpu_plan_ms": gd["plan_ms"], "gpu_plan_ms_all": gd["plan_ms_all"],
             "cpu_plan_ms": cd["plan_ms"], "speedup": cd["plan_ms"] / gd["plan_ms"]}
+        if not args.no_workloads:
+            # the same budget on the other workloads (the CPU search pays per agent and step,
+            # the GPU wave per pass of its longest rollout)
+            others = {}
+            for name in ("c1_highway_mdp", "c3_merge_risk", "c4_coop", "c5_rsbg"):
+                g_ = plan_benchmark(name, 20, 2000, 0, "gpu", device=local_rank)
+                c_ = plan_benchmark(name, 20, 2000, 1, "cpu")
+                others[name] = {"gpu_plan_ms": g_["plan_ms"], "cpu_plan_ms": c_["plan_ms"],
+                                "speedup": c_["plan_ms"] / g_["plan_ms"]}
+            line["plan_default_budget"]["other_workloads"] = others
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

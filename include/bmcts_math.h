@@ -178,11 +178,8 @@ BM_HD float bm_atan(float x) {
  * A zero numerator (an agent exactly on its lane centre line, or |y| == |x|) skips the
  * division: the device's IEEE division would take its slow path for it. */
 BM_HD float bm_atan2(float y, float x) {
-  if (x == 0.0f) {
-    if (y > 0.0f) return BM_PIO2_HI;
-    if (y < 0.0f) return -BM_PIO2_HI;
-    return 0.0f;
-  }
+  /* x == 0 needs no case of its own: it lands in the third range (num = -0, no division,
+   * +-pi/2) or, with y == 0 as well, in the first (num = 0, result +0) */
   const float ay = bm_abs(y), ax = bm_abs(x);
   const int big = ay > 2.414213562373095f * ax;
   const int mid = ay > 0.4142135623730950f * ax;
