@@ -145,17 +145,19 @@ int upload_dt_table(bmcts_engine* e) {
 // the batch fills the GPU, more when it does not (an MCTS wave of a few hundred leaves) or
 // when the per-rollout state of a large scenario would leave too few warps resident.
 // W warps per block share one staged scenario; the grid is persistent (blocks/SM x SMs).
-// AHEAD (hypothesis / risk kernel only): the "ego ahead" variant for batches too small to fill
-// the GPU -- one warp of rollouts plus the ego warp per block (rollout_lane_kernel.cuh).
+// AHEAD: the "ego ahead" / "macro actions ahead" variants for batches too small to fill the GPU
+// -- one warp of rollouts plus one warp that computes the macro actions a pass ahead per block
+// (rollout_lane_kernel.cuh, rollout_lane_coop_kernel.cuh).
 template <int T, bool COOP, bool AHEAD>
 int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cudaStream_t stream,
                   unsigned int* counter) {
-  static_assert(!(COOP && AHEAD), "the cooperative kernel has no ego-ahead variant");
-  auto kern = COOP ? bmcts::rollout_lane_coop_kernel<T> : bmcts::rollout_lane_kernel<T, AHEAD>;
+  auto kern = COOP ? bmcts::rollout_lane_coop_kernel<T, AHEAD> : bmcts::rollout_lane_kernel<T, AHEAD>;
   auto layout = [&](int W) {
     bmcts::LaneLayout l =
         COOP ? bmcts::lane_coop_layout(a.A, a.C, T, W) : bmcts::lane_layout(a.A, a.C, a.H, T, W);
-    if (AHEAD) l.total = bmcts::smem_align16(l.total) + sizeof(bmcts::EgoMail);
+    if (AHEAD)
+      l.total = bmcts::smem_align16(l.total) +
+                (COOP ? sizeof(bmcts::CoopMail) : sizeof(bmcts::EgoMail));
     return l;
   };
   if (AHEAD) force_W = 1;
@@ -262,21 +264,21 @@ int launch_lane(bmcts_engine* e, const bmcts::KernelArgs& a, cudaStream_t stream
     for (int t = 2; t <= 32; t *= 2)
       if (T < t && (long)a.n * t <= lanes_resident && a.A > t / 2) T = t;
   }
-  // the ego-ahead variant when the batch leaves most of the GPU idle (latency bound: an MCTS
-  // wave; measured on c2 / c5: faster up to about a quarter of the lanes the GPU can hold,
-  // slower from half of them); BMCTS_LANE_AHEAD = 0 / 1 forces the choice (tests)
-  bool ahead = !COOP && (long)a.n * T * 2 <= (long)e->sm_count * 32 * 16;
-  if (const char* s = std::getenv("BMCTS_LANE_AHEAD")) ahead = !COOP && std::atoi(s) != 0;
-  if constexpr (!COOP) {
-    if (ahead) {
-      switch (T) {
-        case 32: return launch_lane_T<32, false, true>(e, a, W, stream, counter);
-        case 16: return launch_lane_T<16, false, true>(e, a, W, stream, counter);
-        case 8: return launch_lane_T<8, false, true>(e, a, W, stream, counter);
-        case 4: return launch_lane_T<4, false, true>(e, a, W, stream, counter);
-        case 2: return launch_lane_T<2, false, true>(e, a, W, stream, counter);
-        default: return launch_lane_T<1, false, true>(e, a, W, stream, counter);
-      }
+  // the "ahead" variant when the batch leaves most of the GPU idle (latency bound: an MCTS wave;
+  // measured on c2 / c5: faster up to about a quarter of the lanes the GPU can hold, slower from
+  // half of them); the cooperative kernel's needs a lane per agent.  BMCTS_LANE_AHEAD = 0 / 1
+  // forces the choice (tests)
+  bool ahead = (long)a.n * T * 2 <= (long)e->sm_count * 32 * 16;
+  if (const char* s = std::getenv("BMCTS_LANE_AHEAD")) ahead = std::atoi(s) != 0;
+  if (COOP && a.A > T) ahead = false;
+  if (ahead) {
+    switch (T) {
+      case 32: return launch_lane_T<32, COOP, true>(e, a, W, stream, counter);
+      case 16: return launch_lane_T<16, COOP, true>(e, a, W, stream, counter);
+      case 8: return launch_lane_T<8, COOP, true>(e, a, W, stream, counter);
+      case 4: return launch_lane_T<4, COOP, true>(e, a, W, stream, counter);
+      case 2: return launch_lane_T<2, COOP, true>(e, a, W, stream, counter);
+      default: return launch_lane_T<1, COOP, true>(e, a, W, stream, counter);
     }
   }
   switch (T) {

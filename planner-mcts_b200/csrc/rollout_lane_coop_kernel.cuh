@@ -15,6 +15,14 @@
 // memory, [field][agent][column]: pose, cos/sin heading, arc length on every corridor, current
 // corridor, own flags, own reward, discounted return.  Every float operation mirrors
 // oracle/bmcts_oracle.c.
+//
+// "Macro actions ahead" variant (AHEAD = true; batches too small to fill the GPU, one lane per
+// agent): a macro action reads only the agent's own state and its action comes from the
+// counter-based generator, so -- as for the ego of the hypothesis kernel -- a second warp computes
+// EVERY agent's macro action one pass ahead of the warp that publishes, tests pairs and
+// evaluates, and hands the poses over through shared memory at one named barrier per pass.  An
+// agent the rollout warp removes from the map is simply not read any more.  Same arithmetic in
+// the same order: bit-identical results.
 #pragma once
 
 #include "rollout_lane_kernel.cuh"
@@ -23,6 +31,20 @@ namespace bmcts {
 
 enum { K_X = 0, K_Y, K_TH, K_V, K_CS, K_SN, K_CUR, K_FL, K_RW, K_RA, K_PROJ };  // K_PROJ + c = s
 
+struct CoopAcq {     // the rollout a column works on, posted by the rollout warp every pass
+  uint32_t seq;      // changes with every acquisition
+  uint32_t rid;
+  int depth;
+  uint32_t flags;    // bit 0: expansion step first, bit 1: there is something to do
+  uint32_t am;       // agents alive in the leaf state
+  uint32_t pad_[3];
+};
+struct CoopMail {    // double-buffered by pass parity, like EgoMail
+  uint32_t done[4];
+  CoopAcq acq[2][32];
+  float slot[2][32][8];  // [parity][column * T + agent]: x, y, th, v, cos, sin after the pass
+};
+
 __host__ __device__ inline LaneLayout lane_coop_layout(int A, int C, int T, int warps) {
   LaneLayout l = lane_layout(A, C, 0, T, warps);
   l.warp_bytes = sizeof(float) * (size_t)(K_PROJ + C) * A * (32 / T);
@@ -30,13 +52,13 @@ __host__ __device__ inline LaneLayout lane_coop_layout(int A, int C, int T, int 
   return l;
 }
 
-template <int T>
-__global__ void __launch_bounds__(BMCTS_LANE_MAX_THREADS, BMCTS_LANE_MIN_BLOCKS)
+template <int T, bool AHEAD>
+__global__ void __launch_bounds__(AHEAD ? 64 : BMCTS_LANE_MAX_THREADS, AHEAD ? 1 : BMCTS_LANE_MIN_BLOCKS)
 rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = 32 / T;
-  const int A = p.A, C = p.C;
-  const int warps = blockDim.x >> 5;
+  const int A = p.A, C = p.C;  // AHEAD: A <= T (engine.cu), one agent per lane
+  const int warps = AHEAD ? 1 : blockDim.x >> 5;
   const LaneLayout lay = lane_coop_layout(A, C, T, warps);
 
   // ---- stage scenario prefix, macro actions, config
@@ -67,6 +89,74 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int t = lane % T;
   const int g = lane / T;
+  CoopMail* mail = reinterpret_cast<CoopMail*>(smem_raw + smem_align16(lay.total));
+  if (AHEAD && warp == 1) {
+    // ------------------------------------------------------ the macro-action warp
+    // lane = column * T + agent
+    uint32_t seq = 0, rid = 0;
+    int n = 0, depth = 1;
+    bool expand = false, alive = false;
+    float x = 0.0f, y = 0.0f, th = 0.0f, v = 0.0f, cs = 1.0f, sn = 0.0f;
+    for (uint32_t it = 0;; ++it) {
+      ahead_barrier();  // acquisitions of this pass posted, slots of this pass complete
+      if (mail->done[it & 1u]) break;
+      if (t < A) {
+        const CoopAcq q = mail->acq[it & 1u][g];
+        if (q.seq != seq) {
+          seq = q.seq;
+          rid = q.rid;
+          depth = q.depth;
+          expand = (q.flags & 1u) != 0;
+          alive = (q.flags & 2u) != 0 && ((q.am >> t) & 1u) != 0;
+          n = 0;
+          const float4 q0 = start_pose(p, t, rid);
+          x = q0.x;
+          y = q0.y;
+          th = q0.z;
+          v = q0.w;
+          bm_sincos(th, &sn, &cs);
+        }
+        if (alive) {
+          // the corridor the publish phase finds for this pose (arg min |d|, first on ties, 0)
+          float best = kBig;
+          int cur = 0;
+#pragma unroll 1
+          for (int c = 0; c < C; ++c) {
+            const Proj pr = project(scn.corridors[c], x, y);
+            const float m = pr.in ? bm_abs(pr.d) : kBig;
+            const bool better = m < best;
+            best = better ? m : best;
+            cur = better ? c : cur;
+          }
+          const float Dt = p.dt_table
+                               ? p.dt_table[depth < BMCTS_MAX_DEPTH ? depth : BMCTS_MAX_DEPTH - 1]
+                               : cfg.prediction_k;
+          const size_t gi = (size_t)t * p.n + rid;
+          int action;
+          if (expand) {
+            action = p.action[gi];
+          } else {
+            uint4 rr = draw(p.key0, p.key1, p.first_rollout_id + (uint64_t)rid, (uint32_t)t,
+                            BMCTS_RNG_ROLLOUT_ACTION, (uint32_t)n);
+            action = (int)bm_bounded(rr.x, (uint32_t)scn.n_ego_actions);
+          }
+          const float acc = ego_macro_step(scn, acts, cfg, action, cur, Dt, x, y, th, v, sn, cs);
+          if (expand && p.last_action) p.last_action[gi] = acc;
+          if (expand) expand = false; else n++;
+          depth++;
+          float* s = mail->slot[(it + 1u) & 1u][lane];
+          s[0] = x;
+          s[1] = y;
+          s[2] = th;
+          s[3] = v;
+          s[4] = cs;
+          s[5] = sn;
+        }
+      }
+    }
+    return;
+  }
+  uint32_t pass = 0, acq_seq = 0;  // AHEAD: pass counter (slot parity), acquisitions made
   float* col = reinterpret_cast<float*>(smem_raw + lay.off_state + lay.warp_bytes * warp) + g;
   const int fstride = A * NC;
 #define FLD(f, a) col[(f) * fstride + (a) * NC]
@@ -117,11 +207,29 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
         R = C0 = L = 0.0f;
         f_any = f_last = 0;
         inc0 = inc1 = inc2 = inc3 = 0;
+        acq_seq++;
       }
     }
-    if (__all_sync(0xffffffffu, done)) {
-      retire_warp(p, counter, gridDim.x * (uint32_t)warps, lane);
-      break;
+    {
+      const bool all_done = __all_sync(0xffffffffu, done);
+      if (AHEAD) {
+        if (t == 0) {
+          CoopAcq q;
+          q.seq = acq_seq;
+          q.rid = rid;
+          q.depth = depth;
+          q.flags = (expand ? 1u : 0u) | (active ? 2u : 0u);
+          q.am = am;
+          q.pad_[0] = q.pad_[1] = q.pad_[2] = 0u;
+          mail->acq[pass & 1u][g] = q;
+        }
+        if (lane == 0) mail->done[pass & 1u] = all_done ? 1u : 0u;
+        ahead_barrier();  // the other warp sees the acquisitions; its slots for this pass are written
+      }
+      if (all_done) {
+        retire_warp(p, counter, gridDim.x * (uint32_t)warps, lane);
+        break;
+      }
     }
 
     const bool stepping = active && !fresh;
@@ -162,6 +270,16 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
             }
             continue;
           }
+          if (AHEAD) {  // computed one pass ago by the macro-action warp (which also wrote
+                        // last_action of an expansion step)
+            const float* sl = mail->slot[pass & 1u][lane];
+            x = sl[0];
+            y = sl[1];
+            th = sl[2];
+            v = sl[3];
+            cs = sl[4];
+            sn = sl[5];
+          } else {
           // BehaviorMPMacroActions primitive on the single-track model (spec item 5)
           int action;
           if (expand) {
@@ -214,10 +332,9 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
             bm_sincos(th, &sn, &cs);
           }
           la = acc;
-          if (expand) {
-            if (p.next_pose) p.next_pose[gi] = make_float4(x, y, th, v);
-            if (p.last_action) p.last_action[gi] = la;
+          if (expand && p.last_action) p.last_action[gi] = la;
           }
+          if (expand && p.next_pose) p.next_pose[gi] = make_float4(x, y, th, v);
           if (want_final) p.final_pose[gi] = make_float4(x, y, th, v);
           // World::RemoveInvalidAgents (spec item 6)
           if (!in_rects(rects, x, y) &&
@@ -482,6 +599,7 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
       }
     }
     fresh = false;
+    pass++;
   }
 #undef FLD
 #undef INC

@@ -24,7 +24,8 @@ def lanes_per_rollout(request, monkeypatch):
     """every test runs with the engine's own choice of kernel variant (for these small batches:
     the "ego ahead" variant, engine.cu launch_lane), with each forced number of lanes per
     rollout on the plain variant, and with the ego-ahead variant at 1 / 4 / 16 / 32 lanes
-    (BMCTS_LANE_T / BMCTS_LANE_AHEAD are read at every launch)"""
+    (BMCTS_LANE_T / BMCTS_LANE_AHEAD are read at every launch; the cooperative kernel's ahead
+    variant needs a lane per agent and is the plain one otherwise)"""
     if request.param == "auto":
         monkeypatch.delenv("BMCTS_LANE_T", raising=False)
         monkeypatch.delenv("BMCTS_LANE_AHEAD", raising=False)
