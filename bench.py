@@ -641,6 +641,15 @@ def run_ours(args):
                 others[name] = {"gpu_plan_ms": g_["plan_ms"], "cpu_plan_ms": c_["plan_ms"],
                                 "speedup": c_["plan_ms"] / g_["plan_ms"]}
             line["plan_default_budget"]["other_workloads"] = others
+            # longer rollout caps on c2 (the reference's default cap is 1000 steps): a wave lasts
+            # as long as its longest rollout, so this is where the wave-batched search gains least
+            caps = {}
+            for hz in (100, 1000):
+                g_ = plan_benchmark("c2_merge_sbg", hz, 2000, 0, "gpu", device=local_rank)
+                c_ = plan_benchmark("c2_merge_sbg", hz, 2000, 1, "cpu")
+                caps[str(hz)] = {"gpu_plan_ms": g_["plan_ms"], "cpu_plan_ms": c_["plan_ms"],
+                                 "speedup": c_["plan_ms"] / g_["plan_ms"]}
+            line["plan_default_budget"]["rollout_cap_steps"] = caps
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
