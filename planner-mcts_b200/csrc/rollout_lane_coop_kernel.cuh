@@ -280,59 +280,24 @@ rollout_lane_coop_kernel(const KernelArgs p, unsigned int* __restrict__ counter)
             cs = sl[4];
             sn = sl[5];
           } else {
-          // BehaviorMPMacroActions primitive on the single-track model (spec item 5)
-          int action;
-          if (expand) {
-            action = p.action[gi];
-          } else {
-            uint4 rr = draw(p.key0, p.key1, rollout_id, (uint32_t)a, BMCTS_RNG_ROLLOUT_ACTION,
-                            (uint32_t)n);
-            action = (int)bm_bounded(rr.x, (uint32_t)scn.n_ego_actions);
-          }
-          const bmcts_ego_action act = acts[action];
-          const float acc = bm_clamp(act.acceleration, cfg.lon_acc_min, cfg.lon_acc_max);
-          int tgt = __float_as_int(ca[K_CUR * fstride]);
-          if (act.type == BMCTS_ACT_CHANGE_LEFT && scn.corridors[tgt].left >= 0)
-            tgt = scn.corridors[tgt].left;
-          else if (act.type == BMCTS_ACT_CHANGE_RIGHT && scn.corridors[tgt].right >= 0)
-            tgt = scn.corridors[tgt].right;
-          const bmcts_corridor& corr = scn.corridors[tgt];
-          const float wb = cfg.wheel_base, kct = cfg.crosstrack_gain, dmax = cfg.delta_max;
-          const float vmax = cfg.ego_max_velocity;
-          const float inv_wb = bm_div(1.0f, wb);
-          const int nsub_e = ego_substeps(cfg, Dt);
-          const float dt_e = bm_div(Dt, (float)nsub_e);
-          const bool limit = cfg.limit_steering_rate != 0;
-          const float lat_lo = cfg.lat_acc_min, lat_hi = cfg.lat_acc_max;
-          x = ca[K_X * fstride];
-          y = ca[K_Y * fstride];
-          th = ca[K_TH * fstride];
-          v = ca[K_V * fstride];
-          cs = ca[K_CS * fstride];
-          sn = ca[K_SN * fstride];
-#pragma unroll 1
-          for (int q = 0; q < nsub_e; ++q) {
-            const float fx = bm_fma(wb, cs, x);
-            const float fy = bm_fma(wb, sn, y);
-            const Proj pr = project(corr, fx, fy);
-            const float th_err = bm_norm_angle(corr.angle[pr.seg] - th);
-            float delta = th_err + bm_atan2(-(kct * pr.d), v);
-            delta = bm_clamp(delta, -dmax, dmax);
-            float tn = bm_tan_small(delta);
-            if (limit) {  // lateral acceleration v^2 tan(delta) / L inside [LatAccMin, LatAccMax]
-              const float r = bm_div(wb, bm_max(v * v, 1.0e-6f));
-              tn = bm_clamp(tn, lat_lo * r, lat_hi * r);
+            // BehaviorMPMacroActions primitive on the single-track model (spec item 5)
+            int action;
+            if (expand) {
+              action = p.action[gi];
+            } else {
+              uint4 rr = draw(p.key0, p.key1, rollout_id, (uint32_t)a, BMCTS_RNG_ROLLOUT_ACTION,
+                              (uint32_t)n);
+              action = (int)bm_bounded(rr.x, (uint32_t)scn.n_ego_actions);
             }
-            const float dv = dt_e * v;
-            x = bm_fma(dv, cs, x);
-            y = bm_fma(dv, sn, y);
-            th = bm_fma(dv, tn * inv_wb, th);
-            v = bm_clamp(bm_fma(dt_e, acc, v), 0.0f, vmax);
-            if (q + 1 == nsub_e) th = bm_norm_angle(th);
-            bm_sincos(th, &sn, &cs);
-          }
-          la = acc;
-          if (expand && p.last_action) p.last_action[gi] = la;
+            x = ca[K_X * fstride];
+            y = ca[K_Y * fstride];
+            th = ca[K_TH * fstride];
+            v = ca[K_V * fstride];
+            cs = ca[K_CS * fstride];
+            sn = ca[K_SN * fstride];
+            la = ego_macro_step(scn, acts, cfg, action, __float_as_int(ca[K_CUR * fstride]), Dt, x,
+                                y, th, v, sn, cs);
+            if (expand && p.last_action) p.last_action[gi] = la;
           }
           if (expand && p.next_pose) p.next_pose[gi] = make_float4(x, y, th, v);
           if (want_final) p.final_pose[gi] = make_float4(x, y, th, v);
