@@ -438,6 +438,11 @@ int bmcts_last_kernel_ms(bmcts_engine* e, float* ms);
  * bmcts_last_kernel_ms (the planner's tree search: one launch per MCTS wave, many host threads
  * sharing the driver) switches them off.  bmcts_last_kernel_ms then fails with INVALID_ARG. */
 int bmcts_set_kernel_timing(bmcts_engine* e, int on);
+/* how the last rollout / step kernel was launched: lanes per rollout (1 ... 32), rollout warps
+ * per block, and whether it was the "ahead" variant the engine picks for batches too small to
+ * fill the GPU (0 / 1).  Zeros before the first launch.  Any pointer may be null. */
+int bmcts_last_launch_geometry(const bmcts_engine* e, int* lanes_per_rollout, int* warps_per_block,
+                               int* ahead);
 /* number of kernels this engine has launched since creation */
 uint64_t bmcts_launch_count(const bmcts_engine* e);
 /* the engine's CUDA stream as an opaque pointer (cudaStream_t) */

@@ -159,7 +159,7 @@ EXPORTED_SYMBOLS = [
     "bmcts_create", "bmcts_destroy", "bmcts_set_config", "bmcts_set_scenario",
     "bmcts_rollout_batch", "bmcts_step_batch", "bmcts_expand_rollout_batch",
     "bmcts_expand_rollout_batch_begin", "bmcts_expand_rollout_batch_end",
-    "bmcts_likelihood_batch", "bmcts_sync", "bmcts_last_kernel_ms", "bmcts_set_kernel_timing",
+    "bmcts_likelihood_batch", "bmcts_sync", "bmcts_last_kernel_ms", "bmcts_set_kernel_timing", "bmcts_last_launch_geometry",
     "bmcts_launch_count",
     "bmcts_stream", "bmcts_last_error", "bmcts_status_string", "bmcts_math_probe",
     "bmcts_comm_unique_id", "bmcts_comm_create", "bmcts_comm_destroy", "bmcts_comm_nranks",
@@ -219,6 +219,7 @@ def load_library(path=None):
     lib.bmcts_sync.argtypes = [C.c_void_p]
     lib.bmcts_last_kernel_ms.argtypes = [C.c_void_p, P(C.c_float)]
     lib.bmcts_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.bmcts_last_launch_geometry.argtypes = [C.c_void_p, P(C.c_int), P(C.c_int), P(C.c_int)]
     lib.bmcts_launch_count.argtypes = [C.c_void_p]
     lib.bmcts_launch_count.restype = C.c_uint64
     lib.bmcts_stream.argtypes = [C.c_void_p]

@@ -74,7 +74,8 @@ struct bmcts_engine {
   int max_smem_optin = 0;
   int sm_count = 0;
   unsigned int* d_counter = nullptr;  // work counter of the lane kernel
-  int lane_T = 0, lane_W = 0;          // last launch geometry (introspection / bench)
+  int lane_T = 0, lane_W = 0;          // last launch geometry (bmcts_last_launch_geometry)
+  bool lane_ahead = false;
   // copy / compute pipeline of large host-memory rollout batches: chunk i+1 is uploaded and
   // chunk i-1 downloaded while chunk i computes
   struct PipeSlot {
@@ -233,6 +234,7 @@ int launch_lane_T(bmcts_engine* e, const bmcts::KernelArgs& a, int force_W, cuda
   e->launches++;
   e->lane_T = T;
   e->lane_W = g.W;
+  e->lane_ahead = AHEAD;
   if (std::getenv("BMCTS_DEBUG"))
     std::fprintf(stderr,
                  "[bmcts] lane kernel coop=%d ahead=%d T=%d W=%d blocks/SM=%d grid=%ld smem=%zu n=%d\n",
@@ -1270,6 +1272,15 @@ int bmcts_last_kernel_ms(bmcts_engine* e, float* ms) {
   CU(cudaSetDevice(e->device));
   CU(cudaEventSynchronize(e->ev_stop));
   CU(cudaEventElapsedTime(ms, e->ev_start, e->ev_stop));
+  return BMCTS_OK;
+}
+
+int bmcts_last_launch_geometry(const bmcts_engine* e, int* lanes_per_rollout, int* warps_per_block,
+                               int* ahead) {
+  if (!e) return BMCTS_ERR_INVALID_ARG;
+  if (lanes_per_rollout) *lanes_per_rollout = e->lane_T;
+  if (warps_per_block) *warps_per_block = e->lane_W;
+  if (ahead) *ahead = e->lane_ahead ? 1 : 0;
   return BMCTS_OK;
 }
 

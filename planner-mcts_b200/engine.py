@@ -101,6 +101,12 @@ class RolloutEngine:
         """event records around every launch on / off (on by default; off: last_kernel_ms raises)"""
         self._check(self._lib.bmcts_set_kernel_timing(self._h, 1 if on else 0))
 
+    def last_launch_geometry(self):
+        """(lanes per rollout, rollout warps per block, ahead variant?) of the last kernel launch"""
+        t, w, a = C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.bmcts_last_launch_geometry(self._h, C.byref(t), C.byref(w), C.byref(a)))
+        return int(t.value), int(w.value), bool(a.value)
+
     def launch_count(self):
         return int(self._lib.bmcts_launch_count(self._h))
 

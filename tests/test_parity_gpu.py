@@ -394,3 +394,28 @@ def test_wave_paths_without_driver_calls_change_nothing(monkeypatch):
         monkeypatch.setenv("BMCTS_NO_DONE_FLAG", "1")
         g2 = eng.rollout(pose, alive, hyp, seed=3, stream=it)
         assert np.array_equal(g["result"], g2["result"])
+
+
+def test_engine_picks_the_latency_variant_for_small_batches(lanes_per_rollout, monkeypatch):
+    """batches too small to fill the GPU (MCTS waves) get a lane per agent and the "ahead" variant
+    of the kernel, full-size batches the throughput geometry (engine.cu launch_lane); forced
+    values are honoured"""
+    if lanes_per_rollout != "auto":
+        t, _, ahead = lanes_per_rollout.partition("+")
+        cfg, scn, meta = scenarios.workload("c2_merge_sbg", horizon=5)
+        eng = RolloutEngine(cfg, scn)
+        pose, alive, hyp = scenarios.leaves_for(scn, meta, 40, seed=2)
+        eng.rollout(pose, alive, hyp)
+        assert eng.last_launch_geometry()[0] == int(t)
+        assert eng.last_launch_geometry()[2] == bool(ahead)
+        return
+    for name, agents, t_small, t_big in (("c2_merge_sbg", 10, 16, 1), ("c5_rsbg", 32, 32, 4),
+                                         ("c4_coop", 20, 32, 4), ("c1_highway_mdp", 4, 4, 1)):
+        cfg, scn, meta = scenarios.workload(name, horizon=5)
+        eng = RolloutEngine(cfg, scn)
+        pose, alive, hyp = scenarios.leaves_for(scn, meta, 15, seed=2)
+        eng.rollout(pose, alive, hyp)
+        assert eng.last_launch_geometry()[0] == t_small and eng.last_launch_geometry()[2], name
+        pose, alive, hyp = scenarios.leaves_for(scn, meta, 1 << 16, seed=2)
+        eng.rollout(pose, alive, hyp)
+        assert eng.last_launch_geometry()[0] == t_big and not eng.last_launch_geometry()[2], name
