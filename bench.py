@@ -479,7 +479,7 @@ def run_ours(args):
                     (("c2_merge_sbg@reference_ego_dt_0.02", 0.02, args.horizon),
                      ("c2_merge_sbg@rollout_cap_1000", 0.05, 1000)) if name == "c2_merge_sbg" else ()):
                 cfg_w, scn_w, meta_w = scenarios.workload(name, horizon=hz, ego_dt=ego_dt)
-                n_t = n_w if hz <= 100 else n_w // 4
+                n_t = n_w
                 eng_w = RolloutEngine(cfg_w, scn_w, device=local_rank)
                 st_w = torch.cuda.ExternalStream(eng_w.stream_ptr(), device=dev)
                 arm_w = Arm(eng_w, scn_w, meta_w, n_t, args.share, 11 + rank, dev, rank)
